@@ -1,0 +1,400 @@
+// Non-causal, unmasked flash-attention forward for sm_100a (tcgen05 + TMEM + TMA), head_dim 128 / 64.
+//
+// Replaces F.scaled_dot_product_attention on the reference hot path:
+//   Wan self/cross attention   reference architecture/transformer_wan.py:108-110
+//   CogVideoX joint attention  reference architecture/attention_processor.py:2863
+//
+// Layout contract: Q/K/V/O are token-major, heads contiguous inside a row ([B, N, H*d] views with arbitrary
+// row / batch strides, e.g. the three column blocks of a fused QKV GEMM output). TMA gathers the per-head
+// [128 x d] tiles straight out of that layout, so no head-major transpose is ever materialised.
+//
+// CTA = 384 threads, one CTA per SM, 256 query rows per CTA (two 128-row tiles processed ping-pong):
+//   warps 0-3   softmax warpgroup for Q tile 0   (thread == query row, TMEM lane == row)
+//   warps 4-7   softmax warpgroup for Q tile 1
+//   warp  8     TMA producer (Q once, then K/V ring)
+//   warp  9     MMA issuer   (S_i = Q_i K_j^T  SS-MMA;  O_i += P_i V_j  TS-MMA with P read from TMEM)
+//   warps 10-11 idle (keeps the third warpgroup complete for setmaxnreg)
+// TMEM (512 columns): S0 [0,128) S1 [128,256) O0 [256,256+d) O1 [384,384+d); P_i (bf16) aliases S_i[0,64).
+// MMA issue order per KV tile j:  S0(j), PV1(j-1), S1(j), PV0(j)  -- so the tensor pipe works on one query
+// tile while the other tile's softmax runs on the MUFU/FMA pipes.
+// Online softmax keeps (m, l) in registers; the O rescale is lazy (only when the running max grows by more
+// than 2^8, decided per warp), so the common path never touches O between MMAs.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace fino {
+
+constexpr int ATT_BM = 128;        // query rows per tile (== TMEM lanes)
+constexpr int ATT_BN = 128;        // keys per KV tile
+constexpr int ATT_THREADS = 384;
+constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units
+
+struct AttnParams {
+  __nv_bfloat16* o;
+  int64_t o_row_stride, o_batch_stride;  // elements
+  int nq, nk;
+  int heads;
+  float scale_log2;  // softmax scale * log2(e)
+  int num_kv_tiles;
+};
+
+template <int HD>
+struct AttnCfg {
+  static constexpr int kHalves = HD / 64;                 // 64-column (128 B) swizzle panels per row
+  static constexpr int kPanelBytes = 128 * 128;           // 128 rows x 128 B
+  static constexpr int kTileBytes = kHalves * kPanelBytes;  // one [128 x HD] bf16 tile
+  static constexpr int kKVStages = (HD == 128) ? 2 : 4;
+  static constexpr int kQBytes = 2 * kTileBytes;
+  static constexpr int kSmemBytes = kQBytes + 2 * kKVStages * kTileBytes + 1024 + 256;
+};
+
+template <int HD>
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+  using Cfg = AttnCfg<HD>;
+  constexpr int KST = Cfg::kKVStages;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_smem = smem_base;
+  const uint32_t k_smem = q_smem + Cfg::kQBytes;
+  const uint32_t v_smem = k_smem + KST * Cfg::kTileBytes;
+  const uint32_t bars = v_smem + KST * Cfg::kTileBytes;
+  // barriers: q_full, k_full[KST], k_empty[KST], v_full[KST], v_empty[KST], s_full[2], p_full[2], o_done[2]
+  const uint32_t q_full = bars;
+  auto k_full = [&](int s) { return bars + 8u * (1 + s); };
+  auto k_empty = [&](int s) { return bars + 8u * (1 + KST + s); };
+  auto v_full = [&](int s) { return bars + 8u * (1 + 2 * KST + s); };
+  auto v_empty = [&](int s) { return bars + 8u * (1 + 3 * KST + s); };
+  auto s_full = [&](int i) { return bars + 8u * (1 + 4 * KST + i); };
+  auto p_full = [&](int i) { return bars + 8u * (3 + 4 * KST + i); };
+  auto o_done = [&](int i) { return bars + 8u * (5 + 4 * KST + i); };
+  const uint32_t tmem_ptr_smem = bars + 8u * (7 + 4 * KST);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int q0 = blockIdx.x * (2 * ATT_BM);
+  const int T = p.num_kv_tiles;
+
+  if (warp == 8 && lane == 0) {
+    prefetch_tmap(&tmap_q);
+    prefetch_tmap(&tmap_k);
+    prefetch_tmap(&tmap_v);
+  }
+  if (warp == 9 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KST; ++s) {
+      mbar_init(k_full(s), 1);
+      mbar_init(k_empty(s), 1);
+      mbar_init(v_full(s), 1);
+      mbar_init(v_empty(s), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(s_full(i), 1);
+      mbar_init(p_full(i), 128);
+      mbar_init(o_done(i), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 10) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp >= 8) {
+    setmaxnreg_dec<80>();
+    if (warp == 8) {
+      // ============================ TMA producer ============================
+      if (lane == 0) {
+        const int c_head = head * HD;
+        mbar_arrive_expect_tx(q_full, Cfg::kQBytes);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int hf = 0; hf < Cfg::kHalves; ++hf)
+            tma_load_3d(q_smem + i * Cfg::kTileBytes + hf * Cfg::kPanelBytes, &tmap_q, q_full, c_head + hf * 64,
+                        q0 + i * ATT_BM, batch);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int j = 0; j < T; ++j) {
+          mbar_wait(k_empty(stage), phase ^ 1u, 10 + stage);
+          mbar_arrive_expect_tx(k_full(stage), Cfg::kTileBytes);
+#pragma unroll
+          for (int hf = 0; hf < Cfg::kHalves; ++hf)
+            tma_load_3d(k_smem + stage * Cfg::kTileBytes + hf * Cfg::kPanelBytes, &tmap_k, k_full(stage),
+                        c_head + hf * 64, j * ATT_BN, batch);
+          mbar_wait(v_empty(stage), phase ^ 1u, 20 + stage);
+          mbar_arrive_expect_tx(v_full(stage), Cfg::kTileBytes);
+#pragma unroll
+          for (int hf = 0; hf < Cfg::kHalves; ++hf)
+            tma_load_3d(v_smem + stage * Cfg::kTileBytes + hf * Cfg::kPanelBytes, &tmap_v, v_full(stage),
+                        c_head + hf * 64, j * ATT_BN, batch);
+          if (++stage == KST) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    } else if (warp == 9) {
+      // ============================ MMA issuer ============================
+      if (lane == 0) {
+        constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, 0);  // Q K^T : both K-major
+        constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BM, HD, 1);      // P V   : V is MN-major (d contiguous)
+        const uint32_t tmem_s[2] = {tmem_base + 0u, tmem_base + 128u};
+        const uint32_t tmem_o[2] = {tmem_base + 256u, tmem_base + 384u};
+
+        auto issue_s = [&](int i, int kstage) {
+          const uint32_t qa = q_smem + i * Cfg::kTileBytes;
+          const uint32_t ka = k_smem + kstage * Cfg::kTileBytes;
+#pragma unroll
+          for (int ks = 0; ks < HD / 16; ++ks) {
+            const uint32_t off = (ks >> 2) * Cfg::kPanelBytes + (ks & 3) * 32;
+            umma_ss(tmem_s[i], make_sdesc_sw128(qa + off, 16, 1024), make_sdesc_sw128(ka + off, 16, 1024), idesc_s,
+                    ks != 0 ? 1u : 0u);
+          }
+        };
+        auto issue_pv = [&](int i, int vstage, bool accumulate) {
+          const uint32_t va = v_smem + vstage * Cfg::kTileBytes;
+#pragma unroll
+          for (int ks = 0; ks < ATT_BN / 16; ++ks) {
+            // 16 keys per MMA: advance 16 rows (2048 B) in the V panel; LBO = panel stride (d 64..127), SBO = 8 rows
+            umma_ts(tmem_o[i], tmem_s[i] + ks * 8, make_sdesc_sw128(va + ks * 2048, Cfg::kPanelBytes, 1024), idesc_o,
+                    (accumulate || ks != 0) ? 1u : 0u);
+          }
+        };
+
+        mbar_wait(q_full, 0, 30);
+        tc_fence_after();
+        int stage = 0;        // K / V stage of tile j
+        uint32_t phase = 0;
+        int pstage = 0;       // V stage of tile j-1
+        for (int j = 0; j < T; ++j) {
+          mbar_wait(k_full(stage), phase, 40 + stage);
+          tc_fence_after();
+          issue_s(0, stage);
+          tc_commit(s_full(0));
+          if (j > 0) {
+            mbar_wait(p_full(1), (uint32_t)((j - 1) & 1), 51);
+            tc_fence_after();
+            issue_pv(1, pstage, j - 1 > 0);
+            tc_commit(v_empty(pstage));
+          }
+          issue_s(1, stage);
+          tc_commit(s_full(1));
+          tc_commit(k_empty(stage));
+          mbar_wait(v_full(stage), phase, 60 + stage);
+          mbar_wait(p_full(0), (uint32_t)(j & 1), 50);
+          tc_fence_after();
+          issue_pv(0, stage, j > 0);
+          pstage = stage;
+          if (++stage == KST) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tc_commit(o_done(0));
+        mbar_wait(p_full(1), (uint32_t)((T - 1) & 1), 52);
+        tc_fence_after();
+        issue_pv(1, pstage, T - 1 > 0);
+        tc_commit(v_empty(pstage));
+        tc_commit(o_done(1));
+      }
+    }
+  } else {
+    // ============================ softmax warpgroups ============================
+    setmaxnreg_inc<208>();
+    const int wg = warp >> 2;   // query tile handled by this warpgroup
+    const int quad = warp & 3;  // TMEM lane quadrant
+    const int row_in_tile = quad * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_base + (wg ? 128u : 0u);
+    const uint32_t t_o = tmem_base + lane_base + (wg ? 384u : 256u);
+    const float sl2 = p.scale_log2;
+
+    float m_used = -INFINITY;  // running max (raw score units) the exponentials are referenced to
+    float l_sum = 0.f;
+
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(s_full(wg), (uint32_t)(j & 1), 70 + wg);
+      tc_fence_after();
+      uint32_t s[4][32];
+      tmem_ld_32x32b_x32(t_s + 0, s[0]);
+      tmem_ld_32x32b_x32(t_s + 32, s[1]);
+      tmem_ld_32x32b_x32(t_s + 64, s[2]);
+      tmem_ld_32x32b_x32(t_s + 96, s[3]);
+      tmem_wait_ld();
+
+      const int valid = p.nk - j * ATT_BN;  // keys of this tile that exist (>= 1)
+      if (valid < ATT_BN) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (c * 32 + e >= valid) s[c][e] = 0xff800000u;  // -inf
+      }
+
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          mx0 = fmaxf(mx0, __uint_as_float(s[c][e + 0]));
+          mx1 = fmaxf(mx1, __uint_as_float(s[c][e + 1]));
+          mx2 = fmaxf(mx2, __uint_as_float(s[c][e + 2]));
+          mx3 = fmaxf(mx3, __uint_as_float(s[c][e + 3]));
+        }
+      const float tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      const float m_cand = fmaxf(m_used, tile_max);
+
+      if (j == 0) {
+        m_used = m_cand;
+      } else {
+        const bool need = (m_cand - m_used) * sl2 > ATT_RESCALE_THRESHOLD;
+        if (__any_sync(0xffffffffu, need)) {
+          // PV_i(j-1) retired before S_i(j) was committed, so O_i is quiescent here.
+          const float alpha = need ? ex2_approx((m_used - m_cand) * sl2) : 1.0f;
+          if (need) m_used = m_cand;
+          l_sum *= alpha;
+#pragma unroll
+          for (int c = 0; c < HD / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(t_o + c * 32, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            tmem_st_32x32b_x32(t_o + c * 32, o);
+          }
+        }
+      }
+
+      const float neg_m = -m_used * sl2;
+      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int c2 = 0; c2 < 2; ++c2) {
+          const int c = half * 2 + c2;
+#pragma unroll
+          for (int e = 0; e < 32; e += 4) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(s[c][e + 0]), sl2, neg_m));
+            float p1 = ex2_approx(fmaf(__uint_as_float(s[c][e + 1]), sl2, neg_m));
+            float p2 = ex2_approx(fmaf(__uint_as_float(s[c][e + 2]), sl2, neg_m));
+            float p3 = ex2_approx(fmaf(__uint_as_float(s[c][e + 3]), sl2, neg_m));
+            sum0 += p0;
+            sum1 += p1;
+            sum2 += p2;
+            sum3 += p3;
+            pk[c2 * 16 + e / 2 + 0] = pack_bf16x2(p0, p1);
+            pk[c2 * 16 + e / 2 + 1] = pack_bf16x2(p2, p3);
+          }
+        }
+        // P (bf16, 2 keys per 32-bit column) aliases S_i columns [0,64)
+        tmem_st_32x32b_x32(t_s + half * 32, pk);
+      }
+      l_sum += (sum0 + sum1) + (sum2 + sum3);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(p_full(wg));
+    }
+
+    // ---------------- epilogue: O / l -> bf16 -> global ----------------
+    mbar_wait(o_done(wg), 0, 80 + wg);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_sum;
+    const int qrow = q0 + wg * ATT_BM + row_in_tile;
+    __nv_bfloat16* orow =
+        p.o + (int64_t)batch * p.o_batch_stride + (int64_t)qrow * p.o_row_stride + (int64_t)head * HD;
+#pragma unroll
+    for (int c = 0; c < HD / 32; ++c) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(t_o + c * 32, o);
+      tmem_wait_ld();
+      if (qrow < p.nq) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[8 * e + 0]) * inv_l, __uint_as_float(o[8 * e + 1]) * inv_l);
+          w.y = pack_bf16x2(__uint_as_float(o[8 * e + 2]) * inv_l, __uint_as_float(o[8 * e + 3]) * inv_l);
+          w.z = pack_bf16x2(__uint_as_float(o[8 * e + 4]) * inv_l, __uint_as_float(o[8 * e + 5]) * inv_l);
+          w.w = pack_bf16x2(__uint_as_float(o[8 * e + 6]) * inv_l, __uint_as_float(o[8 * e + 7]) * inv_l);
+          reinterpret_cast<uint4*>(orow + c * 32)[e] = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int HD>
+static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                       int batch, cudaStream_t stream) {
+  using Cfg = AttnCfg<HD>;
+  static bool configured = false;
+  if (!configured) {
+    FINO_CHECK_CUDA(
+        cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  dim3 grid((p.nq + 2 * ATT_BM - 1) / (2 * ATT_BM), p.heads, batch);
+  attn_fwd_kernel<HD><<<grid, ATT_THREADS, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
+  FINO_CHECK_CUDA(cudaGetLastError());
+  return FINO_OK;
+}
+
+int attention_fwd(const void* q, const void* k, const void* v, void* o, int batch, int heads, int64_t nq, int64_t nk,
+                  int head_dim, int64_t q_row_stride, int64_t k_row_stride, int64_t v_row_stride, int64_t o_row_stride,
+                  int64_t q_batch_stride, int64_t k_batch_stride, int64_t v_batch_stride, int64_t o_batch_stride,
+                  float scale, cudaStream_t stream) {
+  FINO_CHECK_ARG(q && k && v && o, "attention: null pointer");
+  FINO_CHECK_ARG(head_dim == 128 || head_dim == 64, "attention: head_dim %d unsupported (64 or 128)", head_dim);
+  FINO_CHECK_ARG(batch > 0 && heads > 0 && nq > 0 && nk > 0, "attention: non-positive shape");
+  FINO_CHECK_ARG(batch <= 65535 && heads <= 65535, "attention: batch/heads exceed grid limits");
+  FINO_CHECK_ARG(q_row_stride % 8 == 0 && k_row_stride % 8 == 0 && v_row_stride % 8 == 0 && o_row_stride % 8 == 0,
+                 "attention: row strides must be multiples of 8 elements");
+  FINO_CHECK_ARG(q_batch_stride % 8 == 0 && k_batch_stride % 8 == 0 && v_batch_stride % 8 == 0 &&
+                     o_batch_stride % 8 == 0,
+                 "attention: batch strides must be multiples of 8 elements");
+  FINO_CHECK_ARG((reinterpret_cast<uintptr_t>(o) & 15) == 0, "attention: output pointer must be 16-byte aligned");
+
+  CUtensorMap tq, tk, tv;
+  const uint64_t inner = (uint64_t)heads * head_dim;
+  auto enc = [&](CUtensorMap* tm, const void* base, int64_t n, int64_t rs, int64_t bs) {
+    uint64_t dims[3] = {inner, (uint64_t)n, (uint64_t)batch};
+    // a batch stride of 0 is not encodable; with batch == 1 any legal value works
+    uint64_t strides[2] = {(uint64_t)rs * 2, (uint64_t)(batch > 1 ? bs : rs * n) * 2};
+    uint32_t box[3] = {64, 128, 1};
+    return encode_tmap_bf16(tm, base, 3, dims, strides, box);
+  };
+  int r;
+  if ((r = enc(&tq, q, nq, q_row_stride, q_batch_stride))) return r;
+  if ((r = enc(&tk, k, nk, k_row_stride, k_batch_stride))) return r;
+  if ((r = enc(&tv, v, nk, v_row_stride, v_batch_stride))) return r;
+
+  AttnParams p;
+  p.o = reinterpret_cast<__nv_bfloat16*>(o);
+  p.o_row_stride = o_row_stride;
+  p.o_batch_stride = o_batch_stride;
+  p.nq = (int)nq;
+  p.nk = (int)nk;
+  p.heads = heads;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  p.num_kv_tiles = (int)((nk + ATT_BN - 1) / ATT_BN);
+  if (head_dim == 128) return launch_attn<128>(tq, tk, tv, p, batch, stream);
+  return launch_attn<64>(tq, tk, tv, p, batch, stream);
+}
+
+}  // namespace fino

@@ -1,0 +1,153 @@
+// extern "C" surface declared in include/frameino_b200.h. Plain pointers and sizes only.
+#include "../../include/frameino_b200.h"
+#include "common.cuh"
+#include <atomic>
+
+namespace fino {
+int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* c, int64_t ldc,
+              int64_t m, int n, int k, int epilogue, int out_fp32, int flags, const void* residual, int64_t ldr,
+              const float* gate, int64_t gate_row_stride, const int32_t* row_index, int64_t rows_per_group,
+              cudaStream_t stream);
+int attention_fwd(const void* q, const void* k, const void* v, void* o, int batch, int heads, int64_t nq, int64_t nk,
+                  int head_dim, int64_t q_row_stride, int64_t k_row_stride, int64_t v_row_stride, int64_t o_row_stride,
+                  int64_t q_batch_stride, int64_t k_batch_stride, int64_t v_batch_stride, int64_t o_batch_stride,
+                  float scale, cudaStream_t stream);
+int ln_modulate(const void* x, void* out, int64_t rows, int dim, int64_t x_stride, int64_t out_stride, float eps,
+                const float* gamma, const float* beta, const float* shift, const float* scale, int64_t mod_row_stride,
+                const int32_t* row_index, int64_t rows_per_group, int flags, cudaStream_t stream);
+int gate_residual(const void* x, const void* y, void* out, int64_t rows, int dim, int64_t x_stride, int64_t y_stride,
+                  int64_t out_stride, const float* gate, int64_t mod_row_stride, const int32_t* row_index,
+                  int64_t rows_per_group, int round_product, cudaStream_t stream);
+int qk_norm_rope(void* x0, int64_t rows0, int64_t stride0, const void* w0, const void* b0, int rope0, void* x1,
+                 int64_t rows1, int64_t stride1, const void* w1, const void* b1, int rope1, int heads, int head_dim,
+                 int norm_mode, float eps, int rope_mode, const float* cos, const float* sin, int64_t seq_len,
+                 int64_t rope_skip, cudaStream_t stream);
+int patchify(const void* x, void* rows, int B, int C, int F, int H, int W, int pt, int ph, int pw, int64_t sb,
+             int64_t sc, int64_t sf, int64_t sh, int64_t sw, int64_t ld, cudaStream_t stream);
+int unpatchify(const void* rows, void* out, int B, int C, int F, int H, int W, int pt, int ph, int pw, int64_t sb,
+               int64_t sc, int64_t sf, int64_t sh, int64_t sw, int64_t ld, int channel_last, cudaStream_t stream);
+int timestep_embedding(const float* t, float* out, int n, int dim, int flip_sin_to_cos, float downscale_freq_shift,
+                       float scale, float max_period, cudaStream_t stream);
+int linear_small_m(const float* x, const void* w, const void* b, float* y, int m, int n, int k, int w_is_bf16,
+                   int act_in, int act_out, int round_in, int round_out, cudaStream_t stream);
+int build_mod_table(const float* table, const float* proj, float* out, int layers, int r, int cols,
+                    int64_t table_layer_stride, cudaStream_t stream);
+}  // namespace fino
+
+static std::atomic<int64_t> g_launches{0};
+static int g_device = -1;
+
+// Every compute entry point: make sure a usable device is bound, then run and count the launch.
+static int ensure_device() {
+  if (g_device >= 0) {
+    cudaError_t e = cudaSetDevice(g_device);
+    if (e != cudaSuccess) {
+      fino::set_last_error("cudaSetDevice(%d) failed: %s", g_device, cudaGetErrorString(e));
+      return fino::FINO_ERR_CUDA;
+    }
+    return 0;
+  }
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    fino::set_last_error("no CUDA device available (%s); frameino_b200 has no CPU fallback",
+                         e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return fino::FINO_ERR_CUDA;
+  }
+  return 0;
+}
+
+#define FINO_ENTRY(call)            \
+  do {                              \
+    int _d = ensure_device();       \
+    if (_d) return _d;              \
+    int _r = (call);                \
+    if (_r == 0) g_launches.fetch_add(1, std::memory_order_relaxed); \
+    return _r;                      \
+  } while (0)
+
+extern "C" {
+
+int fino_abi_version(void) { return FINO_ABI_VERSION; }
+const char* fino_last_error(void) { return fino::get_last_error(); }
+int64_t fino_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int fino_set_device(int device) {
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    fino::set_last_error("cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(e));
+    return fino::FINO_ERR_CUDA;
+  }
+  g_device = device;
+  return 0;
+}
+
+int fino_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* c, int64_t ldc,
+                   int64_t m, int n, int k, int epilogue, int out_fp32, int flags, const void* residual, int64_t ldr,
+                   const float* gate, int64_t gate_row_stride, const int32_t* row_index, int64_t rows_per_group,
+                   void* stream) {
+  FINO_ENTRY(fino::gemm_bf16(a, lda, w, ldw, bias, c, ldc, m, n, k, epilogue, out_fp32, flags, residual, ldr, gate,
+                             gate_row_stride, row_index, rows_per_group, (cudaStream_t)stream));
+}
+
+int fino_attention_fwd(const void* q, const void* k, const void* v, void* o, int batch, int heads, int64_t nq,
+                       int64_t nk, int head_dim, int64_t q_row_stride, int64_t k_row_stride, int64_t v_row_stride,
+                       int64_t o_row_stride, int64_t q_batch_stride, int64_t k_batch_stride, int64_t v_batch_stride,
+                       int64_t o_batch_stride, float scale, void* stream) {
+  FINO_ENTRY(fino::attention_fwd(q, k, v, o, batch, heads, nq, nk, head_dim, q_row_stride, k_row_stride, v_row_stride,
+                                 o_row_stride, q_batch_stride, k_batch_stride, v_batch_stride, o_batch_stride, scale,
+                                 (cudaStream_t)stream));
+}
+
+int fino_ln_modulate(const void* x, void* out, int64_t rows, int dim, int64_t x_stride, int64_t out_stride, float eps,
+                     const float* gamma, const float* beta, const float* shift, const float* scale,
+                     int64_t mod_row_stride, const int32_t* row_index, int64_t rows_per_group, int flags,
+                     void* stream) {
+  FINO_ENTRY(fino::ln_modulate(x, out, rows, dim, x_stride, out_stride, eps, gamma, beta, shift, scale, mod_row_stride,
+                               row_index, rows_per_group, flags, (cudaStream_t)stream));
+}
+
+int fino_gate_residual(const void* x, const void* y, void* out, int64_t rows, int dim, int64_t x_stride,
+                       int64_t y_stride, int64_t out_stride, const float* gate, int64_t mod_row_stride,
+                       const int32_t* row_index, int64_t rows_per_group, int round_product, void* stream) {
+  FINO_ENTRY(fino::gate_residual(x, y, out, rows, dim, x_stride, y_stride, out_stride, gate, mod_row_stride, row_index,
+                                 rows_per_group, round_product, (cudaStream_t)stream));
+}
+
+int fino_qk_norm_rope(void* x0, int64_t rows0, int64_t stride0, const void* w0, const void* b0, int rope0, void* x1,
+                      int64_t rows1, int64_t stride1, const void* w1, const void* b1, int rope1, int heads,
+                      int head_dim, int norm_mode, float eps, int rope_mode, const float* cos, const float* sin,
+                      int64_t seq_len, int64_t rope_skip, void* stream) {
+  FINO_ENTRY(fino::qk_norm_rope(x0, rows0, stride0, w0, b0, rope0, x1, rows1, stride1, w1, b1, rope1, heads, head_dim,
+                                norm_mode, eps, rope_mode, cos, sin, seq_len, rope_skip, (cudaStream_t)stream));
+}
+
+int fino_patchify(const void* x, void* rows, int b, int c, int f, int h, int w, int pt, int ph, int pw, int64_t sb,
+                  int64_t sc, int64_t sf, int64_t sh, int64_t sw, int64_t ld, void* stream) {
+  FINO_ENTRY(fino::patchify(x, rows, b, c, f, h, w, pt, ph, pw, sb, sc, sf, sh, sw, ld, (cudaStream_t)stream));
+}
+
+int fino_unpatchify(const void* rows, void* out, int b, int c, int f, int h, int w, int pt, int ph, int pw, int64_t sb,
+                    int64_t sc, int64_t sf, int64_t sh, int64_t sw, int64_t ld, int channel_last, void* stream) {
+  FINO_ENTRY(fino::unpatchify(rows, out, b, c, f, h, w, pt, ph, pw, sb, sc, sf, sh, sw, ld, channel_last,
+                              (cudaStream_t)stream));
+}
+
+int fino_timestep_embedding(const float* t, float* out, int n, int dim, int flip_sin_to_cos,
+                            float downscale_freq_shift, float scale, float max_period, void* stream) {
+  FINO_ENTRY(fino::timestep_embedding(t, out, n, dim, flip_sin_to_cos, downscale_freq_shift, scale, max_period,
+                                      (cudaStream_t)stream));
+}
+
+int fino_linear_small_m(const float* x, const void* w, const void* b, float* y, int m, int n, int k, int w_is_bf16,
+                        int act_in, int act_out, int round_in, int round_out, void* stream) {
+  FINO_ENTRY(fino::linear_small_m(x, w, b, y, m, n, k, w_is_bf16, act_in, act_out, round_in, round_out,
+                                  (cudaStream_t)stream));
+}
+
+int fino_build_mod_table(const float* table, const float* proj, float* out, int layers, int r, int cols,
+                         int64_t table_layer_stride, void* stream) {
+  FINO_ENTRY(fino::build_mod_table(table, proj, out, layers, r, cols, table_layer_stride, (cudaStream_t)stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,425 @@
+// HBM-bound row kernels of the denoise step: one warp owns one token row, the row lives in registers,
+// reductions are warp shuffles, every global access is a 128-bit vector.
+//
+//   ln_modulate      FP32LayerNorm (+affine) + AdaLN modulate   reference transformer_wan.py:334,339,344-346,536
+//                    CogVideoXLayerNormZero / AdaLayerNorm body  reference cogvideox_transformer_3d.py:134,150,541
+//   gate_residual    x + y*gate                                  reference transformer_wan.py:336,341,348
+//   qk_norm_rope     RMSNorm across heads + 3-D RoPE (Wan)       reference transformer_wan.py:64-90
+//                    per-head LayerNorm + RoPE on video tokens   reference attention_processor.py:2848-2860
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace fino {
+
+constexpr int ROW_WARPS = 8;  // rows per CTA
+
+enum LnFlags : int {
+  LN_FLAG_BF16_STEPS = 1,  // round after LN, after (1+scale), after the product and after the add (bf16 module flow)
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  f[0] = bf16_lo_to_f32(u.x);
+  f[1] = bf16_hi_to_f32(u.x);
+  f[2] = bf16_lo_to_f32(u.y);
+  f[3] = bf16_hi_to_f32(u.y);
+  f[4] = bf16_lo_to_f32(u.z);
+  f[5] = bf16_hi_to_f32(u.z);
+  f[6] = bf16_lo_to_f32(u.w);
+  f[7] = bf16_hi_to_f32(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]);
+  u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]);
+  u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void ld8f(const float* p, float* f) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm (+affine) (+modulate)
+// ------------------------------------------------------------------------------------------------
+template <int CPL>  // 16-byte chunks per lane
+__global__ void __launch_bounds__(ROW_WARPS * 32)
+ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t rows, int dim,
+                   int64_t x_stride, int64_t out_stride, float eps, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, const float* __restrict__ shift, const float* __restrict__ scale,
+                   int64_t mod_row_stride, const int32_t* __restrict__ row_index, int64_t rows_per_group, int flags) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nchunks = dim >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * x_stride);
+  float v[CPL][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nchunks) {
+      uint4 u = ld_stream(xr + c);
+      unpack8(u, v[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sum += v[i][e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[i][e] = 0.f;
+    }
+  }
+  const float mean = warp_sum(sum) / (float)dim;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nchunks) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float d = v[i][e] - mean;
+        sq += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)dim + eps);
+
+  const float* sh = nullptr;
+  const float* sc = nullptr;
+  if (shift != nullptr) {
+    const int64_t g = row_index ? (int64_t)row_index[row] : row / rows_per_group;
+    sh = shift + g * mod_row_stride;
+    sc = scale + g * mod_row_stride;
+  }
+  const bool steps = (flags & LN_FLAG_BF16_STEPS) != 0;
+  uint4* orow = reinterpret_cast<uint4*>(out + row * out_stride);
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nchunks) {
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = (v[i][e] - mean) * rstd;
+      if (gamma != nullptr) {
+        float g[8], b[8];
+        ld8f(gamma + c * 8, g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] *= g[e];
+        if (beta != nullptr) {
+          ld8f(beta + c * 8, b);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) y[e] += b[e];
+        }
+      }
+      if (sh != nullptr) {
+        float s8[8], h8[8];
+        ld8f(sc + c * 8, s8);
+        ld8f(sh + c * 8, h8);
+        if (steps) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) y[e] = rbf(rbf(y[e]) * rbf(1.0f + s8[e])) + h8[e];
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) y[e] = y[e] * (1.0f + s8[e]) + h8[e];
+        }
+      }
+      orow[c] = pack8(y);
+    }
+  }
+}
+
+int ln_modulate(const void* x, void* out, int64_t rows, int dim, int64_t x_stride, int64_t out_stride, float eps,
+                const float* gamma, const float* beta, const float* shift, const float* scale, int64_t mod_row_stride,
+                const int32_t* row_index, int64_t rows_per_group, int flags, cudaStream_t stream) {
+  FINO_CHECK_ARG(x && out, "ln_modulate: null pointer");
+  FINO_CHECK_ARG(rows > 0 && dim > 0 && dim % 8 == 0, "ln_modulate: dim %d must be a positive multiple of 8", dim);
+  FINO_CHECK_ARG(x_stride % 8 == 0 && out_stride % 8 == 0, "ln_modulate: row strides must be multiples of 8");
+  FINO_CHECK_ARG((shift == nullptr) == (scale == nullptr), "ln_modulate: shift and scale go together");
+  FINO_CHECK_ARG(shift == nullptr || mod_row_stride % 4 == 0, "ln_modulate: modulation row stride must be 16B aligned");
+  FINO_CHECK_ARG(shift == nullptr || row_index != nullptr || rows_per_group > 0,
+                 "ln_modulate: need row_index or rows_per_group");
+  FINO_CHECK_ARG(dim <= 32 * 8 * 32, "ln_modulate: dim %d too large (max 8192)", dim);
+  const int cpl = (dim / 8 + 31) / 32;
+  dim3 grid((unsigned)((rows + ROW_WARPS - 1) / ROW_WARPS));
+  if (rows_per_group <= 0) rows_per_group = (int64_t)1 << 62;
+#define LAUNCH_LN(C)                                                                                                 \
+  ln_modulate_kernel<C><<<grid, ROW_WARPS * 32, 0, stream>>>(                                                        \
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)out, rows, dim, x_stride, out_stride, eps, gamma, beta, shift, scale, \
+      mod_row_stride, row_index, rows_per_group, flags)
+  if (cpl <= 1) LAUNCH_LN(1);
+  else if (cpl <= 2) LAUNCH_LN(2);
+  else if (cpl <= 4) LAUNCH_LN(4);
+  else if (cpl <= 8) LAUNCH_LN(8);
+  else if (cpl <= 12) LAUNCH_LN(12);
+  else if (cpl <= 16) LAUNCH_LN(16);
+  else LAUNCH_LN(32);
+#undef LAUNCH_LN
+  FINO_CHECK_CUDA(cudaGetLastError());
+  return FINO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// out = x + y * gate   (gate fp32 per modulation row, optional)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gate_residual_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
+                     __nv_bfloat16* __restrict__ out, int64_t rows, int dim, int64_t x_stride, int64_t y_stride,
+                     int64_t out_stride, const float* __restrict__ gate, int64_t mod_row_stride,
+                     const int32_t* __restrict__ row_index, int64_t rows_per_group, int round_product) {
+  const int nchunks = dim >> 3;
+  const int64_t total = rows * nchunks;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = idx / nchunks;
+    const int c = (int)(idx - row * nchunks);
+    float xv[8], yv[8];
+    unpack8(ld_stream(reinterpret_cast<const uint4*>(x + row * x_stride) + c), xv);
+    unpack8(ld_stream(reinterpret_cast<const uint4*>(y + row * y_stride) + c), yv);
+    if (gate != nullptr) {
+      const int64_t g = row_index ? (int64_t)row_index[row] : row / rows_per_group;
+      float gv[8];
+      ld8f(gate + g * mod_row_stride + c * 8, gv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) yv[e] *= gv[e];
+      if (round_product) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) yv[e] = rbf(yv[e]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) xv[e] += yv[e];
+    reinterpret_cast<uint4*>(out + row * out_stride)[c] = pack8(xv);
+  }
+}
+
+int gate_residual(const void* x, const void* y, void* out, int64_t rows, int dim, int64_t x_stride, int64_t y_stride,
+                  int64_t out_stride, const float* gate, int64_t mod_row_stride, const int32_t* row_index,
+                  int64_t rows_per_group, int round_product, cudaStream_t stream) {
+  FINO_CHECK_ARG(x && y && out, "gate_residual: null pointer");
+  FINO_CHECK_ARG(rows > 0 && dim > 0 && dim % 8 == 0, "gate_residual: dim must be a positive multiple of 8");
+  FINO_CHECK_ARG(x_stride % 8 == 0 && y_stride % 8 == 0 && out_stride % 8 == 0, "gate_residual: strides % 8");
+  FINO_CHECK_ARG(gate == nullptr || row_index != nullptr || rows_per_group > 0,
+                 "gate_residual: need row_index or rows_per_group");
+  if (rows_per_group <= 0) rows_per_group = (int64_t)1 << 62;
+  const int64_t total = rows * (dim / 8);
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  gate_residual_kernel<<<(unsigned)blocks, 256, 0, stream>>>(
+      (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (__nv_bfloat16*)out, rows, dim, x_stride, y_stride, out_stride,
+      gate, mod_row_stride, row_index, rows_per_group, round_product);
+  FINO_CHECK_CUDA(cudaGetLastError());
+  return FINO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// q/k normalisation + rotary embedding, in place
+// ------------------------------------------------------------------------------------------------
+enum QkNormMode : int { QK_RMS_ACROSS_HEADS = 0, QK_LAYERNORM_PER_HEAD = 1 };
+enum RopeMode : int { ROPE_NONE = 0, ROPE_WAN = 1, ROPE_COGVIDEOX = 2 };
+
+struct QkTensor {
+  __nv_bfloat16* ptr;
+  int64_t rows;
+  int64_t row_stride;
+  const __nv_bfloat16* weight;
+  const __nv_bfloat16* bias;
+  int rope;  // apply rope to this tensor
+};
+
+struct QkParams {
+  QkTensor t[2];
+  int heads, head_dim;
+  int norm_mode;
+  float eps;
+  int rope_mode;
+  const float* cos;  // [rope_rows, head_dim] fp32 (full width, as produced by the reference rope modules)
+  const float* sin;
+  int64_t seq_len;    // rows per batch element
+  int64_t rope_skip;  // rows [0, rope_skip) of every sequence are not rotated (CogVideoX text tokens)
+  int64_t blocks0;    // CTAs assigned to tensor 0
+};
+
+template <int CPL>
+__global__ void __launch_bounds__(ROW_WARPS * 32) qk_norm_rope_kernel(const QkParams p) {
+  const int lane = threadIdx.x & 31;
+  const int which = (int64_t)blockIdx.x >= p.blocks0 ? 1 : 0;
+  const QkTensor& t = p.t[which];
+  const int64_t blk = which ? (int64_t)blockIdx.x - p.blocks0 : (int64_t)blockIdx.x;
+  const int64_t row = blk * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= t.rows) return;
+  const int dim = p.heads * p.head_dim;
+  const int nchunks = dim >> 3;
+  uint4* xr = reinterpret_cast<uint4*>(t.ptr + row * t.row_stride);
+  float v[CPL][8];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nchunks) {
+      unpack8(xr[c], v[i]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[i][e] = 0.f;
+    }
+  }
+
+  if (p.norm_mode == QK_RMS_ACROSS_HEADS) {
+    // RMSNorm(D): fp32 mean square -> x*rsqrt -> cast to weight dtype (bf16) -> * weight (bf16 product)
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sq += v[i][e] * v[i][e];
+    const float rstd = rsqrtf(warp_sum(sq) / (float)dim + p.eps);
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      const int c = i * 32 + lane;
+      if (c < nchunks) {
+        float w[8];
+        if (t.weight != nullptr) {
+          unpack8(__ldg(reinterpret_cast<const uint4*>(t.weight) + c), w);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[i][e] = rbf(rbf(v[i][e] * rstd) * w[e]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[i][e] = rbf(v[i][e] * rstd);
+        }
+      }
+    }
+  } else {
+    // LayerNorm(head_dim) per head; a head occupies head_dim/8 consecutive lanes (power of two <= 32)
+    const int lanes_per_head = p.head_dim >> 3;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      const int c = i * 32 + lane;
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += v[i][e];
+      for (int o = lanes_per_head >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s / (float)p.head_dim;
+      float sq = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        float d = v[i][e] - mean;
+        sq += d * d;
+      }
+      for (int o = lanes_per_head >> 1; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+      const float rstd = rsqrtf(sq / (float)p.head_dim + p.eps);
+      if (c < nchunks) {
+        const int hc = c % lanes_per_head;  // chunk inside the head
+        float w[8], b[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          w[e] = 1.f;
+          b[e] = 0.f;
+        }
+        if (t.weight != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(t.weight) + hc), w);
+        if (t.bias != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(t.bias) + hc), b);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[i][e] = rbf((v[i][e] - mean) * rstd * w[e] + b[e]);
+      }
+    }
+  }
+
+  const int64_t s_in_seq = row % p.seq_len;
+  const bool do_rope = t.rope && p.rope_mode != ROPE_NONE && s_in_seq >= p.rope_skip;
+  const float* cos_row = do_rope ? p.cos + (s_in_seq - p.rope_skip) * p.head_dim : nullptr;
+  const float* sin_row = do_rope ? p.sin + (s_in_seq - p.rope_skip) * p.head_dim : nullptr;
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    const int c = i * 32 + lane;
+    if (c < nchunks) {
+      if (do_rope) {
+        const int off = (c * 8) % p.head_dim;
+        float cs[8], sn[8];
+        ld8f(cos_row + off, cs);
+        ld8f(sin_row + off, sn);
+        float o[8];
+        if (p.rope_mode == ROPE_WAN) {
+          // cos = freqs_cos[..., 0::2], sin = freqs_sin[..., 1::2]   (transformer_wan.py:83-87)
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            const float x1 = v[i][e], x2 = v[i][e + 1];
+            o[e] = __fsub_rn(__fmul_rn(x1, cs[e]), __fmul_rn(x2, sn[e + 1]));
+            o[e + 1] = __fadd_rn(__fmul_rn(x1, sn[e + 1]), __fmul_rn(x2, cs[e]));
+          }
+        } else {
+          // x*cos + rotate(x)*sin with rotate = (-x_odd, x_even)   (embeddings.py:1247-1256)
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            const float xe = v[i][e], xo = v[i][e + 1];
+            o[e] = __fadd_rn(__fmul_rn(xe, cs[e]), __fmul_rn(-xo, sn[e]));
+            o[e + 1] = __fadd_rn(__fmul_rn(xo, cs[e + 1]), __fmul_rn(xe, sn[e + 1]));
+          }
+        }
+        xr[c] = pack8(o);
+      } else {
+        xr[c] = pack8(v[i]);
+      }
+    }
+  }
+}
+
+int qk_norm_rope(void* x0, int64_t rows0, int64_t stride0, const void* w0, const void* b0, int rope0, void* x1,
+                 int64_t rows1, int64_t stride1, const void* w1, const void* b1, int rope1, int heads, int head_dim,
+                 int norm_mode, float eps, int rope_mode, const float* cos, const float* sin, int64_t seq_len,
+                 int64_t rope_skip, cudaStream_t stream) {
+  FINO_CHECK_ARG(x0 != nullptr && rows0 > 0, "qk_norm_rope: first tensor missing");
+  FINO_CHECK_ARG(heads > 0 && head_dim >= 8 && head_dim % 8 == 0, "qk_norm_rope: bad heads/head_dim");
+  FINO_CHECK_ARG(stride0 % 8 == 0 && (x1 == nullptr || stride1 % 8 == 0), "qk_norm_rope: strides % 8");
+  FINO_CHECK_ARG(norm_mode == QK_RMS_ACROSS_HEADS || norm_mode == QK_LAYERNORM_PER_HEAD, "qk_norm_rope: norm_mode");
+  if (norm_mode == QK_LAYERNORM_PER_HEAD) {
+    const int lph = head_dim / 8;
+    FINO_CHECK_ARG(lph <= 32 && (lph & (lph - 1)) == 0, "qk_norm_rope: per-head LayerNorm needs head_dim in {8..256} pow2");
+  }
+  FINO_CHECK_ARG(rope_mode >= ROPE_NONE && rope_mode <= ROPE_COGVIDEOX, "qk_norm_rope: rope_mode");
+  const bool any_rope = rope_mode != ROPE_NONE && (rope0 || (x1 && rope1));
+  FINO_CHECK_ARG(!any_rope || (cos && sin && seq_len > 0), "qk_norm_rope: rope tables / seq_len missing");
+  const int dim = heads * head_dim;
+  FINO_CHECK_ARG(dim <= 8192, "qk_norm_rope: heads*head_dim too large");
+  QkParams p;
+  p.t[0] = {(__nv_bfloat16*)x0, rows0, stride0, (const __nv_bfloat16*)w0, (const __nv_bfloat16*)b0, rope0};
+  p.t[1] = {(__nv_bfloat16*)x1, x1 ? rows1 : 0, stride1, (const __nv_bfloat16*)w1, (const __nv_bfloat16*)b1, rope1};
+  p.heads = heads;
+  p.head_dim = head_dim;
+  p.norm_mode = norm_mode;
+  p.eps = eps;
+  p.rope_mode = any_rope ? rope_mode : ROPE_NONE;
+  p.cos = cos;
+  p.sin = sin;
+  p.seq_len = seq_len > 0 ? seq_len : (int64_t)1 << 62;
+  p.rope_skip = rope_skip;
+  p.blocks0 = (rows0 + ROW_WARPS - 1) / ROW_WARPS;
+  const int64_t blocks1 = x1 ? (rows1 + ROW_WARPS - 1) / ROW_WARPS : 0;
+  const int cpl = (dim / 8 + 31) / 32;
+  dim3 grid((unsigned)(p.blocks0 + blocks1));
+#define LAUNCH_QK(C) qk_norm_rope_kernel<C><<<grid, ROW_WARPS * 32, 0, stream>>>(p)
+  if (cpl <= 1) LAUNCH_QK(1);
+  else if (cpl <= 2) LAUNCH_QK(2);
+  else if (cpl <= 4) LAUNCH_QK(4);
+  else if (cpl <= 8) LAUNCH_QK(8);
+  else if (cpl <= 12) LAUNCH_QK(12);
+  else if (cpl <= 16) LAUNCH_QK(16);
+  else LAUNCH_QK(32);
+#undef LAUNCH_QK
+  FINO_CHECK_CUDA(cudaGetLastError());
+  return FINO_OK;
+}
+
+}  // namespace fino

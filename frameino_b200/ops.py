@@ -1,0 +1,303 @@
+"""Tensor-level wrappers over the C ABI (``include/frameino_b200.h``).
+
+PyTorch is used here only for device memory and the current CUDA stream; all arithmetic happens in the hand-written
+sm_100a kernels of ``frameino_b200/csrc``. Every function raises if its inputs are not CUDA tensors — there is no CPU
+path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+EPI_NONE, EPI_GELU_TANH, EPI_SILU, EPI_GATE_RESIDUAL = 0, 1, 2, 3
+GEMM_FLAG_ROUND_PRODUCT = 1
+LN_FLAG_BF16_STEPS = 1
+QK_RMS_ACROSS_HEADS, QK_LAYERNORM_PER_HEAD = 0, 1
+ROPE_NONE, ROPE_WAN, ROPE_COGVIDEOX = 0, 1, 2
+
+_bound_device = None
+
+
+def _prep(*tensors: Optional[torch.Tensor]):
+    """Validates devices, binds the library to the device once, returns (lib, stream pointer)."""
+    global _bound_device
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("frameino_b200 ops need CUDA tensors (no CPU fallback)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"tensors on different devices: {t.device} vs {dev}")
+    lib = _lib.load()
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if _bound_device != idx:
+        _lib.check(lib.fino_set_device(idx), "fino_set_device")
+        _bound_device = idx
+    return lib, torch.cuda.current_stream(dev).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _rows2d(t: torch.Tensor) -> Tuple[int, int, int]:
+    """(rows, cols, row_stride) of a tensor viewed as a 2-D row matrix with contiguous columns (no copy)."""
+    if t.dim() < 2:
+        raise ValueError("need at least 2 dims")
+    if t.stride(-1) != 1:
+        raise ValueError("last dimension must be contiguous")
+    t2 = t if t.dim() == 2 else t.view(-1, t.shape[-1])  # raises if the leading dims do not collapse
+    return t2.shape[0], t2.shape[1], (t2.stride(0) if t2.shape[0] > 1 else t2.shape[1])
+
+
+def linear(
+    x: torch.Tensor,
+    weight: torch.Tensor,
+    bias: Optional[torch.Tensor] = None,
+    *,
+    epilogue: int = EPI_NONE,
+    out: Optional[torch.Tensor] = None,
+    out_dtype: torch.dtype = torch.bfloat16,
+    residual: Optional[torch.Tensor] = None,
+    gate: Optional[torch.Tensor] = None,
+    row_index: Optional[torch.Tensor] = None,
+    rows_per_group: int = 0,
+    round_product: bool = False,
+) -> torch.Tensor:
+    """``epilogue(x @ weight.T + bias)`` on the tcgen05 GEMM. x: [..., K] bf16, weight: [N, K] bf16.
+
+    With ``EPI_GATE_RESIDUAL``: ``residual + bf16(x @ W.T + b) * gate[row_index[row]]`` (gate fp32 [R, >=N]).
+    """
+    assert x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16
+    lib, stream = _prep(x, weight, bias, out, residual, gate, row_index)
+    m, k, lda = _rows2d(x)
+    n, k2 = weight.shape
+    assert k2 == k, f"K mismatch {k2} vs {k}"
+    assert weight.stride(1) == 1
+    if bias is not None:
+        assert bias.dtype == torch.bfloat16 and bias.is_contiguous() and bias.numel() == n
+    if out is None:
+        out = torch.empty(*x.shape[:-1], n, dtype=out_dtype, device=x.device)
+    om, on, ldc = _rows2d(out)
+    assert om == m and on == n
+    ldr = 0
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16
+        rm, rn, ldr = _rows2d(residual)
+        assert rm == m and rn == n
+    gstride = 0
+    if gate is not None:
+        assert gate.dtype == torch.float32 and gate.stride(-1) == 1
+        gstride = gate.stride(0) if gate.dim() == 2 else 0
+    if row_index is not None:
+        assert row_index.dtype == torch.int32 and row_index.is_contiguous() and row_index.numel() == m
+    status = lib.fino_gemm_bf16(
+        x.data_ptr(), lda, weight.data_ptr(), weight.stride(0), _ptr(bias), out.data_ptr(), ldc, m, n, k, epilogue,
+        1 if out.dtype == torch.float32 else 0, GEMM_FLAG_ROUND_PRODUCT if round_product else 0, _ptr(residual), ldr,
+        _ptr(gate), gstride, _ptr(row_index), rows_per_group, stream,
+    )
+    _lib.check(status, "fino_gemm_bf16")
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: Optional[float] = None,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Non-causal attention over token-major tensors. q: [B, Nq, H*d], k/v: [B, Nk, H*d] (any row/batch strides)."""
+    assert q.dtype == k.dtype == v.dtype == torch.bfloat16
+    assert q.dim() == 3 and k.dim() == 3 and v.dim() == 3
+    lib, stream = _prep(q, k, v, out)
+    b, nq, inner = q.shape
+    nk = k.shape[1]
+    d = inner // heads
+    assert d * heads == inner and k.shape == (b, nk, inner) and v.shape == (b, nk, inner)
+    for t in (q, k, v):
+        assert t.stride(2) == 1
+    if out is None:
+        out = torch.empty(b, nq, inner, dtype=torch.bfloat16, device=q.device)
+    assert out.shape == (b, nq, inner) and out.stride(2) == 1
+    if scale is None:
+        scale = d ** -0.5
+    status = lib.fino_attention_fwd(
+        q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), b, heads, nq, nk, d,
+        q.stride(1), k.stride(1), v.stride(1), out.stride(1), q.stride(0), k.stride(0), v.stride(0), out.stride(0),
+        float(scale), stream,
+    )
+    _lib.check(status, "fino_attention_fwd")
+    return out
+
+
+def ln_modulate(
+    x: torch.Tensor,
+    eps: float,
+    *,
+    gamma: Optional[torch.Tensor] = None,
+    beta: Optional[torch.Tensor] = None,
+    shift: Optional[torch.Tensor] = None,
+    scale: Optional[torch.Tensor] = None,
+    row_index: Optional[torch.Tensor] = None,
+    rows_per_group: int = 0,
+    bf16_steps: bool = False,
+    out: Optional[torch.Tensor] = None,
+) -> torch.Tensor:
+    """LayerNorm(x) [*gamma+beta] [*(1+scale)+shift]. shift/scale: fp32 [R, dim] views sharing one row stride."""
+    assert x.dtype == torch.bfloat16
+    lib, stream = _prep(x, gamma, beta, shift, scale, row_index, out)
+    rows, dim, xs = _rows2d(x)
+    if out is None:
+        out = torch.empty_like(x)
+    _, _, os_ = _rows2d(out)
+    mstride = 0
+    if shift is not None:
+        assert scale is not None and shift.dtype == scale.dtype == torch.float32
+        assert shift.dim() == 2 and scale.dim() == 2 and shift.stride(1) == 1 and scale.stride(1) == 1
+        assert shift.stride(0) == scale.stride(0) and shift.shape[1] == dim
+        mstride = shift.stride(0)
+    for t in (gamma, beta):
+        if t is not None:
+            assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == dim
+    if row_index is not None:
+        assert row_index.dtype == torch.int32 and row_index.numel() == rows
+    status = lib.fino_ln_modulate(x.data_ptr(), out.data_ptr(), rows, dim, xs, os_, float(eps), _ptr(gamma),
+                                  _ptr(beta), _ptr(shift), _ptr(scale), mstride, _ptr(row_index), rows_per_group,
+                                  LN_FLAG_BF16_STEPS if bf16_steps else 0, stream)
+    _lib.check(status, "fino_ln_modulate")
+    return out
+
+
+def gate_residual(x: torch.Tensor, y: torch.Tensor, gate: Optional[torch.Tensor] = None,
+                  row_index: Optional[torch.Tensor] = None, rows_per_group: int = 0, round_product: bool = False,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    assert x.dtype == y.dtype == torch.bfloat16
+    lib, stream = _prep(x, y, gate, row_index, out)
+    rows, dim, xs = _rows2d(x)
+    r2, d2, ys = _rows2d(y)
+    assert (rows, dim) == (r2, d2)
+    if out is None:
+        out = torch.empty_like(x)
+    _, _, os_ = _rows2d(out)
+    gs = 0
+    if gate is not None:
+        assert gate.dtype == torch.float32 and gate.dim() == 2 and gate.stride(1) == 1
+        gs = gate.stride(0)
+    status = lib.fino_gate_residual(x.data_ptr(), y.data_ptr(), out.data_ptr(), rows, dim, xs, ys, os_, _ptr(gate), gs,
+                                    _ptr(row_index), rows_per_group, 1 if round_product else 0, stream)
+    _lib.check(status, "fino_gate_residual")
+    return out
+
+
+def qk_norm_rope(
+    x0: torch.Tensor,
+    w0: Optional[torch.Tensor],
+    x1: Optional[torch.Tensor],
+    w1: Optional[torch.Tensor],
+    heads: int,
+    *,
+    b0: Optional[torch.Tensor] = None,
+    b1: Optional[torch.Tensor] = None,
+    rope0: bool = True,
+    rope1: bool = True,
+    norm_mode: int = QK_RMS_ACROSS_HEADS,
+    eps: float = 1e-6,
+    rope_mode: int = ROPE_NONE,
+    cos: Optional[torch.Tensor] = None,
+    sin: Optional[torch.Tensor] = None,
+    seq_len: int = 0,
+    rope_skip: int = 0,
+) -> None:
+    """In-place q/k norm + RoPE. x0/x1: [..., H*d] row views (e.g. column slices of a fused QKV buffer)."""
+    lib, stream = _prep(x0, w0, x1, w1, b0, b1, cos, sin)
+    rows0, dim, s0 = _rows2d(x0)
+    head_dim = dim // heads
+    rows1, s1 = 0, 0
+    if x1 is not None:
+        rows1, dim1, s1 = _rows2d(x1)
+        assert dim1 == dim
+    for t in (w0, w1, b0, b1):
+        if t is not None:
+            assert t.dtype == torch.bfloat16 and t.is_contiguous()
+    if cos is not None:
+        assert cos.dtype == sin.dtype == torch.float32 and cos.is_contiguous() and sin.is_contiguous()
+        assert cos.shape[-1] == head_dim
+    status = lib.fino_qk_norm_rope(x0.data_ptr(), rows0, s0, _ptr(w0), _ptr(b0), 1 if rope0 else 0, _ptr(x1), rows1,
+                                   s1, _ptr(w1), _ptr(b1), 1 if rope1 else 0, heads, head_dim, norm_mode, float(eps),
+                                   rope_mode, _ptr(cos), _ptr(sin), seq_len, rope_skip, stream)
+    _lib.check(status, "fino_qk_norm_rope")
+
+
+def patchify(x: torch.Tensor, dims: Tuple[int, int, int, int, int], strides: Tuple[int, int, int, int, int],
+             patch: Tuple[int, int, int]) -> torch.Tensor:
+    """x viewed as [B,C,F,H,W] through (dims, element strides) -> rows [B*F/pt*H/ph*W/pw, C*pt*ph*pw]."""
+    assert x.dtype == torch.bfloat16
+    lib, stream = _prep(x)
+    b, c, f, h, w = dims
+    pt, ph, pw = patch
+    rows = b * (f // pt) * (h // ph) * (w // pw)
+    kdim = c * pt * ph * pw
+    out = torch.empty(rows, kdim, dtype=torch.bfloat16, device=x.device)
+    status = lib.fino_patchify(x.data_ptr(), out.data_ptr(), b, c, f, h, w, pt, ph, pw, *strides, kdim, stream)
+    _lib.check(status, "fino_patchify")
+    return out
+
+
+def unpatchify(rows: torch.Tensor, out: torch.Tensor, dims: Tuple[int, int, int, int, int],
+               strides: Tuple[int, int, int, int, int], patch: Tuple[int, int, int], channel_last: bool) -> torch.Tensor:
+    assert rows.dtype == out.dtype == torch.bfloat16 and rows.dim() == 2 and rows.stride(1) == 1
+    lib, stream = _prep(rows, out)
+    b, c, f, h, w = dims
+    pt, ph, pw = patch
+    status = lib.fino_unpatchify(rows.data_ptr(), out.data_ptr(), b, c, f, h, w, pt, ph, pw, *strides, rows.stride(0),
+                                 1 if channel_last else 0, stream)
+    _lib.check(status, "fino_unpatchify")
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, flip_sin_to_cos: bool = True, downscale_freq_shift: float = 0.0,
+                       scale: float = 1.0, max_period: float = 10000.0) -> torch.Tensor:
+    assert t.dtype == torch.float32 and t.dim() == 1 and t.is_contiguous()
+    lib, stream = _prep(t)
+    out = torch.empty(t.numel(), dim, dtype=torch.float32, device=t.device)
+    status = lib.fino_timestep_embedding(t.data_ptr(), out.data_ptr(), t.numel(), dim, 1 if flip_sin_to_cos else 0,
+                                         float(downscale_freq_shift), float(scale), float(max_period), stream)
+    _lib.check(status, "fino_timestep_embedding")
+    return out
+
+
+def linear_small_m(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], *, act_in: int = 0,
+                   act_out: int = 0, round_in: bool = False, round_out: bool = False) -> torch.Tensor:
+    """fp32 [m<=8, K] x (fp32|bf16) [N, K] -> fp32 [m, N]."""
+    assert x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()
+    assert weight.dtype in (torch.float32, torch.bfloat16) and weight.is_contiguous()
+    if bias is not None:
+        assert bias.dtype == weight.dtype and bias.is_contiguous()
+    lib, stream = _prep(x, weight, bias)
+    m, k = x.shape
+    n = weight.shape[0]
+    assert weight.shape[1] == k
+    out = torch.empty(m, n, dtype=torch.float32, device=x.device)
+    status = lib.fino_linear_small_m(x.data_ptr(), weight.data_ptr(), _ptr(bias), out.data_ptr(), m, n, k,
+                                     1 if weight.dtype == torch.bfloat16 else 0, act_in, act_out,
+                                     1 if round_in else 0, 1 if round_out else 0, stream)
+    _lib.check(status, "fino_linear_small_m")
+    return out
+
+
+def build_mod_table(table: torch.Tensor, proj: torch.Tensor, layers: int, table_layer_stride: int) -> torch.Tensor:
+    """out[l, r, :] = table[l*stride : l*stride+cols] + proj[r, :] (fp32)."""
+    assert table.dtype == proj.dtype == torch.float32 and proj.dim() == 2 and proj.is_contiguous()
+    lib, stream = _prep(table, proj)
+    r, cols = proj.shape
+    out = torch.empty(layers, r, cols, dtype=torch.float32, device=proj.device)
+    status = lib.fino_build_mod_table(table.data_ptr(), proj.data_ptr(), out.data_ptr(), layers, r, cols,
+                                      table_layer_stride, stream)
+    _lib.check(status, "fino_build_mod_table")
+    return out
+
+
+def launch_count() -> int:
+    return int(_lib.load().fino_launch_count())

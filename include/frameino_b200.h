@@ -1,0 +1,115 @@
+/* frameino_b200 — C ABI of the B200-native FrameINO denoise-step kernels (sm_100a).
+ *
+ * The reference (UVA-Computer-Vision-Lab/FrameINO) has no FFI of its own: its hot path is PyTorch library calls
+ * issued from architecture/transformer_wan.py, architecture/cogvideox_transformer_3d.py and
+ * architecture/attention_processor.py. Each entry point below replaces one of those call sites (cited per
+ * function) and is what a reference-side binding (ctypes) would bind.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; tensors are bf16 unless the type says float/int32_t;
+ *   - strides are in ELEMENTS; `stream` is a cudaStream_t passed as void*;
+ *   - return value: 0 = ok, 1 = invalid argument, 2 = CUDA error, 3 = unsupported; the message is available from
+ *     fino_last_error() (thread local). There is no CPU fallback: without a GPU every compute entry point fails.
+ *   - "modulation rows": AdaLN tables are fp32 [R, row_stride]; the row used for token `row` is
+ *     row_index[row] when row_index != NULL, else row / rows_per_group.
+ */
+#ifndef FRAMEINO_B200_H_
+#define FRAMEINO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FINO_ABI_VERSION 1
+
+/* status / bookkeeping ------------------------------------------------------------------------------------ */
+int fino_abi_version(void);
+const char* fino_last_error(void);
+/* Binds the library's CUDA runtime to `device` (one process per GPU: call once with LOCAL_RANK). */
+int fino_set_device(int device);
+/* Number of kernels this library has launched since load (for bench.py's gpu_launches). */
+int64_t fino_launch_count(void);
+
+/* epilogues of fino_gemm_bf16 */
+#define FINO_EPI_NONE 0          /* C = A W^T + bias                                                         */
+#define FINO_EPI_GELU_TANH 1     /* C = gelu_tanh(bf16(A W^T + bias))      FeedForward, transformer_wan.py:347 */
+#define FINO_EPI_SILU 2          /* C = silu(bf16(A W^T + bias))                                             */
+#define FINO_EPI_GATE_RESIDUAL 3 /* C = residual + bf16(A W^T + bias) * gate   transformer_wan.py:336,341,348 */
+#define FINO_GEMM_FLAG_ROUND_PRODUCT 1 /* round gate*y to bf16 first (CogVideoX, cogvideox_transformer_3d.py:146) */
+
+/* C[m,n] = epilogue(A[m,k] * W[n,k]^T + bias[n]); tcgen05/TMEM/TMA persistent GEMM.
+ * Replaces nn.Linear on the hot path: transformer_wan.py:60-62,117,347,486,537; attention_processor.py:2837-2839,2870.
+ * out_fp32: 0 -> C is bf16, 1 -> C is float. k, n, lda, ldw, ldc (and ldr) must be multiples of 8. */
+int fino_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* c, int64_t ldc,
+                   int64_t m, int n, int k, int epilogue, int out_fp32, int flags, const void* residual, int64_t ldr,
+                   const float* gate, int64_t gate_row_stride, const int32_t* row_index, int64_t rows_per_group,
+                   void* stream);
+
+/* O = softmax(Q K^T * scale) V, non-causal, no mask; tcgen05 flash attention, head_dim 64 or 128.
+ * Replaces F.scaled_dot_product_attention: transformer_wan.py:108-110, attention_processor.py:2863.
+ * Q/K/V/O are [batch, n, heads*head_dim] views (heads contiguous inside a row). */
+int fino_attention_fwd(const void* q, const void* k, const void* v, void* o, int batch, int heads, int64_t nq,
+                       int64_t nk, int head_dim, int64_t q_row_stride, int64_t k_row_stride, int64_t v_row_stride,
+                       int64_t o_row_stride, int64_t q_batch_stride, int64_t k_batch_stride, int64_t v_batch_stride,
+                       int64_t o_batch_stride, float scale, void* stream);
+
+#define FINO_LN_FLAG_BF16_STEPS 1 /* emulate the bf16 module flow of CogVideoXLayerNormZero / AdaLayerNorm */
+
+/* out = LayerNorm(x) [*gamma + beta] [*(1+scale) + shift], fp32 math, one rounding.
+ * Replaces FP32LayerNorm + modulate: transformer_wan.py:334,339,344-346,536; cogvideox_transformer_3d.py:134,150,536-541.
+ * gamma/beta/shift/scale are float and optional (NULL). */
+int fino_ln_modulate(const void* x, void* out, int64_t rows, int dim, int64_t x_stride, int64_t out_stride, float eps,
+                     const float* gamma, const float* beta, const float* shift, const float* scale,
+                     int64_t mod_row_stride, const int32_t* row_index, int64_t rows_per_group, int flags, void* stream);
+
+/* out = x + y * gate (gate optional). Replaces transformer_wan.py:336,341,348 when not fused into a GEMM epilogue. */
+int fino_gate_residual(const void* x, const void* y, void* out, int64_t rows, int dim, int64_t x_stride,
+                       int64_t y_stride, int64_t out_stride, const float* gate, int64_t mod_row_stride,
+                       const int32_t* row_index, int64_t rows_per_group, int round_product, void* stream);
+
+#define FINO_QK_RMS_ACROSS_HEADS 0   /* RMSNorm over heads*head_dim  (Wan, attention_processor.py:208-211)   */
+#define FINO_QK_LAYERNORM_PER_HEAD 1 /* LayerNorm(head_dim) per head (CogVideoX, attention_processor.py:195-197) */
+#define FINO_ROPE_NONE 0
+#define FINO_ROPE_WAN 1       /* transformer_wan.py:75-90       */
+#define FINO_ROPE_COGVIDEOX 2 /* embeddings.py:1219-1258        */
+
+/* In-place q/k normalisation + rotary embedding for up to two tensors (x1 may be NULL).
+ * Replaces norm_q/norm_k + apply_rotary_emb: transformer_wan.py:64-90; attention_processor.py:2848-2860.
+ * weights/biases are bf16 ([heads*head_dim] for RMS, [head_dim] for per-head LayerNorm); cos/sin are float
+ * [*, head_dim] tables exactly as the reference rope modules produce them; token s of every `seq_len`-long sequence
+ * uses table row s - rope_skip and tokens with s < rope_skip are not rotated. */
+int fino_qk_norm_rope(void* x0, int64_t rows0, int64_t stride0, const void* w0, const void* b0, int rope0, void* x1,
+                      int64_t rows1, int64_t stride1, const void* w1, const void* b1, int rope1, int heads,
+                      int head_dim, int norm_mode, float eps, int rope_mode, const float* cos, const float* sin,
+                      int64_t seq_len, int64_t rope_skip, void* stream);
+
+/* x[b,c,f,h,w] (element strides sb..sw) -> rows[(b,f/pt,h/ph,w/pw), (c,pt,ph,pw)], row stride ld.
+ * Turns the patch-embedding convolutions into a GEMM: transformer_wan.py:486-487; embeddings.py:734-738. */
+int fino_patchify(const void* x, void* rows, int b, int c, int f, int h, int w, int pt, int ph, int pw, int64_t sb,
+                  int64_t sc, int64_t sf, int64_t sh, int64_t sw, int64_t ld, void* stream);
+
+/* rows -> out[b,c,f,h,w] (element strides sb..sw). channel_last = 1: row layout (pt,ph,pw,c)
+ * (transformer_wan.py:539-543); 0: (c,pt,ph,pw) (cogvideox_transformer_3d.py:549-550). */
+int fino_unpatchify(const void* rows, void* out, int b, int c, int f, int h, int w, int pt, int ph, int pw, int64_t sb,
+                    int64_t sc, int64_t sf, int64_t sh, int64_t sw, int64_t ld, int channel_last, void* stream);
+
+/* Sinusoidal timestep embedding, float in/out [n] -> [n, dim]. Replaces embeddings.py:27-78. */
+int fino_timestep_embedding(const float* t, float* out, int n, int dim, int flip_sin_to_cos,
+                            float downscale_freq_shift, float scale, float max_period, void* stream);
+
+/* y[m,n] = act_out(act_in(x)[m,k] * w[n,k]^T + b), m <= 8, float activations, w/b float or bf16.
+ * The de-duplicated time MLP: transformer_wan.py:182-183; cogvideox_transformer_3d.py:485. act: 0 none, 1 SiLU. */
+int fino_linear_small_m(const float* x, const void* w, const void* b, float* y, int m, int n, int k, int w_is_bf16,
+                        int act_in, int act_out, int round_in, int round_out, void* stream);
+
+/* out[l,r,c] = table[l*table_layer_stride + c] + proj[r,c] (float): the per-layer AdaLN rows
+ * scale_shift_table + temb of transformer_wan.py:317-331, 520-527. */
+int fino_build_mod_table(const float* table, const float* proj, float* out, int layers, int r, int cols,
+                         int64_t table_layer_stride, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRAMEINO_B200_H_ */
