@@ -35,6 +35,7 @@ SIGNATURES = {
     "fino_timestep_embedding": (_I, [_P, _P, _I, _I, _I, _F, _F, _F, _P]),
     "fino_linear_small_m": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fino_build_mod_table": (_I, [_P, _P, _P, _I, _I, _I, _L, _P]),
+    "fino_swap01": (_I, [_P, _P, _L, _L, _L, _P]),
 }
 
 

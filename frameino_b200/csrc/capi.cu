@@ -32,6 +32,7 @@ int linear_small_m(const float* x, const void* w, const void* b, float* y, int m
                    int act_in, int act_out, int round_in, int round_out, cudaStream_t stream);
 int build_mod_table(const float* table, const float* proj, float* out, int layers, int r, int cols,
                     int64_t table_layer_stride, cudaStream_t stream);
+int swap01(const void* in, void* out, int64_t A, int64_t B, int64_t inner, cudaStream_t stream);
 }  // namespace fino
 
 static std::atomic<int64_t> g_launches{0};
@@ -148,6 +149,10 @@ int fino_linear_small_m(const float* x, const void* w, const void* b, float* y, 
 int fino_build_mod_table(const float* table, const float* proj, float* out, int layers, int r, int cols,
                          int64_t table_layer_stride, void* stream) {
   FINO_ENTRY(fino::build_mod_table(table, proj, out, layers, r, cols, table_layer_stride, (cudaStream_t)stream));
+}
+
+int fino_swap01(const void* in, void* out, int64_t a, int64_t b, int64_t inner, void* stream) {
+  FINO_ENTRY(fino::swap01(in, out, a, b, inner, (cudaStream_t)stream));
 }
 
 }  // extern "C"

@@ -268,4 +268,33 @@ int build_mod_table(const float* table, const float* proj, float* out, int layer
   return FINO_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// out[b][a][:] = in[a][b][:]   (16-byte vectors; `inner` bf16 elements per row, multiple of 8)
+// The (de)interleave step on either side of the Ulysses all-to-all.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+swap01_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int64_t A, int64_t B, int vec_per_row) {
+  const int64_t total = A * B * vec_per_row;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    // idx enumerates the OUTPUT [b][a][v]
+    const int v = (int)(idx % vec_per_row);
+    const int64_t t = idx / vec_per_row;
+    const int64_t a = t % A;
+    const int64_t b = t / A;
+    out[idx] = in[(a * B + b) * vec_per_row + v];
+  }
+}
+
+int swap01(const void* in, void* out, int64_t A, int64_t B, int64_t inner, cudaStream_t stream) {
+  FINO_CHECK_ARG(in && out && A > 0 && B > 0 && inner > 0 && inner % 8 == 0, "swap01: bad arguments");
+  const int64_t total = A * B * (inner / 8);
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 32;
+  if (blocks > cap) blocks = cap;
+  swap01_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const uint4*)in, (uint4*)out, A, B, (int)(inner / 8));
+  FINO_CHECK_CUDA(cudaGetLastError());
+  return FINO_OK;
+}
+
 }  // namespace fino

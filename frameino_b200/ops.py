@@ -299,5 +299,16 @@ def build_mod_table(table: torch.Tensor, proj: torch.Tensor, layers: int, table_
     return out
 
 
+def swap01(x: torch.Tensor, a: int, b: int, inner: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Contiguous [a, b, inner] -> [b, a, inner] (bf16, inner % 8 == 0)."""
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() == a * b * inner
+    lib, stream = _prep(x, out)
+    if out is None:
+        out = torch.empty(b, a, inner, dtype=x.dtype, device=x.device)
+    assert out.is_contiguous() and out.numel() == x.numel()
+    _lib.check(lib.fino_swap01(x.data_ptr(), out.data_ptr(), a, b, inner, stream), "fino_swap01")
+    return out
+
+
 def launch_count() -> int:
     return int(_lib.load().fino_launch_count())

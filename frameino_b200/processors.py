@@ -1,0 +1,176 @@
+"""Native attention processors — the reference's ``AttnProcessor`` plugin surface (boundary #2).
+
+Drop-in replacements for
+  WanAttnProcessor2_0         reference architecture/transformer_wan.py:38-119
+  CogVideoXAttnProcessor2_0   reference architecture/attention_processor.py:2805-2877 (and the Fused variant :2880-2948)
+with the same call signatures, reading weights off the ``attn`` container (diffusers' ``Attention`` or
+``frameino_b200.modules.Attention``). They issue only frameino_b200 CUDA kernels: fused-QKV tcgen05 GEMM, in-place
+q/k norm + RoPE, tcgen05 flash attention, out-projection GEMM (optionally with the gated residual fused in).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import ops
+
+
+def _fused_weights(attn, names: Tuple[str, ...], tag: str):
+    """Concatenated [sum(out), in] weight (+bias) of several nn.Linear projections, cached on the module and
+    refreshed when any source parameter changes (data_ptr / in-place version)."""
+    mods = [getattr(attn, n) for n in names]
+    key = tuple((m.weight.data_ptr(), m.weight._version, None if m.bias is None else m.bias._version) for m in mods)
+    cache = attn.__dict__.setdefault("_fino_cache", {})
+    hit = cache.get(tag)
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    with torch.no_grad():
+        w = torch.cat([m.weight for m in mods], dim=0).contiguous()
+        b = None
+        if mods[0].bias is not None:
+            b = torch.cat([m.bias for m in mods], dim=0).contiguous()
+    cache[tag] = (key, w, b)
+    return w, b
+
+
+def _check_dtype(t: torch.Tensor, what: str) -> None:
+    if t.dtype != torch.bfloat16:
+        raise NotImplementedError(f"frameino_b200 kernels compute in bf16; {what} is {t.dtype}")
+    if not t.is_cuda:
+        raise RuntimeError(f"frameino_b200 has no CPU path; {what} is on {t.device}")
+
+
+def _rope_table(t: torch.Tensor, head_dim: int) -> torch.Tensor:
+    t = t.reshape(-1, head_dim)
+    if t.dtype != torch.float32 or not t.is_contiguous():
+        t = t.float().contiguous()
+    return t
+
+
+class FinoWanAttnProcessor:
+    """``processor(attn, hidden_states, encoder_hidden_states=None, attention_mask=None, rotary_emb=None)`` -> Tensor.
+
+    Extra keyword (only passed by frameino_b200's own block): ``fino_residual=(x, gate, row_index, rows_per_group)``
+    fuses ``x + out * gate`` (transformer_wan.py:336 / :341) into the out-projection epilogue and returns ``x``.
+    """
+
+    def __call__(
+        self,
+        attn,
+        hidden_states: torch.Tensor,
+        encoder_hidden_states: Optional[torch.Tensor] = None,
+        attention_mask: Optional[torch.Tensor] = None,
+        rotary_emb: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+        fino_residual=None,
+    ) -> torch.Tensor:
+        if attention_mask is not None:
+            raise NotImplementedError("attention_mask is not supported (the reference never passes one)")
+        if getattr(attn, "add_k_proj", None) is not None:
+            raise NotImplementedError("Wan I2V added-KV branch (added_kv_proj_dim) is not part of the FrameINO path")
+        _check_dtype(hidden_states, "hidden_states")
+        heads = attn.heads
+        b, n, _ = hidden_states.shape
+        norm_q, norm_k = attn.norm_q, attn.norm_k
+        eps = getattr(norm_q, "eps", 1e-6) if norm_q is not None else 1e-6
+        if encoder_hidden_states is None:
+            w, bias = _fused_weights(attn, ("to_q", "to_k", "to_v"), "qkv")
+            qkv = ops.linear(hidden_states, w, bias)  # [B, N, 3D]
+            d_model = w.shape[0] // 3
+            q, k, v = qkv[..., :d_model], qkv[..., d_model:2 * d_model], qkv[..., 2 * d_model:]
+        else:
+            _check_dtype(encoder_hidden_states, "encoder_hidden_states")
+            q = ops.linear(hidden_states, attn.to_q.weight, attn.to_q.bias)
+            w, bias = _fused_weights(attn, ("to_k", "to_v"), "kv")
+            kv = ops.linear(encoder_hidden_states, w, bias)  # [B, T, 2D]
+            d_model = w.shape[0] // 2
+            k, v = kv[..., :d_model], kv[..., d_model:]
+        head_dim = d_model // heads
+        if norm_q is not None or rotary_emb is not None:
+            if norm_q is None:
+                raise NotImplementedError("RoPE without qk-norm is not used by the reference Wan path")
+            cos = sin = None
+            mode = ops.ROPE_NONE
+            if rotary_emb is not None:
+                cos, sin = _rope_table(rotary_emb[0], head_dim), _rope_table(rotary_emb[1], head_dim)
+                if cos.shape[0] != n:
+                    raise ValueError(f"rotary table has {cos.shape[0]} rows for {n} tokens")
+                mode = ops.ROPE_WAN
+            ops.qk_norm_rope(q, norm_q.weight, k, norm_k.weight, heads, norm_mode=ops.QK_RMS_ACROSS_HEADS, eps=eps,
+                             rope_mode=mode, cos=cos, sin=sin, seq_len=n)
+        scale = getattr(attn, "scale", head_dim ** -0.5)
+        sp = attn.__dict__.get("_fino_sp")
+        if sp is not None and encoder_hidden_states is None:
+            o = sp.attention(qkv, heads, scale)  # Ulysses all-to-all around the full-sequence attention
+        else:
+            o = ops.attention(q, k, v, heads, scale=scale)
+        wo, bo = attn.to_out[0].weight, attn.to_out[0].bias
+        if fino_residual is not None:
+            x, gate, row_index, rows_per_group = fino_residual
+            return ops.linear(o, wo, bo, epilogue=ops.EPI_GATE_RESIDUAL, residual=x, gate=gate, row_index=row_index,
+                              rows_per_group=rows_per_group, out=x)
+        return ops.linear(o, wo, bo)
+
+
+class FinoCogVideoXAttnProcessor:
+    """``processor(attn, hidden_states, encoder_hidden_states, attention_mask=None, image_rotary_emb=None)``
+    -> ``(hidden_states, encoder_hidden_states)`` (attention_processor.py:2815-2877).
+
+    Extra keywords (frameino_b200's own block only): ``fino_joint_text_len=T`` means ``hidden_states`` already is the
+    joint ``[text, video]`` sequence whose first T rows are text, and the joint output is returned un-split;
+    ``fino_residual=(x, gate, row_index)`` fuses ``x + gate * out`` into the out-projection epilogue.
+    """
+
+    def __call__(
+        self,
+        attn,
+        hidden_states: torch.Tensor,
+        encoder_hidden_states: torch.Tensor,
+        attention_mask: Optional[torch.Tensor] = None,
+        image_rotary_emb: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+        fino_joint_text_len: Optional[int] = None,
+        fino_residual=None,
+    ):
+        if attention_mask is not None:
+            raise NotImplementedError("attention_mask is not supported (the reference never passes one)")
+        _check_dtype(hidden_states, "hidden_states")
+        if fino_joint_text_len is None:
+            text_len = encoder_hidden_states.size(1)
+            joint = torch.cat([encoder_hidden_states, hidden_states], dim=1)  # :2827
+        else:
+            text_len = fino_joint_text_len
+            joint = hidden_states
+        heads = attn.heads
+        b, s, _ = joint.shape
+        if getattr(attn, "fused_projections", False) and hasattr(attn, "to_qkv"):
+            w, bias = attn.to_qkv.weight, attn.to_qkv.bias  # FusedCogVideoXAttnProcessor2_0, :2910
+        else:
+            w, bias = _fused_weights(attn, ("to_q", "to_k", "to_v"), "qkv")
+        qkv = ops.linear(joint, w, bias)
+        d_model = w.shape[0] // 3
+        head_dim = d_model // heads
+        q, k, v = qkv[..., :d_model], qkv[..., d_model:2 * d_model], qkv[..., 2 * d_model:]
+        norm_q, norm_k = attn.norm_q, attn.norm_k
+        cos = sin = None
+        mode = ops.ROPE_NONE
+        if image_rotary_emb is not None:
+            cos, sin = _rope_table(image_rotary_emb[0], head_dim), _rope_table(image_rotary_emb[1], head_dim)
+            if cos.shape[0] != s - text_len:
+                raise ValueError(f"rotary table has {cos.shape[0]} rows for {s - text_len} video tokens")
+            mode = ops.ROPE_COGVIDEOX
+        if norm_q is not None:
+            ops.qk_norm_rope(q, norm_q.weight, k, norm_k.weight, heads, b0=norm_q.bias, b1=norm_k.bias,
+                             rope1=not getattr(attn, "is_cross_attention", False),
+                             norm_mode=ops.QK_LAYERNORM_PER_HEAD, eps=getattr(norm_q, "eps", 1e-6), rope_mode=mode,
+                             cos=cos, sin=sin, seq_len=s, rope_skip=text_len)
+        elif mode != ops.ROPE_NONE:
+            raise NotImplementedError("RoPE without qk-norm is not used by the reference CogVideoX path")
+        o = ops.attention(q, k, v, heads, scale=getattr(attn, "scale", head_dim ** -0.5))
+        if fino_residual is not None:  # x + gate * out (cogvideox_transformer_3d.py:146-147), joint layout only
+            x, gate, row_index = fino_residual
+            return ops.linear(o, attn.to_out[0].weight, attn.to_out[0].bias, epilogue=ops.EPI_GATE_RESIDUAL,
+                              residual=x, gate=gate, row_index=row_index, round_product=True, out=x)
+        out = ops.linear(o, attn.to_out[0].weight, attn.to_out[0].bias)  # :2870
+        if fino_joint_text_len is not None:
+            return out
+        return out[:, text_len:], out[:, :text_len]  # :2874-2877 (video, text)

@@ -1,0 +1,217 @@
+"""Seeded synthetic weights and inputs for the configurations BASELINE.json names (no checkpoints or datasets are
+reachable offline). Pure functions of (config, seed): the same recipe feeds the native model, the CPU oracle and the
+golden-vector generator, so all three see identical tensors.
+
+State-dict keys follow the diffusers layout the reference checkpoints use.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+
+# ---- Wan -------------------------------------------------------------------------------------------------------
+WAN_TINY = dict(patch_size=(1, 2, 2), num_attention_heads=8, attention_head_dim=32, in_channels=32, out_channels=16,
+                text_dim=64, freq_dim=256, ffn_dim=1024, num_layers=2, cross_attn_norm=True,
+                qk_norm="rms_norm_across_heads", eps=1e-6, rope_max_seq_len=1024)
+# head_dim 128 at a size the CPU oracle still finishes in seconds (used by the GPU parity tests)
+WAN_SMALL = dict(patch_size=(1, 2, 2), num_attention_heads=4, attention_head_dim=128, in_channels=32, out_channels=16,
+                 text_dim=128, freq_dim=256, ffn_dim=2048, num_layers=2, cross_attn_norm=True,
+                 qk_norm="rms_norm_across_heads", eps=1e-6, rope_max_seq_len=1024)
+WAN22_5B = dict(patch_size=(1, 2, 2), num_attention_heads=24, attention_head_dim=128, in_channels=96, out_channels=48,
+                text_dim=4096, freq_dim=256, ffn_dim=14336, num_layers=30, cross_attn_norm=True,
+                qk_norm="rms_norm_across_heads", eps=1e-6, rope_max_seq_len=1024)
+
+WAN_KEEP_FP32 = ("time_embedder", "scale_shift_table", "norm1", "norm2", "norm3")  # transformer_wan.py:393
+
+
+def wan_param_shapes(cfg: dict) -> Dict[str, Tuple[int, ...]]:
+    d = cfg["num_attention_heads"] * cfg["attention_head_dim"]
+    pt, ph, pw = cfg["patch_size"]
+    f = cfg["ffn_dim"]
+    shapes: Dict[str, Tuple[int, ...]] = {
+        "patch_embedding.weight": (d, cfg["in_channels"], pt, ph, pw),
+        "patch_embedding.bias": (d,),
+        "condition_embedder.time_embedder.linear_1.weight": (d, cfg["freq_dim"]),
+        "condition_embedder.time_embedder.linear_1.bias": (d,),
+        "condition_embedder.time_embedder.linear_2.weight": (d, d),
+        "condition_embedder.time_embedder.linear_2.bias": (d,),
+        "condition_embedder.time_proj.weight": (6 * d, d),
+        "condition_embedder.time_proj.bias": (6 * d,),
+        "condition_embedder.text_embedder.linear_1.weight": (d, cfg["text_dim"]),
+        "condition_embedder.text_embedder.linear_1.bias": (d,),
+        "condition_embedder.text_embedder.linear_2.weight": (d, d),
+        "condition_embedder.text_embedder.linear_2.bias": (d,),
+        "scale_shift_table": (1, 2, d),
+        "proj_out.weight": (cfg["out_channels"] * pt * ph * pw, d),
+        "proj_out.bias": (cfg["out_channels"] * pt * ph * pw,),
+    }
+    for i in range(cfg["num_layers"]):
+        p = f"blocks.{i}"
+        shapes[f"{p}.scale_shift_table"] = (1, 6, d)
+        for a in ("attn1", "attn2"):
+            for proj in ("to_q", "to_k", "to_v", "to_out.0"):
+                shapes[f"{p}.{a}.{proj}.weight"] = (d, d)
+                shapes[f"{p}.{a}.{proj}.bias"] = (d,)
+            shapes[f"{p}.{a}.norm_q.weight"] = (d,)
+            shapes[f"{p}.{a}.norm_k.weight"] = (d,)
+        if cfg.get("cross_attn_norm", True):
+            shapes[f"{p}.norm2.weight"] = (d,)
+            shapes[f"{p}.norm2.bias"] = (d,)
+        shapes[f"{p}.ffn.net.0.proj.weight"] = (f, d)
+        shapes[f"{p}.ffn.net.0.proj.bias"] = (f,)
+        shapes[f"{p}.ffn.net.2.weight"] = (d, f)
+        shapes[f"{p}.ffn.net.2.bias"] = (d,)
+    return shapes
+
+
+def _fill(name: str, shape: Tuple[int, ...], gen: torch.Generator, device) -> torch.Tensor:
+    """Value recipe: GEMM weights N(0, 1/fan_in), biases N(0, 0.02^2), norm gains 1 + 0.1 N(0,1),
+    scale_shift_table N(0,1)/sqrt(D) (as transformer_wan.py:306,450), positional tables N(0, 0.02^2)."""
+    if name.endswith("scale_shift_table"):
+        return torch.randn(shape, generator=gen, device=device) / math.sqrt(shape[-1])
+    if "pos_embedding" in name:
+        return torch.randn(shape, generator=gen, device=device) * 0.02
+    if name.endswith(".bias"):
+        return torch.randn(shape, generator=gen, device=device) * 0.02
+    if len(shape) == 1:  # norm gains
+        return 1.0 + 0.1 * torch.randn(shape, generator=gen, device=device)
+    fan_in = 1
+    for s in shape[1:]:
+        fan_in *= s
+    return torch.randn(shape, generator=gen, device=device) / math.sqrt(fan_in)
+
+
+def make_state_dict(shapes: Dict[str, Tuple[int, ...]], seed: int, dtype: torch.dtype = torch.float32,
+                    keep_fp32: Tuple[str, ...] = (), device="cpu") -> Dict[str, torch.Tensor]:
+    """Fills parameters in sorted-key order from one seeded generator. ``dtype`` applies to everything except keys
+    containing one of ``keep_fp32`` (diffusers' ``_keep_in_fp32_modules``)."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    sd = {}
+    for name in sorted(shapes):
+        t = _fill(name, shapes[name], gen, device)
+        keep = any(k in name for k in keep_fp32)
+        sd[name] = t if (keep or dtype == torch.float32) else t.to(dtype)
+    return sd
+
+
+def make_wan_state_dict(cfg: dict, seed: int = 0, dtype: torch.dtype = torch.float32, device="cpu"):
+    return make_state_dict(wan_param_shapes(cfg), seed, dtype, WAN_KEEP_FP32 if dtype != torch.float32 else (), device)
+
+
+def make_wan_inputs(cfg: dict, latent_frames: int, height: int, width: int, n_id: int = 1, text_len: int = 16,
+                    text_true_len: Optional[int] = None, t_value: float = 500.0, batch: int = 1, seed: int = 0,
+                    per_token_timestep: bool = True, dtype: torch.dtype = torch.float32, device="cpu"):
+    """Inputs shaped like the FrameINO Wan sampler builds them (pipelines/pipeline_wan_i2v_motion_FrameINO.py:826-858):
+    ``[noisy latents ‖ ID frames]`` frame-wise, trajectory latents channel-wise with zeros on the ID frames; text rows
+    past the true prompt length are exact zeros (:235-238); per-token timesteps are 0 on latent frame 0 and ``t``
+    elsewhere including the ID tokens (:832-843)."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed + 1000)
+    c_half = cfg["in_channels"] // 2
+    f_all = latent_frames + n_id
+    lat = torch.randn(batch, c_half, f_all, height, width, generator=gen, device=device)
+    traj = torch.randn(batch, c_half, f_all, height, width, generator=gen, device=device)
+    if n_id > 0:
+        traj[:, :, latent_frames:] = 0
+    hidden = torch.cat([lat, traj], dim=1).to(dtype)
+    text = torch.randn(batch, text_len, cfg["text_dim"], generator=gen, device=device)
+    if text_true_len is not None:
+        text[:, text_true_len:] = 0
+    text = text.to(dtype)
+    pt, ph, pw = cfg["patch_size"]
+    tokens_per_frame = (height // ph) * (width // pw)
+    n_tokens = (f_all // pt) * tokens_per_frame
+    if per_token_timestep:
+        ts = torch.full((batch, n_tokens), float(t_value), device=device)
+        ts[:, :tokens_per_frame] = 0.0
+    else:
+        ts = torch.full((batch,), float(t_value), device=device)
+    return hidden, ts, text
+
+
+# ---- CogVideoX -------------------------------------------------------------------------------------------------
+COG_TINY = dict(num_attention_heads=4, attention_head_dim=64, in_channels=48, out_channels=16, time_embed_dim=64,
+                text_embed_dim=64, num_layers=2, sample_width=16, sample_height=12, sample_frames=9, patch_size=2,
+                temporal_compression_ratio=4, max_text_seq_length=10, norm_eps=1e-5,
+                use_rotary_positional_embeddings=True, use_learned_positional_embeddings=True, use_FrameIn=True)
+COG_5B_I2V = dict(num_attention_heads=48, attention_head_dim=64, in_channels=48, out_channels=16, time_embed_dim=512,
+                  text_embed_dim=4096, num_layers=42, sample_width=90, sample_height=60, sample_frames=49,
+                  patch_size=2, temporal_compression_ratio=4, max_text_seq_length=226, norm_eps=1e-5,
+                  use_rotary_positional_embeddings=True, use_learned_positional_embeddings=True, use_FrameIn=True)
+
+
+def cog_param_shapes(cfg: dict) -> Dict[str, Tuple[int, ...]]:
+    d = cfg["num_attention_heads"] * cfg["attention_head_dim"]
+    hd = cfg["attention_head_dim"]
+    p = cfg["patch_size"]
+    te = cfg["time_embed_dim"]
+    frames = (cfg["sample_frames"] - 1) // cfg["temporal_compression_ratio"] + 1
+    n_patches = (cfg["sample_height"] // p) * (cfg["sample_width"] // p) * frames
+    shapes: Dict[str, Tuple[int, ...]] = {
+        "patch_embed.proj.weight": (d, cfg["in_channels"], p, p),
+        "patch_embed.proj.bias": (d,),
+        "patch_embed.text_proj.weight": (d, cfg["text_embed_dim"]),
+        "patch_embed.text_proj.bias": (d,),
+        "time_embedding.linear_1.weight": (te, d),
+        "time_embedding.linear_1.bias": (te,),
+        "time_embedding.linear_2.weight": (te, te),
+        "time_embedding.linear_2.bias": (te,),
+        "norm_final.weight": (d,),
+        "norm_final.bias": (d,),
+        "norm_out.linear.weight": (2 * d, te),
+        "norm_out.linear.bias": (2 * d,),
+        "norm_out.norm.weight": (d,),
+        "norm_out.norm.bias": (d,),
+        "proj_out.weight": (p * p * cfg["out_channels"], d),
+        "proj_out.bias": (p * p * cfg["out_channels"],),
+    }
+    if cfg.get("use_learned_positional_embeddings", False):
+        shapes["patch_embed.pos_embedding"] = (1, cfg["max_text_seq_length"] + n_patches, d)
+    for i in range(cfg["num_layers"]):
+        b = f"transformer_blocks.{i}"
+        for nrm in ("norm1", "norm2"):
+            shapes[f"{b}.{nrm}.linear.weight"] = (6 * d, te)
+            shapes[f"{b}.{nrm}.linear.bias"] = (6 * d,)
+            shapes[f"{b}.{nrm}.norm.weight"] = (d,)
+            shapes[f"{b}.{nrm}.norm.bias"] = (d,)
+        for proj in ("to_q", "to_k", "to_v", "to_out.0"):
+            shapes[f"{b}.attn1.{proj}.weight"] = (d, d)
+            shapes[f"{b}.attn1.{proj}.bias"] = (d,)
+        for nrm in ("norm_q", "norm_k"):
+            shapes[f"{b}.attn1.{nrm}.weight"] = (hd,)
+            shapes[f"{b}.attn1.{nrm}.bias"] = (hd,)
+        shapes[f"{b}.ff.net.0.proj.weight"] = (4 * d, d)
+        shapes[f"{b}.ff.net.0.proj.bias"] = (4 * d,)
+        shapes[f"{b}.ff.net.2.weight"] = (d, 4 * d)
+        shapes[f"{b}.ff.net.2.bias"] = (d,)
+    return shapes
+
+
+def make_cog_state_dict(cfg: dict, seed: int = 0, dtype: torch.dtype = torch.float32, device="cpu"):
+    sd = make_state_dict(cog_param_shapes(cfg), seed, dtype, (), device)
+    if "patch_embed.pos_embedding" in sd:
+        sd["patch_embed.pos_embedding"][:, : cfg["max_text_seq_length"]] = 0  # text rows are zeros, embeddings.py:710-713
+    return sd
+
+
+def make_cog_inputs(cfg: dict, latent_frames: int, height: int, width: int, n_id: int = 1, batch: int = 2,
+                    text_len: Optional[int] = None, t_value: float = 500.0, seed: int = 0,
+                    dtype: torch.dtype = torch.float32, device="cpu"):
+    """[B, F+n_id, 48, H, W] = cat(noisy‖ID, image‖0, traj‖0) on the channel axis
+    (pipelines/pipeline_cogvideox_i2v_motion_FrameINO.py:856-881); scalar timestep per sample."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed + 2000)
+    c3 = cfg["in_channels"] // 3
+    f_all = latent_frames + n_id
+    parts = [torch.randn(batch, f_all, c3, height, width, generator=gen, device=device) for _ in range(3)]
+    if n_id > 0:
+        parts[1][:, latent_frames:] = 0
+        parts[2][:, latent_frames:] = 0
+    hidden = torch.cat(parts, dim=2).to(dtype)
+    tl = cfg["max_text_seq_length"] if text_len is None else text_len
+    text = torch.randn(batch, tl, cfg["text_embed_dim"], generator=gen, device=device).to(dtype)
+    ts = torch.full((batch,), float(t_value), device=device)
+    return hidden, ts, text

@@ -1,0 +1,343 @@
+"""B200-native ``WanTransformer3DModel`` — drop-in for the reference class of the same name
+(reference architecture/transformer_wan.py:353-552): same constructor config, same ``forward`` signature and return
+type, same diffusers state-dict key names, same attributes the FrameINO pipeline reads (``.config``, ``.dtype``,
+``.cache_context``). The forward issues only frameino_b200 CUDA kernels.
+
+What changes relative to the reference arithmetic (and why it is still the same function):
+  * the time MLP runs on the UNIQUE timestep values and tokens index the result (the reference recomputes it per
+    token, transformer_wan.py:175-183, :317-319; bit-identical per row, removes ~3.8 TFLOP and ~60 GB of HBM traffic);
+  * q/k/v projections run as one GEMM over a concatenated weight; LayerNorm+modulate, RMSNorm+RoPE and the gated
+    residuals are fused kernels / GEMM epilogues with the reference's cast points preserved.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Any, Dict, Optional, Tuple, Union
+
+import torch
+from torch import nn
+
+from . import ops
+from .modules import Attention, FeedForward, ModelBase, TextProjection, TimestepEmbedding, WeightOnlyNorm, logger
+from .processors import FinoWanAttnProcessor
+
+
+@dataclass
+class Transformer2DModelOutput:
+    """diffusers.models.modeling_outputs.Transformer2DModelOutput stand-in (attribute + index access)."""
+
+    sample: torch.Tensor
+
+    def __getitem__(self, i):
+        return (self.sample,)[i]
+
+
+def _rope_1d(dim: int, max_len: int, theta: float = 10000.0) -> Tuple[torch.Tensor, torch.Tensor]:
+    # embeddings.py:1153-1207 (use_real, repeat_interleave_real, float64 frequencies)
+    freqs = 1.0 / (theta ** (torch.arange(0, dim, 2, dtype=torch.float64)[: dim // 2] / dim))
+    ang = torch.outer(torch.arange(max_len, dtype=torch.float64), freqs)
+    return ang.cos().repeat_interleave(2, dim=1).float(), ang.sin().repeat_interleave(2, dim=1).float()
+
+
+class WanRotaryPosEmbed(nn.Module):
+    """3-D RoPE tables (transformer_wan.py:192-253). ``forward`` returns ``(cos, sin)`` each [1, 1, N, head_dim]
+    fp32 in (frame, height, width) token order; the gathered table is cached per latent shape."""
+
+    def __init__(self, attention_head_dim: int, patch_size: Tuple[int, int, int], max_seq_len: int,
+                 theta: float = 10000.0):
+        super().__init__()
+        self.attention_head_dim = attention_head_dim
+        self.patch_size = tuple(patch_size)
+        self.max_seq_len = max_seq_len
+        h_dim = w_dim = 2 * (attention_head_dim // 6)
+        t_dim = attention_head_dim - h_dim - w_dim
+        tabs = [_rope_1d(d, max_seq_len, theta) for d in (t_dim, h_dim, w_dim)]
+        self.register_buffer("freqs_cos", torch.cat([t[0] for t in tabs], dim=1), persistent=False)
+        self.register_buffer("freqs_sin", torch.cat([t[1] for t in tabs], dim=1), persistent=False)
+        self._cache: Dict[Any, Tuple[torch.Tensor, torch.Tensor]] = {}
+
+    def forward(self, hidden_states: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        _, _, f, h, w = hidden_states.shape
+        key = (f, h, w, self.freqs_cos.device)
+        hit = self._cache.get(key)
+        if hit is not None:
+            return hit
+        p_t, p_h, p_w = self.patch_size
+        ppf, pph, ppw = f // p_t, h // p_h, w // p_w
+        d = self.attention_head_dim
+        split = [d - 2 * (d // 3), d // 3, d // 3]
+        if split[1] != 2 * (d // 6):
+            raise ValueError(f"attention_head_dim={d}: RoPE band split {split} disagrees with the table construction "
+                             "(the reference has the same restriction, transformer_wan.py:206-207 vs :233-237)")
+        out = []
+        for tab in (self.freqs_cos, self.freqs_sin):
+            tf, th, tw = tab.split(split, dim=1)
+            tf = tf[:ppf].view(ppf, 1, 1, -1).expand(ppf, pph, ppw, -1)
+            th = th[:pph].view(1, pph, 1, -1).expand(ppf, pph, ppw, -1)
+            tw = tw[:ppw].view(1, 1, ppw, -1).expand(ppf, pph, ppw, -1)
+            out.append(torch.cat([tf, th, tw], dim=-1).reshape(1, 1, ppf * pph * ppw, -1).contiguous())
+        self._cache = {key: (out[0], out[1])}
+        return out[0], out[1]
+
+
+class WanTimeTextImageEmbedding(nn.Module):
+    """Parameter layout of transformer_wan.py:146-189 (time_embedder, time_proj, text_embedder)."""
+
+    def __init__(self, dim: int, time_freq_dim: int, time_proj_dim: int, text_embed_dim: int,
+                 image_embed_dim: Optional[int] = None):
+        super().__init__()
+        if image_embed_dim is not None:
+            raise NotImplementedError("image_dim (Wan2.1 I2V CLIP branch) is not part of the FrameINO Wan2.2 path")
+        self.time_freq_dim = time_freq_dim
+        self.time_embedder = TimestepEmbedding(time_freq_dim, dim)
+        self.time_proj = nn.Linear(dim, time_proj_dim)
+        self.text_embedder = TextProjection(text_embed_dim, dim)
+        self.image_embedder = None
+
+
+class WanTransformerBlock(nn.Module):
+    """transformer_wan.py:257-350. Parameters only differ from the reference in that norm layers without affine
+    parameters hold nothing; ``forward`` launches the fused kernels."""
+
+    def __init__(self, dim: int, ffn_dim: int, num_heads: int, qk_norm: str = "rms_norm_across_heads",
+                 cross_attn_norm: bool = False, eps: float = 1e-6, added_kv_proj_dim: Optional[int] = None):
+        super().__init__()
+        if added_kv_proj_dim is not None:
+            raise NotImplementedError("added_kv_proj_dim (Wan2.1 I2V) is not part of the FrameINO Wan2.2 path")
+        self.eps = eps
+        self.norm1 = WeightOnlyNorm(dim, eps, elementwise_affine=False)
+        self.attn1 = Attention(dim, num_heads, dim // num_heads, qk_norm, eps, processor=FinoWanAttnProcessor())
+        self.attn2 = Attention(dim, num_heads, dim // num_heads, qk_norm, eps, processor=FinoWanAttnProcessor())
+        self.norm2 = WeightOnlyNorm(dim, eps, elementwise_affine=True, bias=True) if cross_attn_norm else nn.Identity()
+        self.ffn = FeedForward(dim, ffn_dim)
+        self.norm3 = WeightOnlyNorm(dim, eps, elementwise_affine=False)
+        self.scale_shift_table = nn.Parameter(torch.randn(1, 6, dim) / dim ** 0.5)
+
+    def forward(self, hidden_states: torch.Tensor, encoder_hidden_states: torch.Tensor, mod: torch.Tensor,
+                row_index: Optional[torch.Tensor], rows_per_group: int, rotary_emb) -> torch.Tensor:
+        """``mod``: fp32 [R, 6*dim] = scale_shift_table + timestep_proj rows (shift, scale, gate, c_shift, c_scale,
+        c_gate). ``hidden_states`` [B, N, dim] is updated in place and returned."""
+        x = hidden_states
+        dim = x.shape[-1]
+        shift, scale, gate = mod[:, 0:dim], mod[:, dim:2 * dim], mod[:, 2 * dim:3 * dim]
+        c_shift, c_scale, c_gate = mod[:, 3 * dim:4 * dim], mod[:, 4 * dim:5 * dim], mod[:, 5 * dim:6 * dim]
+        sel = dict(row_index=row_index, rows_per_group=rows_per_group)
+
+        # 1. self-attention (:334-336)
+        h = ops.ln_modulate(x, self.eps, shift=shift, scale=scale, **sel)
+        if isinstance(self.attn1.processor, FinoWanAttnProcessor):
+            x = self.attn1(hidden_states=h, rotary_emb=rotary_emb, fino_residual=(x, gate, row_index, rows_per_group))
+        else:  # foreign processor plugged in through set_processor: keep the reference dataflow
+            a = self.attn1(hidden_states=h, rotary_emb=rotary_emb)
+            x = ops.gate_residual(x, a.contiguous(), gate, out=x, **sel)
+
+        # 2. cross-attention (:339-341)
+        if isinstance(self.norm2, WeightOnlyNorm):
+            h = ops.ln_modulate(x, self.eps, gamma=self.norm2.weight, beta=self.norm2.bias, out=h)
+        else:
+            h = x
+        if isinstance(self.attn2.processor, FinoWanAttnProcessor):
+            x = self.attn2(hidden_states=h, encoder_hidden_states=encoder_hidden_states,
+                           fino_residual=(x, None, None, 0))
+        else:
+            a = self.attn2(hidden_states=h, encoder_hidden_states=encoder_hidden_states)
+            x = ops.gate_residual(x, a.contiguous(), out=x)
+
+        # 3. feed-forward (:344-348)
+        h = ops.ln_modulate(x, self.eps, shift=c_shift, scale=c_scale, out=h if h is not x else None, **sel)
+        up, down = self.ffn.net[0].proj, self.ffn.net[2]
+        f = ops.linear(h, up.weight, up.bias, epilogue=ops.EPI_GELU_TANH)
+        x = ops.linear(f, down.weight, down.bias, epilogue=ops.EPI_GATE_RESIDUAL, residual=x, gate=c_gate, out=x, **sel)
+        return x
+
+
+class WanTransformer3DModel(ModelBase):
+    """Drop-in for reference ``architecture.transformer_wan.WanTransformer3DModel`` (see module docstring)."""
+
+    _supports_gradient_checkpointing = False
+    _skip_layerwise_casting_patterns = ["patch_embedding", "condition_embedder", "norm"]
+    _no_split_modules = ["WanTransformerBlock"]
+    _keep_in_fp32_modules = ["time_embedder", "scale_shift_table", "norm1", "norm2", "norm3"]
+    _keys_to_ignore_on_load_unexpected = ["norm_added_q"]
+    _repeated_blocks = ["WanTransformerBlock"]
+
+    def __init__(
+        self,
+        patch_size: Tuple[int, int, int] = (1, 2, 2),
+        num_attention_heads: int = 40,
+        attention_head_dim: int = 128,
+        in_channels: int = 16,
+        out_channels: int = 16,
+        text_dim: int = 4096,
+        freq_dim: int = 256,
+        ffn_dim: int = 13824,
+        num_layers: int = 40,
+        cross_attn_norm: bool = True,
+        qk_norm: Optional[str] = "rms_norm_across_heads",
+        eps: float = 1e-6,
+        image_dim: Optional[int] = None,
+        added_kv_proj_dim: Optional[int] = None,
+        rope_max_seq_len: int = 1024,
+        pos_embed_seq_len: Optional[int] = None,
+    ) -> None:
+        super().__init__()
+        self._register_config(
+            patch_size=tuple(patch_size), num_attention_heads=num_attention_heads,
+            attention_head_dim=attention_head_dim, in_channels=in_channels, out_channels=out_channels,
+            text_dim=text_dim, freq_dim=freq_dim, ffn_dim=ffn_dim, num_layers=num_layers,
+            cross_attn_norm=cross_attn_norm, qk_norm=qk_norm, eps=eps, image_dim=image_dim,
+            added_kv_proj_dim=added_kv_proj_dim, rope_max_seq_len=rope_max_seq_len, pos_embed_seq_len=pos_embed_seq_len,
+        )
+        inner_dim = num_attention_heads * attention_head_dim
+        out_channels = out_channels or in_channels
+        self.rope = WanRotaryPosEmbed(attention_head_dim, patch_size, rope_max_seq_len)
+        self.patch_embedding = nn.Conv3d(in_channels, inner_dim, kernel_size=patch_size, stride=patch_size)
+        self.condition_embedder = WanTimeTextImageEmbedding(inner_dim, freq_dim, inner_dim * 6, text_dim, image_dim)
+        self.blocks = nn.ModuleList(
+            [WanTransformerBlock(inner_dim, ffn_dim, num_attention_heads, qk_norm, cross_attn_norm, eps,
+                                 added_kv_proj_dim) for _ in range(num_layers)]
+        )
+        self.norm_out = WeightOnlyNorm(inner_dim, eps, elementwise_affine=False)
+        self.proj_out = nn.Linear(inner_dim, out_channels * math.prod(patch_size))
+        self.scale_shift_table = nn.Parameter(torch.randn(1, 2, inner_dim) / inner_dim ** 0.5)
+        self.gradient_checkpointing = False
+        self._sst_cache = None
+        self.sequence_parallel = None  # set by frameino_b200.ulysses.enable_sequence_parallel
+
+    # ------------------------------------------------------------------------------------------------------------
+    def to_inference_dtype(self, dtype: torch.dtype = torch.bfloat16) -> "WanTransformer3DModel":
+        """Casts like ``from_pretrained(torch_dtype=bf16)`` + ``_keep_in_fp32_modules`` (transformer_wan.py:393)."""
+        for name, p in self.named_parameters():
+            keep = any(k in name for k in self._keep_in_fp32_modules)
+            p.data = p.data.to(torch.float32 if keep else dtype)
+        return self
+
+    def _stacked_tables(self) -> torch.Tensor:
+        """[L, 6*D] fp32 copy of every block's scale_shift_table (refreshed if a table changes)."""
+        key = tuple((b.scale_shift_table.data_ptr(), b.scale_shift_table._version) for b in self.blocks)
+        if self._sst_cache is None or self._sst_cache[0] != key:
+            with torch.no_grad():
+                t = torch.stack([b.scale_shift_table.reshape(-1).float() for b in self.blocks]).contiguous()
+            self._sst_cache = (key, t)
+        return self._sst_cache[1]
+
+    def _conditioning(self, timestep: torch.Tensor, batch: int, tokens: int):
+        """De-duplicated time MLP. Returns (temb_rows fp32-of-bf16 [R, D], proj_rows fp32-of-bf16 [R, 6D],
+        row_index int32 [B*N] or None, rows_per_group)."""
+        ce = self.condition_embedder
+        if timestep.ndim == 2:  # [B, N] per-token timesteps (wan 2.2 ti2v, transformer_wan.py:490-492)
+            if timestep.shape != (batch, tokens):
+                raise ValueError(f"timestep shape {tuple(timestep.shape)} != (batch, tokens) = ({batch}, {tokens})")
+            uniq, inverse = torch.unique(timestep.reshape(-1).float(), return_inverse=True)
+            row_index = inverse.to(torch.int32).contiguous()
+            rows_per_group = 0
+        else:
+            if timestep.ndim == 0:
+                timestep = timestep.reshape(1).expand(batch)
+            uniq = timestep.reshape(-1).float().contiguous()
+            if uniq.numel() != batch:
+                raise ValueError(f"timestep has {uniq.numel()} entries for batch {batch}")
+            row_index = None
+            rows_per_group = tokens
+        r = uniq.numel()
+        te = ce.time_embedder
+        emb = ops.timestep_embedding(uniq.contiguous(), ce.time_freq_dim, True, 0.0)  # :175
+        dt = self.proj_out.weight.dtype
+        if r <= 8:
+            w_f32 = te.linear_1.weight.dtype == torch.float32
+            h = ops.linear_small_m(emb, te.linear_1.weight, te.linear_1.bias, act_out=1, round_in=not w_f32,
+                                   round_out=not w_f32)
+            temb = ops.linear_small_m(h, te.linear_2.weight, te.linear_2.bias, round_out=not w_f32)
+            temb = temb.to(dt).float()  # .type_as(encoder_hidden_states), :182
+            proj = ops.linear_small_m(temb, ce.time_proj.weight, ce.time_proj.bias, act_in=1, round_in=True,
+                                      round_out=True)  # :183 (bf16 module)
+        else:
+            # many distinct timesteps: run the MLP on the tensor cores in the model dtype
+            w1, w2 = te.linear_1, te.linear_2
+            h = ops.linear(emb.to(dt), w1.weight.to(dt), w1.bias.to(dt), epilogue=ops.EPI_SILU)
+            temb_b = ops.linear(h, w2.weight.to(dt), w2.bias.to(dt))
+            temb = temb_b.float()
+            s = torch.nn.functional.silu(temb_b)
+            proj = ops.linear(s, ce.time_proj.weight, ce.time_proj.bias).float()
+        return temb, proj, row_index, rows_per_group
+
+    # ------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(
+        self,
+        hidden_states: torch.Tensor,
+        timestep: torch.Tensor,
+        encoder_hidden_states: torch.Tensor,
+        encoder_hidden_states_image: Optional[torch.Tensor] = None,
+        return_dict: bool = True,
+        attention_kwargs: Optional[Dict[str, Any]] = None,
+    ) -> Union[Transformer2DModelOutput, Tuple[torch.Tensor]]:
+        if attention_kwargs is not None and attention_kwargs.get("scale", None) is not None:
+            logger.warning("Passing `scale` via `attention_kwargs` when not using the PEFT backend is ineffective.")
+        if encoder_hidden_states_image is not None:
+            raise NotImplementedError("encoder_hidden_states_image (Wan2.1 I2V) is not part of the FrameINO path")
+        if not hidden_states.is_cuda:
+            raise RuntimeError("frameino_b200 has no CPU path: move the model and inputs to a CUDA device")
+        dt = self.proj_out.weight.dtype
+        if dt != torch.bfloat16:
+            raise NotImplementedError(f"model dtype {dt}: call .to_inference_dtype(torch.bfloat16) first")
+        cfg = self.config
+        batch, channels, frames, height, width = hidden_states.shape
+        p_t, p_h, p_w = cfg.patch_size
+        ppf, pph, ppw = frames // p_t, height // p_h, width // p_w
+        tokens = ppf * pph * ppw
+        dim = cfg.num_attention_heads * cfg.attention_head_dim
+
+        rotary_emb = self.rope(hidden_states)  # :484
+        hs = hidden_states.to(dt)
+        rows = ops.patchify(hs, (batch, channels, frames, height, width), hs.stride(), (p_t, p_h, p_w))
+        temb, proj, row_index, rows_per_group = self._conditioning(timestep, batch, tokens)
+
+        sp = self.sequence_parallel
+        if sp is not None:  # Ulysses: every rank keeps a contiguous token slice (frameino_b200/ulysses.py)
+            if batch != 1:
+                raise NotImplementedError("sequence parallelism handles batch 1 (the Wan sampler runs B=1 forwards)")
+            sp.plan(tokens)
+            rows = sp.shard_rows(rows.view(1, tokens, -1)).view(sp.n_loc, -1)
+            if row_index is not None:
+                row_index = sp.shard_rows(row_index.view(1, tokens)).view(-1)
+            rotary_emb = tuple(sp.shard_rows(t, dim=2) for t in rotary_emb)
+            rows_per_group = sp.rows_per_group(rows_per_group)
+        n_loc = rows.shape[0] // batch
+
+        pe = self.patch_embedding
+        x = ops.linear(rows, pe.weight.view(dim, -1), pe.bias).view(batch, n_loc, dim)  # :486-487
+
+        ce = self.condition_embedder
+        text_in = encoder_hidden_states.to(dt)
+        t1, t2 = ce.text_embedder.linear_1, ce.text_embedder.linear_2
+        text = ops.linear(ops.linear(text_in, t1.weight, t1.bias, epilogue=ops.EPI_GELU_TANH), t2.weight, t2.bias)  # :185
+
+        # per-layer modulation rows: scale_shift_table + timestep_proj.float()  (:317-331)
+        mod_all = ops.build_mod_table(self._stacked_tables(), proj.contiguous(), len(self.blocks), 6 * dim)
+
+        taps = self.__dict__.get("_fino_taps")  # parity tests set this to a dict to collect per-layer outputs
+        if taps is not None:
+            taps["patch_embed"] = x.clone()
+            taps["text"] = text.clone()
+        for i, block in enumerate(self.blocks):  # :516-517
+            x = block(x, text, mod_all[i], row_index, rows_per_group, rotary_emb)
+            if taps is not None:
+                taps[f"blocks.{i}.out"] = x.clone()
+
+        # output modulation (:520-536): scale_shift_table[1,2,D] + temb
+        out_mod = ops.build_mod_table(self.scale_shift_table.reshape(1, 2 * dim).float(),
+                                      temb.repeat(1, 2).contiguous(), 1, 2 * dim)[0]
+        h = ops.ln_modulate(x, cfg.eps, shift=out_mod[:, :dim], scale=out_mod[:, dim:], row_index=row_index,
+                            rows_per_group=rows_per_group)
+        y = ops.linear(h, self.proj_out.weight, self.proj_out.bias)  # :537
+        if sp is not None:
+            y = sp.gather_rows(y)
+        c_out = y.shape[-1] // (p_t * p_h * p_w)
+        out = torch.empty(batch, c_out, frames, height, width, dtype=dt, device=x.device)
+        ops.unpatchify(y.view(batch * tokens, -1), out, (batch, c_out, frames, height, width), out.stride(),
+                       (p_t, p_h, p_w), channel_last=True)  # :539-543
+        if not return_dict:
+            return (out,)
+        return Transformer2DModelOutput(sample=out)

@@ -109,6 +109,10 @@ int fino_linear_small_m(const float* x, const void* w, const void* b, float* y, 
 int fino_build_mod_table(const float* table, const float* proj, float* out, int layers, int r, int cols,
                          int64_t table_layer_stride, void* stream);
 
+/* out[b][a][:] = in[a][b][:] with `inner` contiguous bf16 elements (multiple of 8) per (a,b): the pack / unpack step
+ * around the Ulysses head<->sequence all-to-all (new capability, no reference counterpart: SURVEY.md 8e). */
+int fino_swap01(const void* in, void* out, int64_t a, int64_t b, int64_t inner, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

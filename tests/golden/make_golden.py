@@ -1,0 +1,129 @@
+#!/usr/bin/env python
+"""Generates the golden vectors under tests/golden/ by EXECUTING THE REFERENCE'S OWN SOURCE FILES
+(/root/reference/architecture/{transformer_wan,cogvideox_transformer_3d,attention_processor,embeddings}.py) on CPU in
+fp32, with tests/golden/diffusers_shim standing in for the absent `diffusers` package (see its __init__ docstring for
+what is restated there). Weights and inputs come from the seeded recipe in frameino_b200/synth.py, so the fixtures
+hold only outputs and a few per-layer taps.
+
+Run in the build container (needs /root/reference):  python tests/golden/make_golden.py
+The GPU box never runs this; tests only read the committed *.pt files.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("FRAMEINO_REFERENCE", "/root/reference")
+sys.path.insert(0, os.path.join(HERE, "diffusers_shim"))
+sys.path.insert(0, REF)
+sys.path.insert(0, ROOT)
+
+from frameino_b200 import synth  # noqa: E402
+
+
+def _tap_summary(t: torch.Tensor) -> torch.Tensor:
+    """First 256 values + mean |x| + max |x| of a tapped tensor (keeps fixtures small)."""
+    f = t.detach().float().reshape(-1)
+    return torch.cat([f[:256], f.abs().mean()[None], f.abs().max()[None]])
+
+
+def wan_golden():
+    os.chdir(REF)  # the reference appends abspath('.') to sys.path for its local imports
+    from architecture.transformer_wan import WanTransformer3DModel  # the reference class itself
+
+    out = {}
+    for name, cfg, shape in (("tiny", synth.WAN_TINY, (5, 16, 16)), ("small", synth.WAN_SMALL, (3, 16, 16))):
+        torch.manual_seed(0)
+        model = WanTransformer3DModel(**cfg).eval()
+        sd = synth.make_wan_state_dict(cfg, seed=0)
+        missing, unexpected = model.load_state_dict(sd, strict=True)
+        taps = {}
+        hooks = []
+        for i, blk in enumerate(model.blocks):
+            hooks.append(blk.register_forward_hook(lambda m, a, o, i=i: taps.__setitem__(f"blocks.{i}.out", _tap_summary(o))))
+            hooks.append(blk.attn1.register_forward_hook(lambda m, a, o, i=i: taps.__setitem__(f"blocks.{i}.attn1", _tap_summary(o))))
+            hooks.append(blk.attn2.register_forward_hook(lambda m, a, o, i=i: taps.__setitem__(f"blocks.{i}.attn2", _tap_summary(o))))
+        f, h, w = shape
+        for mode in ("per_token", "scalar"):
+            hidden, ts, text = synth.make_wan_inputs(cfg, f, h, w, n_id=1, text_len=16, text_true_len=11,
+                                                     per_token_timestep=(mode == "per_token"))
+            with torch.no_grad():
+                y = model(hidden_states=hidden, timestep=ts, encoder_hidden_states=text, return_dict=False)[0]
+            out[f"{name}.{mode}.sample"] = y.clone()
+            for k, v in taps.items():
+                out[f"{name}.{mode}.{k}"] = v.clone()
+        for hk in hooks:
+            hk.remove()
+        # rope tables the reference module produces for this latent shape
+        cos, sin = model.rope(hidden)
+        out[f"{name}.rope_cos"] = cos.clone()
+        out[f"{name}.rope_sin"] = sin.clone()
+    torch.save(out, os.path.join(HERE, "wan_golden.pt"))
+    print("wrote wan_golden.pt:", {k: tuple(v.shape) for k, v in out.items() if k.endswith("sample")})
+
+
+def cog_golden():
+    os.chdir(REF)
+    from architecture.cogvideox_transformer_3d import CogVideoXTransformer3DModel
+    from architecture.embeddings import get_3d_rotary_pos_embed
+
+    cfg = synth.COG_TINY
+    torch.manual_seed(0)
+    model = CogVideoXTransformer3DModel(**cfg).eval()
+    sd = synth.make_cog_state_dict(cfg, seed=0)
+    model.load_state_dict(sd, strict=True)
+    out = {}
+    lat_f = (cfg["sample_frames"] - 1) // cfg["temporal_compression_ratio"] + 1
+    h, w = cfg["sample_height"], cfg["sample_width"]
+    hidden, ts, text = synth.make_cog_inputs(cfg, lat_f, h, w, n_id=1, batch=2)
+    gh, gw = h // cfg["patch_size"], w // cfg["patch_size"]
+    # pipelines/pipeline_cogvideox_i2v_motion_FrameINO.py:540-584 (1.0 checkpoints) + :834-839 (ID frame = frame-0 rows)
+    cos, sin = get_3d_rotary_pos_embed(cfg["attention_head_dim"], ((0, 0), (gh, gw)), (gh, gw), lat_f)
+    cos = torch.cat([cos, cos[: gh * gw]], dim=0)
+    sin = torch.cat([sin, sin[: gh * gw]], dim=0)
+    taps = {}
+    hooks = [blk.register_forward_hook(lambda m, a, o, i=i: taps.__setitem__(f"blocks.{i}.out", _tap_summary(o[0])))
+             for i, blk in enumerate(model.transformer_blocks)]
+    with torch.no_grad():
+        y = model(hidden_states=hidden, encoder_hidden_states=text, timestep=ts, image_rotary_emb=(cos, sin),
+                  return_dict=False)[0]
+    out["tiny.sample"] = y.clone()
+    out["tiny.rope_cos"] = cos.clone()
+    out["tiny.rope_sin"] = sin.clone()
+    for k, v in taps.items():
+        out[f"tiny.{k}"] = v.clone()
+    for hk in hooks:
+        hk.remove()
+    # fused-projection path of the reference (fuse_qkv_projections -> FusedCogVideoXAttnProcessor2_0)
+    model.fuse_qkv_projections()
+    with torch.no_grad():
+        y2 = model(hidden_states=hidden, encoder_hidden_states=text, timestep=ts, image_rotary_emb=(cos, sin),
+                   return_dict=False)[0]
+    out["tiny.sample_fused"] = y2.clone()
+    # non-default canvas: trilinear resize of the positional table (embeddings.py:782-798)
+    hidden_b, ts_b, text_b = synth.make_cog_inputs(cfg, lat_f, h + 4, w - 4, n_id=1, batch=1, seed=3)
+    gh2, gw2 = (h + 4) // cfg["patch_size"], (w - 4) // cfg["patch_size"]
+    cos2, sin2 = get_3d_rotary_pos_embed(cfg["attention_head_dim"], ((0, 0), (gh2, gw2)), (gh2, gw2), lat_f)
+    cos2 = torch.cat([cos2, cos2[: gh2 * gw2]], dim=0)
+    sin2 = torch.cat([sin2, sin2[: gh2 * gw2]], dim=0)
+    model.unfuse_qkv_projections()
+    with torch.no_grad():
+        y3 = model(hidden_states=hidden_b, encoder_hidden_states=text_b, timestep=ts_b, image_rotary_emb=(cos2, sin2),
+                   return_dict=False)[0]
+    out["tiny.sample_resized"] = y3.clone()
+    out["tiny.rope_cos_resized"] = cos2.clone()
+    out["tiny.rope_sin_resized"] = sin2.clone()
+    torch.save(out, os.path.join(HERE, "cog_golden.pt"))
+    print("wrote cog_golden.pt:", {k: tuple(v.shape) for k, v in out.items() if "sample" in k})
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["wan", "cog"]
+    if "wan" in which:
+        wan_golden()
+    if "cog" in which:
+        cog_golden()

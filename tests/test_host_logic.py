@@ -1,0 +1,134 @@
+"""Host-side mirror of the reference interface: state-dict layout, config surface, processor plumbing."""
+import inspect
+import os
+
+import pytest
+import torch
+
+from frameino_b200 import synth
+from frameino_b200.cogvideox import CogVideoXTransformer3DModel, sincos_pos_embed_3d
+from frameino_b200.modules import Attention
+from frameino_b200.processors import FinoCogVideoXAttnProcessor, FinoWanAttnProcessor
+from frameino_b200.ulysses import SequenceParallel
+from frameino_b200.wan import WanTransformer3DModel
+
+
+def test_wan_state_dict_layout_is_the_diffusers_layout():
+    m = WanTransformer3DModel(**synth.WAN_TINY)
+    shapes = synth.wan_param_shapes(synth.WAN_TINY)
+    sd = m.state_dict()
+    assert set(sd) == set(shapes)
+    for k, v in sd.items():
+        assert tuple(v.shape) == shapes[k], k
+    # non-persistent rope buffers, as transformer_wan.py:225-226
+    assert "rope.freqs_cos" not in sd and hasattr(m.rope, "freqs_cos")
+
+
+def test_cog_state_dict_layout_is_the_diffusers_layout():
+    m = CogVideoXTransformer3DModel(**synth.COG_TINY)
+    shapes = synth.cog_param_shapes(synth.COG_TINY)
+    sd = m.state_dict()
+    assert set(sd) == set(shapes)
+    for k, v in sd.items():
+        assert tuple(v.shape) == shapes[k], k
+
+
+def test_forward_signatures_match_the_reference():
+    wan = list(inspect.signature(WanTransformer3DModel.forward).parameters)
+    assert wan == ["self", "hidden_states", "timestep", "encoder_hidden_states", "encoder_hidden_states_image",
+                   "return_dict", "attention_kwargs"]  # transformer_wan.py:454-462
+    cog = list(inspect.signature(CogVideoXTransformer3DModel.forward).parameters)
+    assert cog == ["self", "hidden_states", "encoder_hidden_states", "timestep", "timestep_cond", "ofs",
+                   "image_rotary_emb", "attention_kwargs", "return_dict"]  # cogvideox_transformer_3d.py:446-456
+    wp = list(inspect.signature(FinoWanAttnProcessor.__call__).parameters)[:6]
+    assert wp == ["self", "attn", "hidden_states", "encoder_hidden_states", "attention_mask", "rotary_emb"]
+    cp = list(inspect.signature(FinoCogVideoXAttnProcessor.__call__).parameters)[:6]
+    assert cp == ["self", "attn", "hidden_states", "encoder_hidden_states", "attention_mask", "image_rotary_emb"]
+
+
+def test_config_and_pipeline_facing_attributes():
+    m = WanTransformer3DModel(**synth.WAN_TINY)
+    assert m.config.image_dim is None and m.config["patch_size"] == (1, 2, 2)
+    assert m.dtype == torch.float32
+    with m.cache_context("cond"):
+        pass
+    m.to_inference_dtype(torch.bfloat16)
+    assert m.dtype == torch.bfloat16
+    assert m.condition_embedder.time_embedder.linear_1.weight.dtype == torch.float32  # _keep_in_fp32_modules
+    assert m.blocks[0].scale_shift_table.dtype == torch.float32
+    assert m.blocks[0].norm2.weight.dtype == torch.float32
+    assert m.blocks[0].attn1.norm_q.weight.dtype == torch.bfloat16  # norm_q is NOT kept in fp32
+    c = CogVideoXTransformer3DModel(**synth.COG_TINY)
+    for k in ("patch_size", "patch_size_t", "sample_width", "sample_height", "sample_frames", "attention_head_dim",
+              "use_rotary_positional_embeddings", "ofs_embed_dim"):
+        assert k in c.config
+
+
+def test_processor_plumbing():
+    m = CogVideoXTransformer3DModel(**synth.COG_TINY)
+    procs = m.attn_processors
+    assert len(procs) == synth.COG_TINY["num_layers"]
+    assert all(k.endswith("attn1.processor") for k in procs)
+
+    class Foreign:
+        def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, image_rotary_emb=None):
+            return hidden_states, encoder_hidden_states
+
+    m.set_attn_processor(Foreign())
+    assert all(isinstance(p, Foreign) for p in m.attn_processors.values())
+    with pytest.raises(ValueError):
+        m.set_attn_processor({"x": Foreign()})
+    m.fuse_qkv_projections()
+    a = m.transformer_blocks[0].attn1
+    assert a.fused_projections and a.to_qkv.weight.shape == (3 * 256, 256)
+    assert torch.equal(a.to_qkv.weight[:256], a.to_q.weight)
+    m.unfuse_qkv_projections()
+    assert all(isinstance(p, Foreign) for p in m.attn_processors.values())
+
+
+def test_attention_forward_filters_kwargs_by_processor_signature():
+    seen = {}
+
+    class P:
+        def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, rotary_emb=None):
+            seen["rotary_emb"] = rotary_emb
+            return hidden_states
+
+    attn = Attention(64, 2, 32, "rms_norm_across_heads", 1e-6, processor=P())
+    out = attn(torch.zeros(1, 4, 64), rotary_emb="R", not_a_param=1)  # extra kwarg is dropped with a warning
+    assert out.shape == (1, 4, 64) and seen["rotary_emb"] == "R"
+    with pytest.raises(ValueError):
+        Attention(64, 2, 32, "l2", 1e-6)
+
+
+def test_models_refuse_cpu_inputs():
+    m = WanTransformer3DModel(**synth.WAN_TINY)
+    h, ts, text = synth.make_wan_inputs(synth.WAN_TINY, 2, 8, 8)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(h, ts, text)
+
+
+def test_unsupported_reference_branches_fail_loudly():
+    with pytest.raises(NotImplementedError):
+        WanTransformer3DModel(**{**synth.WAN_TINY, "image_dim": 1280})
+    with pytest.raises(NotImplementedError):
+        CogVideoXTransformer3DModel(**{**synth.COG_TINY, "patch_size_t": 2})
+
+
+def test_sincos_pos_embed_matches_reference_golden(golden_dir):
+    """The default (non-learned) pos_embedding buffer equals the reference's get_3d_sincos_pos_embed output: the
+    reference golden run adds it to the patch embedding, so check through the value recipe instead — here only the
+    closed form of one entry."""
+    pe = sincos_pos_embed_3d(64, grid_w=4, grid_h=3, frames=2, spatial_scale=1.875, temporal_scale=1.0)
+    assert pe.shape == (2, 12, 64)
+    # temporal band = first 16 dims: [sin(t*w_i) (8), cos(t*w_i) (8)]
+    t = 1.0
+    w = 1.0 / 10000 ** (torch.arange(8, dtype=torch.float64) / 8.0)
+    assert torch.allclose(pe[1, 0, :8].double(), torch.sin(t * w), atol=1e-6)
+    assert torch.allclose(pe[1, 0, 8:16].double(), torch.cos(t * w), atol=1e-6)
+
+
+def test_sequence_partition():
+    assert SequenceParallel.partition(28160, 8) == (3520, 28160)
+    assert SequenceParallel.partition(19126, 8) == (2391, 19128)
+    assert SequenceParallel.partition(10, 4) == (3, 12)

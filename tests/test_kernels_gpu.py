@@ -1,0 +1,261 @@
+"""-m gpu: every C-ABI kernel against the CPU oracle's primitives on the same seeded inputs (bf16 data; the oracle
+computes in fp32 / with the reference's cast points). Tolerances are bf16 rounding: rel err = max|a-b| / max|b|."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 1e-2  # one bf16 ulp is 2^-8 = 3.9e-3 relative; results are compared after an independent rounding
+
+
+@pytest.fixture(scope="module")
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from frameino_b200 import ops as _ops
+
+    return _ops
+
+
+def bf(*shape, scale=1.0, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).bfloat16()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,dim", [(1, 8), (37, 256), (513, 3072), (64, 5120)])
+def test_ln_modulate_vs_oracle(ops, rows, dim):
+    from oracle.wan_oracle import fp32_layer_norm
+
+    x = bf(rows, dim, scale=2.0)
+    r = 3
+    tab = torch.randn(r, 6 * dim, generator=torch.Generator().manual_seed(1)) * 0.5
+    ridx = torch.randint(0, r, (rows,), generator=torch.Generator().manual_seed(2)).int()
+    shift, scale = tab[:, :dim], tab[:, dim:2 * dim]
+    ref = (fp32_layer_norm(x.float(), None, None, 1e-6) * (1 + scale[ridx.long()]) + shift[ridx.long()]).bfloat16()
+    tc = tab.cuda()
+    out = ops.ln_modulate(x.cuda(), 1e-6, shift=tc[:, :dim], scale=tc[:, dim:2 * dim], row_index=ridx.cuda())
+    assert rel_err(out, ref) <= BF16_TOL
+    g, b = torch.randn(dim), torch.randn(dim)
+    ref2 = fp32_layer_norm(x.float(), g, b, 1e-6).bfloat16()
+    out2 = ops.ln_modulate(x.cuda(), 1e-6, gamma=g.cuda(), beta=b.cuda())
+    assert rel_err(out2, ref2) <= BF16_TOL
+    # scalar-timestep form: one modulation row per group of rows
+    per = (rows + r - 1) // r
+    gi = (torch.arange(rows) // per).long()
+    ref3 = (fp32_layer_norm(x.float(), None, None, 1e-6) * (1 + scale[gi]) + shift[gi]).bfloat16()
+    out3 = ops.ln_modulate(x.cuda(), 1e-6, shift=tc[:, :dim], scale=tc[:, dim:2 * dim], rows_per_group=per)
+    assert rel_err(out3, ref3) <= BF16_TOL
+
+
+def test_ln_bf16_module_flow_vs_torch(ops):
+    """CogVideoXLayerNormZero body: bf16 LayerNorm, then bf16 (1+scale) multiply and shift add."""
+    rows, dim = 300, 3072
+    x = bf(rows, dim, scale=1.5)
+    g, b = bf(dim, seed=3), bf(dim, seed=4)
+    sc, sh = bf(2, dim, scale=0.3, seed=5), bf(2, dim, scale=0.3, seed=6)
+    gi = (torch.arange(rows) // 150).long()
+    ref = F.layer_norm(x, (dim,), g, b, 1e-5) * (1 + sc)[gi] + sh[gi]
+    out = ops.ln_modulate(x.cuda(), 1e-5, gamma=g.float().cuda(), beta=b.float().cuda(), shift=sh.float().cuda(),
+                          scale=sc.float().cuda(), rows_per_group=150, bf16_steps=True)
+    assert rel_err(out, ref) <= BF16_TOL
+
+
+def test_gate_residual(ops):
+    x, y = bf(515, 768), bf(515, 768, seed=1)
+    gate = torch.randn(2, 768)
+    ridx = torch.randint(0, 2, (515,)).int()
+    ref = (x.float() + y * gate[ridx.long()]).bfloat16()
+    out = ops.gate_residual(x.cuda(), y.cuda(), gate.cuda(), row_index=ridx.cuda())
+    assert rel_err(out, ref) <= BF16_TOL
+    assert rel_err(ops.gate_residual(x.cuda(), y.cuda()), x + y) <= BF16_TOL
+
+
+@pytest.mark.parametrize("b,n,h,d", [(1, 384, 8, 32), (2, 300, 24, 128), (1, 77, 4, 128)])
+def test_qk_rmsnorm_rope_vs_oracle(ops, b, n, h, d):
+    from oracle.wan_oracle import apply_wan_rope, rms_norm
+
+    dm = h * d
+    qkv = bf(b, n, 3 * dm)
+    wq, wk = (1 + 0.1 * torch.randn(dm)).bfloat16(), (1 + 0.1 * torch.randn(dm)).bfloat16()
+    ang = torch.rand(n, d // 2) * 6.28
+    cos = ang.cos().repeat_interleave(2, dim=1).contiguous()
+    sin = ang.sin().repeat_interleave(2, dim=1).contiguous()
+
+    def ref(x, w):
+        y = rms_norm(x, w, 1e-6).unflatten(2, (h, -1)).transpose(1, 2)
+        y = apply_wan_rope(y, cos[None, None], sin[None, None])
+        return y.transpose(1, 2).flatten(2)
+
+    rq, rk = ref(qkv[..., :dm], wq), ref(qkv[..., dm:2 * dm], wk)
+    g = qkv.cuda()
+    ops.qk_norm_rope(g[..., :dm], wq.cuda(), g[..., dm:2 * dm], wk.cuda(), h, rope_mode=ops.ROPE_WAN, cos=cos.cuda(),
+                     sin=sin.cuda(), seq_len=n)
+    assert rel_err(g[..., :dm], rq) <= BF16_TOL
+    assert rel_err(g[..., dm:2 * dm], rk) <= BF16_TOL
+    assert torch.equal(g[..., 2 * dm:].cpu(), qkv[..., 2 * dm:])  # V untouched
+    # cross-attention form: different row counts, no rope
+    q2, k2 = bf(n, dm, seed=7), bf(16, dm, seed=8)
+    gq, gk = q2.cuda(), k2.cuda()
+    ops.qk_norm_rope(gq, wq.cuda(), gk, wk.cuda(), h)
+    assert rel_err(gq, rms_norm(q2, wq, 1e-6)) <= BF16_TOL
+    assert rel_err(gk, rms_norm(k2, wk, 1e-6)) <= BF16_TOL
+
+
+def test_qk_layernorm_rope_cog_vs_oracle(ops):
+    from oracle.cog_oracle import apply_cog_rope
+
+    b, text, nv, h, d = 2, 10, 150, 6, 64
+    s, dm = text + nv, h * d
+    qkv = bf(b, s, 3 * dm)
+    w, bb = (1 + 0.1 * torch.randn(d)).bfloat16(), (0.1 * torch.randn(d)).bfloat16()
+    ang = torch.rand(nv, d // 2) * 6.28
+    cos = ang.cos().repeat_interleave(2, dim=1).contiguous()
+    sin = ang.sin().repeat_interleave(2, dim=1).contiguous()
+
+    def ref(x):
+        y = F.layer_norm(x.view(b, s, h, d).transpose(1, 2), (d,), w, bb, 1e-6).clone()
+        y[:, :, text:] = apply_cog_rope(y[:, :, text:], cos, sin)
+        return y.transpose(1, 2).reshape(b, s, dm)
+
+    rq, rk = ref(qkv[..., :dm]), ref(qkv[..., dm:2 * dm])
+    g = qkv.cuda()
+    ops.qk_norm_rope(g[..., :dm], w.cuda(), g[..., dm:2 * dm], w.cuda(), h, b0=bb.cuda(), b1=bb.cuda(),
+                     norm_mode=ops.QK_LAYERNORM_PER_HEAD, rope_mode=ops.ROPE_COGVIDEOX, cos=cos.cuda(), sin=sin.cuda(),
+                     seq_len=s, rope_skip=text)
+    assert rel_err(g[..., :dm], rq) <= BF16_TOL
+    assert rel_err(g[..., dm:2 * dm], rk) <= BF16_TOL
+
+
+@pytest.mark.parametrize("m,n,k", [(1, 8, 8), (128, 256, 64), (300, 192, 384), (1000, 3072, 1024), (2, 18432, 512),
+                                   (4097, 264, 136)])
+def test_gemm_vs_oracle(ops, m, n, k):
+    a = bf(m, k)
+    w = bf(n, k, scale=1 / math.sqrt(k), seed=1)
+    bias = bf(n, seed=2)
+    ref = F.linear(a.float(), w.float(), bias.float())
+    assert rel_err(ops.linear(a.cuda(), w.cuda(), bias.cuda()), ref) <= BF16_TOL
+    assert rel_err(ops.linear(a.cuda(), w.cuda(), None), F.linear(a.float(), w.float())) <= BF16_TOL
+    assert rel_err(ops.linear(a.cuda(), w.cuda(), bias.cuda(), out_dtype=torch.float32), ref) <= 1e-4
+
+
+def test_gemm_epilogues_vs_oracle(ops):
+    m, n, k = 777, 1024, 512
+    a, w, bias = bf(m, k), bf(n, k, scale=1 / math.sqrt(k), seed=1), bf(n, seed=2)
+    lin = F.linear(a.float(), w.float(), bias.float()).bfloat16()
+    ag, wg, bg = a.cuda(), w.cuda(), bias.cuda()
+    assert rel_err(ops.linear(ag, wg, bg, epilogue=ops.EPI_GELU_TANH), F.gelu(lin, approximate="tanh")) <= BF16_TOL
+    assert rel_err(ops.linear(ag, wg, bg, epilogue=ops.EPI_SILU), F.silu(lin)) <= BF16_TOL
+    x = bf(m, n, seed=3)
+    gate = torch.randn(3, n)
+    ridx = torch.randint(0, 3, (m,)).int()
+    ref = (x.float() + lin * gate[ridx.long()]).bfloat16()  # transformer_wan.py:336
+    out = ops.linear(ag, wg, bg, epilogue=ops.EPI_GATE_RESIDUAL, residual=x.cuda(), gate=gate.cuda(),
+                     row_index=ridx.cuda())
+    assert rel_err(out, ref) <= BF16_TOL
+    xc = x.cuda().clone()  # in place, as the block uses it
+    ops.linear(ag, wg, bg, epilogue=ops.EPI_GATE_RESIDUAL, residual=xc, gate=gate.cuda(), row_index=ridx.cuda(), out=xc)
+    assert rel_err(xc, ref) <= BF16_TOL
+    out = ops.linear(ag, wg, bg, epilogue=ops.EPI_GATE_RESIDUAL, residual=x.cuda())  # transformer_wan.py:341
+    assert rel_err(out, x + lin) <= BF16_TOL
+    gb = gate.bfloat16()
+    ref_cog = x + gb[ridx.long()] * lin  # cogvideox_transformer_3d.py:146 (all bf16)
+    out = ops.linear(ag, wg, bg, epilogue=ops.EPI_GATE_RESIDUAL, residual=x.cuda(), gate=gb.float().cuda(),
+                     row_index=ridx.cuda(), round_product=True)
+    assert rel_err(out, ref_cog) <= BF16_TOL
+
+
+def _sdpa_ref(q, k, v, heads):
+    from oracle.wan_oracle import sdpa
+
+    b, nq, inner = q.shape
+    d = inner // heads
+    o = sdpa(q.view(b, nq, heads, d).transpose(1, 2).float(), k.view(b, -1, heads, d).transpose(1, 2).float(),
+             v.view(b, -1, heads, d).transpose(1, 2).float())
+    return o.transpose(1, 2).reshape(b, nq, inner)
+
+
+@pytest.mark.parametrize("hd", [128, 64])
+@pytest.mark.parametrize("b,h,nq,nk", [(1, 1, 1, 1), (1, 1, 256, 128), (1, 2, 130, 257), (2, 3, 1000, 1000),
+                                       (1, 2, 300, 16), (1, 2, 2048, 2048)])
+def test_attention_vs_oracle(ops, hd, b, h, nq, nk):
+    dm = h * hd
+    q, k, v = bf(b, nq, dm), bf(b, nk, dm, seed=1), bf(b, nk, dm, seed=2)
+    out = ops.attention(q.cuda(), k.cuda(), v.cuda(), h)
+    assert rel_err(out, _sdpa_ref(q, k, v, h)) <= BF16_TOL
+
+
+@pytest.mark.parametrize("hd", [128, 64])
+def test_attention_strided_fused_qkv_and_peaky_scores(ops, hd):
+    b, h, n = 2, 3, 700
+    dm = h * hd
+    qkv = bf(b, n, 3 * dm, scale=2.5)  # |scores| up to ~70: exercises the lazy-rescale path of the online softmax
+    g = qkv.cuda()
+    out = ops.attention(g[..., :dm], g[..., dm:2 * dm], g[..., 2 * dm:], h)
+    ref = _sdpa_ref(qkv[..., :dm].contiguous(), qkv[..., dm:2 * dm].contiguous(), qkv[..., 2 * dm:].contiguous(), h)
+    assert rel_err(out, ref) <= BF16_TOL
+
+
+def test_patchify_unpatchify_vs_oracle(ops):
+    b, c, f, h, w, dm = 1, 32, 6, 16, 16, 256
+    x = bf(b, c, f, h, w)
+    wt, bias = bf(dm, c, 1, 2, 2, scale=0.1, seed=1), bf(dm, seed=2)
+    ref = F.conv3d(x.float(), wt.float(), bias.float(), stride=(1, 2, 2)).flatten(2).transpose(1, 2).reshape(-1, dm)
+    xg = x.cuda()
+    rows = ops.patchify(xg, (b, c, f, h, w), xg.stride(), (1, 2, 2))
+    y = ops.linear(rows, wt.cuda().view(dm, -1), bias.cuda())
+    assert rel_err(y, ref) <= BF16_TOL
+    # Wan unpatchify (transformer_wan.py:539-543)
+    co = 16
+    r = bf(b * f * (h // 2) * (w // 2), 4 * co, seed=3)
+    ref = r.reshape(b, f, h // 2, w // 2, 1, 2, 2, -1).permute(0, 7, 1, 4, 2, 5, 3, 6).flatten(6, 7).flatten(4, 5).flatten(2, 3)
+    out = torch.empty(b, co, f, h, w, dtype=torch.bfloat16, device="cuda")
+    ops.unpatchify(r.cuda(), out, (b, co, f, h, w), out.stride(), (1, 2, 2), True)
+    assert torch.equal(out.cpu(), ref)
+    # CogVideoX unpatchify (cogvideox_transformer_3d.py:549-550), output layout [B, F, C, H, W]
+    r = bf(2 * 3 * 4 * 6, 16 * 4, seed=4)
+    ref = r.reshape(2, 3, 4, 6, -1, 2, 2).permute(0, 1, 4, 2, 5, 3, 6).flatten(5, 6).flatten(3, 4)
+    out = torch.empty(2, 3, 16, 8, 12, dtype=torch.bfloat16, device="cuda")
+    st = out.stride()
+    ops.unpatchify(r.cuda(), out, (2, 16, 3, 8, 12), (st[0], st[2], st[1], st[3], st[4]), (1, 2, 2), False)
+    assert torch.equal(out.cpu(), ref)
+
+
+def test_timestep_embedding_and_small_linear_vs_oracle(ops):
+    from oracle.wan_oracle import sinusoidal_embedding
+
+    t = torch.tensor([0.0, 500.0, 999.0, 37.5])
+    ref = sinusoidal_embedding(t, 256)
+    out = ops.timestep_embedding(t.cuda(), 256)
+    assert float((out.cpu() - ref).abs().max()) <= 2e-4  # sin/cos of arguments up to 1e3 in fp32
+    x = torch.randn(2, 256)
+    w, b = torch.randn(3072, 256) * 0.05, torch.randn(3072) * 0.1
+    ref = F.silu(F.linear(x, w, b))
+    assert rel_err(ops.linear_small_m(x.cuda(), w.cuda(), b.cuda(), act_out=1), ref) <= 1e-5
+    wb, bb = w.bfloat16(), b.bfloat16()
+    ref = F.linear(F.silu(x).bfloat16(), wb, bb)
+    out = ops.linear_small_m(x.cuda(), wb.cuda(), bb.cuda(), act_in=1, round_in=True, round_out=True)
+    assert rel_err(out, ref) <= BF16_TOL
+
+
+def test_swap01_and_mod_table(ops):
+    x = bf(6, 4, 64)
+    out = ops.swap01(x.cuda().view(-1), 6, 4, 64)
+    assert torch.equal(out.cpu(), x.transpose(0, 1).contiguous())
+    tab, proj = torch.randn(5, 6 * 64), torch.randn(3, 6 * 64)
+    o = ops.build_mod_table(tab.cuda(), proj.cuda(), 5, 6 * 64)
+    assert torch.equal(o.cpu(), tab[:, None] + proj[None])
+
+
+def test_invalid_arguments_raise(ops):
+    from frameino_b200._lib import FinoError
+
+    with pytest.raises(FinoError):
+        ops.attention(bf(1, 8, 96).cuda(), bf(1, 8, 96).cuda(), bf(1, 8, 96).cuda(), 1)  # head_dim 96 unsupported
+    with pytest.raises(FinoError):
+        ops.linear(bf(4, 12).cuda(), bf(8, 12).cuda())  # K not a multiple of 8

@@ -1,0 +1,111 @@
+"""The CPU oracle against golden vectors produced by the reference's own source files (tests/golden/make_golden.py)."""
+import os
+
+import pytest
+import torch
+
+from frameino_b200 import synth
+from oracle import cog_oracle, wan_oracle
+
+
+@pytest.fixture(scope="module")
+def wan_golden(golden_dir):
+    return torch.load(os.path.join(golden_dir, "wan_golden.pt"))
+
+
+@pytest.fixture(scope="module")
+def cog_golden(golden_dir):
+    return torch.load(os.path.join(golden_dir, "cog_golden.pt"))
+
+
+WAN_CASES = [("tiny", synth.WAN_TINY, (5, 16, 16)), ("small", synth.WAN_SMALL, (3, 16, 16))]
+
+
+@pytest.mark.parametrize("name,cfg,shape", WAN_CASES)
+@pytest.mark.parametrize("mode", ["per_token", "scalar"])
+def test_wan_oracle_matches_reference_output(wan_golden, name, cfg, shape, mode):
+    sd = synth.make_wan_state_dict(cfg, seed=0)
+    hidden, ts, text = synth.make_wan_inputs(cfg, *shape, n_id=1, text_len=16, text_true_len=11,
+                                             per_token_timestep=(mode == "per_token"))
+    taps = {}
+    out = wan_oracle.wan_forward(sd, wan_oracle.WanConfig(**cfg), hidden, ts, text, taps=taps)
+    ref = wan_golden[f"{name}.{mode}.sample"]
+    assert out.shape == ref.shape
+    assert torch.allclose(out, ref, rtol=0, atol=1e-5), float((out - ref).abs().max())
+    for i in range(cfg["num_layers"]):
+        tap = taps[f"blocks.{i}.out"].float().reshape(-1)
+        g = wan_golden[f"{name}.{mode}.blocks.{i}.out"]
+        assert torch.allclose(tap[:256], g[:256], atol=1e-5)
+        assert abs(float(tap.abs().mean()) - float(g[256])) < 1e-5
+
+
+@pytest.mark.parametrize("name,cfg,shape", WAN_CASES)
+def test_wan_rope_tables_match_reference(wan_golden, name, cfg, shape):
+    cos, sin = wan_oracle.wan_rope(wan_oracle.WanConfig(**cfg), shape[0] + 1, shape[1], shape[2])
+    assert torch.equal(cos, wan_golden[f"{name}.rope_cos"])
+    assert torch.equal(sin, wan_golden[f"{name}.rope_sin"])
+
+
+def test_wan_rope_closed_form():
+    """Independent closed form: band (44, 42, 42) for d=128, pair i of a band rotates by pos * theta^(-2i/band)."""
+    cfg = wan_oracle.WanConfig(**synth.WAN_SMALL)
+    cos, sin = wan_oracle.wan_rope(cfg, 4, 16, 16)
+    f, h, w = 4, 8, 8
+    tok = (2 * h + 5) * w + 3  # frame 2, row 5, col 3
+    bands = [(44, 2), (42, 5), (42, 3)]
+    expect_c, expect_s = [], []
+    for dim, pos in bands:
+        for i in range(dim // 2):
+            a = pos * (10000.0 ** (-2.0 * i / dim))
+            expect_c += [torch.cos(torch.tensor(a, dtype=torch.float64))] * 2
+            expect_s += [torch.sin(torch.tensor(a, dtype=torch.float64))] * 2
+    assert torch.allclose(cos[0, 0, tok].double(), torch.stack(expect_c), atol=1e-6)
+    assert torch.allclose(sin[0, 0, tok].double(), torch.stack(expect_s), atol=1e-6)
+
+
+def test_wan_per_token_equals_scalar_when_uniform():
+    """Per-token timesteps that are all equal must reproduce the scalar-timestep branch (H1/H2 of SURVEY.md)."""
+    cfg = synth.WAN_TINY
+    sd = synth.make_wan_state_dict(cfg, seed=1)
+    hidden, ts, text = synth.make_wan_inputs(cfg, 3, 16, 16, per_token_timestep=True)
+    ts_uniform = torch.full_like(ts, 321.0)
+    ocfg = wan_oracle.WanConfig(**cfg)
+    a = wan_oracle.wan_forward(sd, ocfg, hidden, ts_uniform, text)
+    b = wan_oracle.wan_forward(sd, ocfg, hidden, torch.tensor([321.0]), text)
+    assert torch.allclose(a, b, atol=1e-5)
+
+
+def test_wan_patchify_is_a_gemm():
+    cfg = synth.WAN_TINY
+    sd = synth.make_wan_state_dict(cfg, seed=2)
+    x = torch.randn(1, 32, 3, 8, 8)
+    conv = torch.nn.functional.conv3d(x, sd["patch_embedding.weight"], sd["patch_embedding.bias"], stride=(1, 2, 2))
+    conv = conv.flatten(2).transpose(1, 2)
+    rows = x.reshape(1, 32, 3, 4, 2, 4, 2).permute(0, 2, 3, 5, 1, 4, 6).reshape(1, 48, 128)
+    gemm = rows @ sd["patch_embedding.weight"].reshape(256, -1).t() + sd["patch_embedding.bias"]
+    assert torch.allclose(conv, gemm, atol=1e-5)
+
+
+def test_cog_oracle_matches_reference_output(cog_golden):
+    cfg = synth.COG_TINY
+    sd = synth.make_cog_state_dict(cfg, seed=0)
+    hidden, ts, text = synth.make_cog_inputs(cfg, 3, 12, 16, n_id=1, batch=2)
+    cos, sin = cog_oracle.cog_rope_3d(64, (6, 8), 3, 1)
+    assert torch.equal(cos, cog_golden["tiny.rope_cos"]) and torch.equal(sin, cog_golden["tiny.rope_sin"])
+    taps = {}
+    out = cog_oracle.cog_forward(sd, cfg, hidden, text, ts, (cos, sin), taps=taps)
+    assert torch.allclose(out, cog_golden["tiny.sample"], atol=1e-5)
+    # the reference's fused-projection processor gives the same numbers as the unfused one
+    assert torch.allclose(cog_golden["tiny.sample_fused"], cog_golden["tiny.sample"], atol=1e-5)
+    for i in range(cfg["num_layers"]):
+        tap = taps[f"transformer_blocks.{i}.out"].float().reshape(-1)
+        assert torch.allclose(tap[:256], cog_golden[f"tiny.blocks.{i}.out"][:256], atol=1e-5)
+
+
+def test_cog_oracle_resized_canvas(cog_golden):
+    cfg = synth.COG_TINY
+    sd = synth.make_cog_state_dict(cfg, seed=0)
+    hidden, ts, text = synth.make_cog_inputs(cfg, 3, 16, 12, n_id=1, batch=1, seed=3)
+    cos, sin = cog_oracle.cog_rope_3d(64, (8, 6), 3, 1)
+    out = cog_oracle.cog_forward(sd, cfg, hidden, text, ts, (cos, sin))
+    assert torch.allclose(out, cog_golden["tiny.sample_resized"], atol=1e-4)
