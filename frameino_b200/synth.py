@@ -215,3 +215,28 @@ def make_cog_inputs(cfg: dict, latent_frames: int, height: int, width: int, n_id
     text = torch.randn(batch, tl, cfg["text_embed_dim"], generator=gen, device=device).to(dtype)
     ts = torch.full((batch,), float(t_value), device=device)
     return hidden, ts, text
+
+
+# ---- full-size construction without a CPU copy ------------------------------------------------------------------
+def build_wan_on_device(cfg: dict, seed: int = 0, device="cuda", dtype: torch.dtype = torch.bfloat16):
+    """Random-init ``frameino_b200.WanTransformer3DModel`` materialised directly on ``device`` (the 5B model would
+    need 20 GB of host RAM otherwise): parameters are created on the meta device, then filled one by one from the
+    seeded recipe with the ``from_pretrained(torch_dtype=bf16)`` + ``_keep_in_fp32_modules`` dtype policy."""
+    from .wan import WanRotaryPosEmbed, WanTransformer3DModel
+
+    with torch.device("meta"):
+        model = WanTransformer3DModel(**cfg)
+    shapes = wan_param_shapes(cfg)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    model.to_empty(device=device)
+    params = dict(model.named_parameters())
+    assert set(params) == set(shapes), "state-dict layout drifted from synth.wan_param_shapes"
+    with torch.no_grad():
+        for name in sorted(shapes):
+            keep = any(k in name for k in WAN_KEEP_FP32)
+            t = _fill(name, shapes[name], gen, device)
+            p = params[name]
+            p.data = t.to(torch.float32 if keep else dtype)
+    model.rope = WanRotaryPosEmbed(cfg["attention_head_dim"], cfg["patch_size"], cfg["rope_max_seq_len"]).to(device)
+    return model.eval()
