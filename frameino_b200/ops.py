@@ -118,11 +118,31 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
     assert d * heads == inner and k.shape == (b, nk, inner) and v.shape == (b, nk, inner)
     for t in (q, k, v):
         assert t.stride(2) == 1
+    if scale is None:
+        scale = d ** -0.5
+    if d not in (64, 128):
+        # The tcgen05 kernel is built for the production head dims (128 Wan, 64 CogVideoX). Other head dims (the tiny
+        # test config uses 32) are zero-padded per head to the next supported width: zero columns add nothing to
+        # Q K^T and the padded output columns are dropped, so the result is unchanged.
+        if d > 128 or d % 8 != 0:
+            raise _lib.FinoError(f"attention: head_dim {d} unsupported (multiples of 8 up to 128)")
+        dp = 64 if d < 64 else 128
+
+        def pad(t):
+            n = t.shape[1]
+            tp = torch.zeros(b, n, heads, dp, dtype=t.dtype, device=t.device)
+            tp[..., :d] = t.reshape(b, n, heads, d) if t.is_contiguous() else t.unflatten(2, (heads, d))
+            return tp.view(b, n, heads * dp)
+
+        op = attention(pad(q), pad(k), pad(v), heads, scale=scale)
+        res = op.view(b, nq, heads, dp)[..., :d].reshape(b, nq, inner)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
     if out is None:
         out = torch.empty(b, nq, inner, dtype=torch.bfloat16, device=q.device)
     assert out.shape == (b, nq, inner) and out.stride(2) == 1
-    if scale is None:
-        scale = d ** -0.5
     status = lib.fino_attention_fwd(
         q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), b, heads, nq, nk, d,
         q.stride(1), k.stride(1), v.stride(1), out.stride(1), q.stride(0), k.stride(0), v.stride(0), out.stride(0),

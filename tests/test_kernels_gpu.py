@@ -256,6 +256,6 @@ def test_invalid_arguments_raise(ops):
     from frameino_b200._lib import FinoError
 
     with pytest.raises(FinoError):
-        ops.attention(bf(1, 8, 96).cuda(), bf(1, 8, 96).cuda(), bf(1, 8, 96).cuda(), 1)  # head_dim 96 unsupported
+        ops.attention(bf(1, 8, 136).cuda(), bf(1, 8, 136).cuda(), bf(1, 8, 136).cuda(), 1)  # head_dim 136 unsupported
     with pytest.raises(FinoError):
         ops.linear(bf(4, 12).cuda(), bf(8, 12).cuda())  # K not a multiple of 8

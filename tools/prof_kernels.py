@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""Runs each hot kernel a few times at the Wan2.2-5B config-2 shapes so that `ncu -k regex:<name>` can capture it.
+Usage: python tools/prof_kernels.py [attn] [attn64] [gemm] [ffn] [ln] [qk]"""
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from frameino_b200 import ops  # noqa: E402
+
+which = sys.argv[1:] or ["attn", "gemm", "ln", "qk"]
+n, h, hd = 28160, 24, 128
+d = h * hd
+torch.manual_seed(0)
+if "attn" in which:
+    qkv = torch.randn(1, n, 3 * d, device="cuda").bfloat16()
+    o = torch.empty(1, n, d, device="cuda", dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.attention(qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:], h, out=o)
+if "attn64" in which:
+    n2, h2 = 19126, 48
+    qkv = torch.randn(1, n2, 3 * d, device="cuda").bfloat16()
+    for _ in range(3):
+        ops.attention(qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:], h2)
+if "gemm" in which:
+    a = torch.randn(n, d, device="cuda").bfloat16()
+    w = (torch.randn(3 * d, d, device="cuda") / math.sqrt(d)).bfloat16()
+    b = torch.randn(3 * d, device="cuda").bfloat16()
+    o = torch.empty(n, 3 * d, device="cuda", dtype=torch.bfloat16)
+    for _ in range(3):
+        ops.linear(a, w, b, out=o)
+if "ffn" in which:
+    f = 14336
+    a = torch.randn(n, d, device="cuda").bfloat16()
+    w = (torch.randn(f, d, device="cuda") / math.sqrt(d)).bfloat16()
+    b = torch.randn(f, device="cuda").bfloat16()
+    for _ in range(3):
+        y = ops.linear(a, w, b, epilogue=ops.EPI_GELU_TANH)
+if "ln" in which:
+    x = torch.randn(n, d, device="cuda").bfloat16()
+    tab = torch.randn(2, 6 * d, device="cuda")
+    ridx = torch.zeros(n, device="cuda", dtype=torch.int32)
+    ridx[880:] = 1
+    o = torch.empty_like(x)
+    for _ in range(3):
+        ops.ln_modulate(x, 1e-6, shift=tab[:, :d], scale=tab[:, d:2 * d], row_index=ridx, out=o)
+if "qk" in which:
+    qkv = torch.randn(1, n, 3 * d, device="cuda").bfloat16()
+    wq = torch.ones(d, device="cuda").bfloat16()
+    cos = torch.rand(n, hd, device="cuda")
+    sin = torch.rand(n, hd, device="cuda")
+    for _ in range(3):
+        ops.qk_norm_rope(qkv[..., :d], wq, qkv[..., d:2 * d], wq, h, rope_mode=ops.ROPE_WAN, cos=cos, sin=sin, seq_len=n)
+torch.cuda.synchronize()
+print("done", which)
