@@ -26,6 +26,7 @@ SIGNATURES = {
     "fino_set_device": (_I, [_I]),
     "fino_launch_count": (_L, []),
     "fino_gemm_bf16": (_I, [_P, _L, _P, _L, _P, _P, _L, _L, _I, _I, _I, _I, _I, _P, _L, _P, _L, _P, _L, _P]),
+    "fino_gemm_set_mode": (_I, [_I]),
     "fino_attention_fwd": (_I, [_P, _P, _P, _P, _I, _I, _L, _L, _I, _L, _L, _L, _L, _L, _L, _L, _L, _F, _P]),
     "fino_ln_modulate": (_I, [_P, _P, _L, _I, _L, _L, _F, _P, _P, _P, _P, _L, _P, _L, _I, _P]),
     "fino_gate_residual": (_I, [_P, _P, _P, _L, _I, _L, _L, _L, _P, _L, _P, _L, _I, _P]),

@@ -33,6 +33,7 @@ int linear_small_m(const float* x, const void* w, const void* b, float* y, int m
 int build_mod_table(const float* table, const float* proj, float* out, int layers, int r, int cols,
                     int64_t table_layer_stride, cudaStream_t stream);
 int swap01(const void* in, void* out, int64_t A, int64_t B, int64_t inner, cudaStream_t stream);
+void gemm_set_mode(int mode);
 }  // namespace fino
 
 static std::atomic<int64_t> g_launches{0};
@@ -149,6 +150,15 @@ int fino_linear_small_m(const float* x, const void* w, const void* b, float* y, 
 int fino_build_mod_table(const float* table, const float* proj, float* out, int layers, int r, int cols,
                          int64_t table_layer_stride, void* stream) {
   FINO_ENTRY(fino::build_mod_table(table, proj, out, layers, r, cols, table_layer_stride, (cudaStream_t)stream));
+}
+
+int fino_gemm_set_mode(int mode) {
+  if (mode < 0 || mode > 2) {
+    fino::set_last_error("fino_gemm_set_mode: mode %d out of range (0 auto, 1 single-CTA, 2 CTA-pair)", mode);
+    return fino::FINO_ERR_INVALID;
+  }
+  fino::gemm_set_mode(mode);
+  return 0;
 }
 
 int fino_swap01(const void* in, void* out, int64_t a, int64_t b, int64_t inner, void* stream) {

@@ -1,4 +1,4 @@
-// Persistent, warp-specialised bf16 GEMM for sm_100a:  C[M,N] = epilogue(A[M,K] * W[N,K]^T + bias)
+// Persistent, warp-specialised bf16 GEMMs for sm_100a:  C[M,N] = epilogue(A[M,K] * W[N,K]^T + bias)
 //
 // Replaces the nn.Linear calls of the reference hot path (cuBLAS via torch):
 //   to_q/to_k/to_v/to_out  reference architecture/transformer_wan.py:60-62,117
@@ -7,49 +7,26 @@
 // with the elementwise tails fused into the epilogue (bias, GELU-tanh, SiLU, gate*y + residual;
 // reference transformer_wan.py:336,341,348).
 //
-// Design (B200): one CTA per SM, 256 threads.
-//   warp 0        TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, 4-stage mbarrier ring)
-//   warp 1        MMA issuer     (one elected thread, tcgen05.mma cta_group::1 kind::f16, 128 x BN x 16)
-//   warp 2        TMEM allocator (2 accumulator stages x BN fp32 columns)
+// Two kernels, same roles per CTA (256 threads):
+//   warp 0        TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, mbarrier ring)
+//   warp 1        MMA issuer     (one elected thread, tcgen05.mma kind::f16)
+//   warp 2        TMEM allocator (2 accumulator stages)
 //   warps 4..7    epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> 16B global stores)
 // The accumulator is double buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1.
-#include "common.cuh"
-#include "ptx.cuh"
+//
+//   gemm_bf16_kernel<BN>     one CTA per SM, 128 x BN tile, cta_group::1.  Used for small problems.
+//   gemm2_bf16_kernel        CTA PAIR (cluster of 2 on one TPC), 256 x 256 tile, cta_group::2: each CTA stages its
+//                            own 128 rows of A and HALF of the W tile (128 of the 256 N rows); the pair's tensor
+//                            cores read the W halves from both SMs. That cuts shared-memory traffic per MMA from
+//                            12 KB to 8 KB per SM — the 1-CTA kernel was shared-memory-bandwidth bound (ncu:
+//                            l1tex 83 % busy, tensor pipe 57 %; profiles/r01_gemm_qkv_ncu.txt).
+#include "gemm_common.cuh"
 
 namespace fino {
 
-constexpr int GEMM_BM = 128;
-constexpr int GEMM_BK = 64;  // 64 bf16 = 128 B = one swizzle-128B row
-constexpr int GEMM_THREADS = 256;
-
-enum GemmEpilogue : int {
-  EPI_NONE = 0,           // C = acc (+bias)
-  EPI_GELU_TANH = 1,      // C = gelu_tanh(bf16(acc+bias))
-  EPI_SILU = 2,           // C = silu(bf16(acc+bias))
-  EPI_GATE_RESIDUAL = 3,  // C = residual + bf16(acc+bias) * gate[row_index[row]]   (gate optional => 1)
-};
-enum GemmFlags : int {
-  GEMM_FLAG_ROUND_PRODUCT = 1,  // round gate*y to bf16 before the residual add (CogVideoX bf16 flow)
-};
-
-struct GemmParams {
-  int64_t M;
-  int N, K;
-  const __nv_bfloat16* bias;  // [N] or null
-  void* C;
-  int64_t ldc;
-  int out_fp32;
-  int epilogue;
-  int flags;
-  const __nv_bfloat16* residual;
-  int64_t ldr;
-  const float* gate;  // fp32 [R, gate_row_stride], column = output column
-  int64_t gate_row_stride;
-  const int32_t* row_index;  // [M] or null => row / rows_per_group
-  int64_t rows_per_group;
-  int num_m_tiles, num_n_tiles;
-};
-
+// ================================================================================================
+// 1-CTA kernel
+// ================================================================================================
 template <int BN>
 struct GemmCfg {
   static constexpr int kStages = (BN == 256) ? 4 : 6;
@@ -59,27 +36,6 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = 2 * BN;  // 512 or 256 (power of two)
 };
-
-__device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int& mt, int& nt) {
-  // groups of 8 M-tiles; inside a group N is the slow axis so that the 8 CTAs sharing a W tile run together
-  constexpr int GM = 8;
-  int tiles_per_group = GM * num_n;
-  int g = tile / tiles_per_group;
-  int first_m = g * GM;
-  int gm = min(GM, num_m - first_m);
-  int r = tile - g * tiles_per_group;
-  nt = r / gm;
-  mt = first_m + (r - nt * gm);
-}
-
-__device__ __forceinline__ float gelu_tanh_f(float x) {
-  // 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715x^3)))  (torch GELU(approximate="tanh"))
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float inner = k0 * (x + k1 * x * x * x);
-  return 0.5f * x * (1.0f + tanhf(inner));
-}
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-__device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -187,7 +143,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ===================== epilogue =====================
     const int q = warp & 3;  // TMEM lane quadrant this warp may touch
     int it = 0;
-    const __nv_bfloat16* __restrict__ bias = p.bias;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       int mt, nt;
       tile_coords(tile, p.num_m_tiles, p.num_n_tiles, mt, nt);
@@ -197,11 +152,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       const int64_t row = (int64_t)mt * GEMM_BM + q * 32 + lane;
       const bool row_ok = row < p.M;
-      const float* gate_row = nullptr;
-      if (p.epilogue == EPI_GATE_RESIDUAL && p.gate != nullptr && row_ok) {
-        int64_t gi = p.row_index ? (int64_t)p.row_index[row] : (row / p.rows_per_group);
-        gate_row = p.gate + gi * p.gate_row_stride;
-      }
+      const float* gate_row = gate_row_ptr(p, row, row_ok);
       const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
@@ -210,101 +161,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr_row + c * 32, r);
         tmem_wait_ld();
-        if (!row_ok) continue;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        const int ncol = min(32, p.N - col0);
-        if (bias != nullptr) {
-          if (ncol == 32) {
-            const uint4* bp = reinterpret_cast<const uint4*>(bias + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 b = __ldg(bp + j);
-              v[8 * j + 0] += bf16_lo_to_f32(b.x);
-              v[8 * j + 1] += bf16_hi_to_f32(b.x);
-              v[8 * j + 2] += bf16_lo_to_f32(b.y);
-              v[8 * j + 3] += bf16_hi_to_f32(b.y);
-              v[8 * j + 4] += bf16_lo_to_f32(b.z);
-              v[8 * j + 5] += bf16_hi_to_f32(b.z);
-              v[8 * j + 6] += bf16_lo_to_f32(b.w);
-              v[8 * j + 7] += bf16_hi_to_f32(b.w);
-            }
-          } else {
-            for (int j = 0; j < ncol; ++j) v[j] += __bfloat162float(bias[col0 + j]);
-          }
-        }
-        if (p.epilogue == EPI_GELU_TANH) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(round_bf16(v[j]));
-        } else if (p.epilogue == EPI_SILU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = silu_f(round_bf16(v[j]));
-        } else if (p.epilogue == EPI_GATE_RESIDUAL) {
-          const __nv_bfloat16* rp = p.residual + row * p.ldr + col0;
-          if (ncol == 32) {
-            float g[32];
-            if (gate_row != nullptr) {
-              const float4* gp = reinterpret_cast<const float4*>(gate_row + col0);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 t = __ldg(gp + j);
-                g[4 * j + 0] = t.x;
-                g[4 * j + 1] = t.y;
-                g[4 * j + 2] = t.z;
-                g[4 * j + 3] = t.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) g[j] = 1.0f;
-            }
-            const uint4* rp4 = reinterpret_cast<const uint4*>(rp);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 x = __ldg(rp4 + j);
-              float xr[8] = {bf16_lo_to_f32(x.x), bf16_hi_to_f32(x.x), bf16_lo_to_f32(x.y), bf16_hi_to_f32(x.y),
-                             bf16_lo_to_f32(x.z), bf16_hi_to_f32(x.z), bf16_lo_to_f32(x.w), bf16_hi_to_f32(x.w)};
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                float y = round_bf16(v[8 * j + e]) * g[8 * j + e];
-                if (p.flags & GEMM_FLAG_ROUND_PRODUCT) y = round_bf16(y);
-                v[8 * j + e] = xr[e] + y;
-              }
-            }
-          } else {
-            for (int j = 0; j < ncol; ++j) {
-              float g = gate_row ? gate_row[col0 + j] : 1.0f;
-              float y = round_bf16(v[j]) * g;
-              if (p.flags & GEMM_FLAG_ROUND_PRODUCT) y = round_bf16(y);
-              v[j] = __bfloat162float(rp[j]) + y;
-            }
-          }
-        }
-        if (p.out_fp32) {
-          float* cp = reinterpret_cast<float*>(p.C) + row * p.ldc + col0;
-          if (ncol == 32) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              reinterpret_cast<float4*>(cp)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            for (int j = 0; j < ncol; ++j) cp[j] = v[j];
-          }
-        } else {
-          __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0;
-          if (ncol == 32) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-              o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-              o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-              o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-              reinterpret_cast<uint4*>(cp)[j] = o;
-            }
-          } else {
-            for (int j = 0; j < ncol; ++j) cp[j] = __float2bfloat16_rn(v[j]);
-          }
-        }
+        if (row_ok) epilogue_chunk(p, row, col0, gate_row, r);
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
@@ -319,6 +176,167 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
+// ================================================================================================
+// CTA-pair kernel: 256 x 256 tile per cluster of 2
+// ================================================================================================
+struct Gemm2Cfg {
+  static constexpr int BN = 256;                              // N columns per cluster tile
+  static constexpr int kStages = 6;
+  static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;       // this CTA's 128 rows of A
+  static constexpr int kBBytes = (BN / 2) * GEMM_BK * 2;      // this CTA's half (128 rows) of the W tile
+  static constexpr int kStageBytes = kABytes + kBBytes;       // 32 KB
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kTmemCols = 2 * BN;                    // two accumulator stages of 256 fp32 columns
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const GemmParams p) {
+  using Cfg = Gemm2Cfg;
+  constexpr int kStages = Cfg::kStages;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint32_t bars = smem_base + kStages * Cfg::kStageBytes;
+  auto full_bar = [&](int s) { return bars + 8u * s; };                         // used in the leader CTA only
+  auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };            // per CTA (multicast commit)
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages + s); };        // per CTA (multicast commit)
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + 2 + s); };   // leader only, 8 warp arrivals
+  uint32_t tmem_ptr_smem = bars + 8u * (2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;  // tiles of 256 x 256
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);   // leader's producer arrives once with the byte count of BOTH CTAs
+      mbar_init(empty_bar(s), 1);  // one multicast tcgen05.commit
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 8);  // 4 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc_2cta(tmem_ptr_smem, Cfg::kTmemCols);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        int mt, nt;
+        tile_coords(tile, p.num_m_tiles, p.num_n_tiles, mt, nt);
+        const int row_a = mt * 2 * GEMM_BM + (int)cta_rank * GEMM_BM;
+        const int row_b = nt * BN + (int)cta_rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u, 100 + stage);
+          uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
+          uint32_t b_dst = a_dst + Cfg::kABytes;
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+          tma_load_2d_2cta(a_dst, &tmap_a, full_bar(stage), kb * GEMM_BK, row_a);
+          tma_load_2d_2cta(b_dst, &tmap_b, full_bar(stage), kb * GEMM_BK, row_b);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * GEMM_BM, BN, 0);  // M = 256 across the pair
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u, 200 + acc);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait_cluster(full_bar(stage), phase, 300 + stage);
+          tc_fence_after();
+          uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
+          uint32_t b_addr = a_addr + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            uint64_t adesc = make_sdesc_sw128(a_addr + k * 32, 16, 1024);
+            uint64_t bdesc = make_sdesc_sw128(b_addr + k * 32, 16, 1024);
+            umma_ss_2cta(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit_2cta(empty_bar(stage), 0b11);  // frees this stage in BOTH CTAs
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tc_commit_2cta(tfull_bar(acc), 0b11);  // accumulator halves ready in both CTAs
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int q = warp & 3;
+    int it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      int mt, nt;
+      tile_coords(tile, p.num_m_tiles, p.num_n_tiles, mt, nt);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait_cluster(tfull_bar(acc), acc_phase, 400 + acc);
+      tc_fence_after();
+      const int64_t row = (int64_t)mt * 2 * GEMM_BM + (int64_t)cta_rank * GEMM_BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const float* gate_row = gate_row_ptr(p, row, row_ok);
+      const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = nt * BN + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr_row + c * 32, r);
+        tmem_wait_ld();
+        if (row_ok) epilogue_chunk(p, row, col0, gate_row, r);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);  // to the leader's barrier
+    }
+  }
+
+  // Neither CTA may exit (or free TMEM) while its peer can still read its shared memory / write its barriers.
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ================================================================================================
+// host side
+// ================================================================================================
 template <int BN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
@@ -334,6 +352,26 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   FINO_CHECK_CUDA(cudaGetLastError());
   return FINO_OK;
 }
+
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg;
+  static bool configured = false;
+  if (!configured) {
+    FINO_CHECK_CUDA(
+        cudaFuncSetAttribute(gemm2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  int tiles = p.num_m_tiles * p.num_n_tiles;
+  int clusters = num_sms() / 2;
+  if (tiles < clusters) clusters = tiles;
+  gemm2_bf16_kernel<<<2 * clusters, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  FINO_CHECK_CUDA(cudaGetLastError());
+  return FINO_OK;
+}
+
+// mode: 0 = auto, 1 = force the 1-CTA kernel, 2 = force the CTA-pair kernel
+static int g_gemm_mode = 0;
+void gemm_set_mode(int mode) { g_gemm_mode = mode; }
 
 int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void* bias, void* c, int64_t ldc,
               int64_t m, int n, int k, int epilogue, int out_fp32, int flags, const void* residual, int64_t ldr,
@@ -351,7 +389,9 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
     FINO_CHECK_ARG(gate == nullptr || row_index != nullptr || rows_per_group > 0,
                    "gemm: gate needs row_index or rows_per_group");
   }
-  const int BN = (n > 128) ? 256 : 128;
+  const bool pair = g_gemm_mode == 2 || (g_gemm_mode == 0 && m > 256 && n > 128);
+  const int BN = pair ? 256 : ((n > 128) ? 256 : 128);
+  const int BM = pair ? 2 * GEMM_BM : GEMM_BM;
   GemmParams p;
   p.M = m;
   p.N = n;
@@ -368,7 +408,7 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
   p.gate_row_stride = gate_row_stride;
   p.row_index = row_index;
   p.rows_per_group = rows_per_group > 0 ? rows_per_group : (int64_t)1 << 62;
-  p.num_m_tiles = (int)((m + GEMM_BM - 1) / GEMM_BM);
+  p.num_m_tiles = (int)((m + BM - 1) / BM);
   p.num_n_tiles = (n + BN - 1) / BN;
 
   CUtensorMap ta, tb;
@@ -382,10 +422,11 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
   {
     uint64_t dims[2] = {(uint64_t)k, (uint64_t)n};
     uint64_t strides[1] = {(uint64_t)ldw * 2};
-    uint32_t box[2] = {GEMM_BK, (uint32_t)BN};
+    uint32_t box[2] = {GEMM_BK, (uint32_t)(pair ? BN / 2 : BN)};
     int r = encode_tmap_bf16(&tb, w, 2, dims, strides, box);
     if (r) return r;
   }
+  if (pair) return launch_gemm2(ta, tb, p, stream);
   if (BN == 256) return launch_gemm<256>(ta, tb, p, stream);
   return launch_gemm<128>(ta, tb, p, stream);
 }

@@ -330,5 +330,10 @@ def swap01(x: torch.Tensor, a: int, b: int, inner: int, out: Optional[torch.Tens
     return out
 
 
+def gemm_set_mode(mode: int) -> None:
+    """0 auto, 1 single-CTA tcgen05 GEMM, 2 CTA-pair (cta_group::2) GEMM."""
+    _lib.check(_lib.load().fino_gemm_set_mode(mode), "fino_gemm_set_mode")
+
+
 def launch_count() -> int:
     return int(_lib.load().fino_launch_count())

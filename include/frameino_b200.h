@@ -47,6 +47,10 @@ int fino_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const
                    const float* gate, int64_t gate_row_stride, const int32_t* row_index, int64_t rows_per_group,
                    void* stream);
 
+/* Tuning / test hook: 0 = choose per shape (default), 1 = always the single-CTA kernel, 2 = always the CTA-pair
+ * (cta_group::2, 256x256 tile) kernel. */
+int fino_gemm_set_mode(int mode);
+
 /* O = softmax(Q K^T * scale) V, non-causal, no mask; tcgen05 flash attention, head_dim 64 or 128.
  * Replaces F.scaled_dot_product_attention: transformer_wan.py:108-110, attention_processor.py:2863.
  * Q/K/V/O are [batch, n, heads*head_dim] views (heads contiguous inside a row). */

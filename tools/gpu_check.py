@@ -366,7 +366,54 @@ def check_attn_perf():
     return res
 
 
+def check_gemm2():
+    """CTA-pair (cta_group::2) GEMM vs the single-CTA kernel: correctness on ragged shapes + throughput."""
+    import torch
+    from frameino_b200 import ops
+
+    torch.manual_seed(6)
+    res = {}
+    for (m, n, k) in [(256, 256, 64), (512, 512, 256), (300, 264, 384), (1000, 3072, 3072), (5000, 192, 512),
+                      (2, 3072, 256), (28160, 3072, 3072)]:
+        a = torch.randn(m, k, device="cuda").bfloat16()
+        w = (torch.randn(n, k, device="cuda") / math.sqrt(k)).bfloat16()
+        bias = torch.randn(n, device="cuda").bfloat16()
+        ref = torch.nn.functional.linear(a, w, bias).float()
+        for mode in (1, 2):
+            ops.gemm_set_mode(mode)
+            y = ops.linear(a, w, bias)
+            torch.cuda.synchronize()
+            res[f"mode{mode}_{m}x{n}x{k}"] = _rel(y, ref)
+    m, n, k = 777, 1024, 512
+    a = torch.randn(m, k, device="cuda").bfloat16()
+    w = (torch.randn(n, k, device="cuda") / math.sqrt(k)).bfloat16()
+    bias = torch.randn(n, device="cuda").bfloat16()
+    x = torch.randn(m, n, device="cuda").bfloat16()
+    gate = torch.randn(3, n, device="cuda")
+    ridx = torch.randint(0, 3, (m,), device="cuda", dtype=torch.int32)
+    lin = (a.float() @ w.float().t() + bias.float()).bfloat16()
+    ops.gemm_set_mode(2)
+    y = ops.linear(a, w, bias, epilogue=ops.EPI_GATE_RESIDUAL, residual=x, gate=gate, row_index=ridx)
+    res["mode2_gate_residual"] = _rel(y, (x.float() + lin * gate[ridx.long()]).bfloat16())
+    res["mode2_gelu"] = _rel(ops.linear(a, w, bias, epilogue=ops.EPI_GELU_TANH),
+                             torch.nn.functional.gelu(lin, approximate="tanh"))
+    for (m, n, k) in [(28160, 3072, 3072), (28160, 9216, 3072), (28160, 14336, 3072), (28160, 3072, 14336)]:
+        a = torch.randn(m, k, device="cuda").bfloat16()
+        w = (torch.randn(n, k, device="cuda") / math.sqrt(k)).bfloat16()
+        bias = torch.randn(n, device="cuda").bfloat16()
+        o = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+        for mode in (1, 2):
+            ops.gemm_set_mode(mode)
+            ms = _time_ms(lambda: ops.linear(a, w, bias, out=o), iters=10, warmup=3)
+            res[f"tflops_mode{mode}_{m}x{n}x{k}"] = 2.0 * m * n * k / ms / 1e9
+        ms_t = _time_ms(lambda: torch.nn.functional.linear(a, w, bias), iters=10, warmup=3)
+        res[f"tflops_torch_{m}x{n}x{k}"] = 2.0 * m * n * k / ms_t / 1e9
+    ops.gemm_set_mode(0)
+    return res
+
+
 CHECKS = {
+    "gemm2": check_gemm2,
     "ln": check_ln,
     "gate": check_gate,
     "qk": check_qk,
