@@ -153,8 +153,8 @@ int fino_build_mod_table(const float* table, const float* proj, float* out, int 
 }
 
 int fino_gemm_set_mode(int mode) {
-  if (mode < 0 || mode > 2) {
-    fino::set_last_error("fino_gemm_set_mode: mode %d out of range (0 auto, 1 single-CTA, 2 CTA-pair)", mode);
+  if (mode < 0 || mode > 3) {
+    fino::set_last_error("fino_gemm_set_mode: mode %d out of range (0 auto, 1 single-CTA, 2 CTA-pair 256x256, 3 CTA-pair 512x256)", mode);
     return fino::FINO_ERR_INVALID;
   }
   fino::gemm_set_mode(mode);

@@ -177,24 +177,33 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }
 
 // ================================================================================================
-// CTA-pair kernel: 256 x 256 tile per cluster of 2
+// CTA-pair kernel (cta_group::2). MH = M-halves (128-row accumulators) per CTA:
+//   MH = 1: cluster tile 256 x 256, two accumulator stages (epilogue overlaps the next main loop)
+//   MH = 2: cluster tile 512 x 256, each CTA owns 256 rows x 256 columns = all 512 TMEM columns, single stage.
+//           48 KB of operands per 256x256x64 MACs per SM instead of 32 KB per 128x256x64: the L2->SM fill path
+//           (ncu l1tex 83 % busy with MH = 1) stops being the limiter.
 // ================================================================================================
+template <int MH>
 struct Gemm2Cfg {
-  static constexpr int BN = 256;                              // N columns per cluster tile
-  static constexpr int kStages = 6;
-  static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;       // this CTA's 128 rows of A
-  static constexpr int kBBytes = (BN / 2) * GEMM_BK * 2;      // this CTA's half (128 rows) of the W tile
-  static constexpr int kStageBytes = kABytes + kBBytes;       // 32 KB
+  static constexpr int BN = 256;                               // N columns per cluster tile
+  static constexpr int kStages = (MH == 1) ? 6 : 4;
+  static constexpr int kABytes = MH * GEMM_BM * GEMM_BK * 2;   // this CTA's MH*128 rows of A
+  static constexpr int kBBytes = (BN / 2) * GEMM_BK * 2;       // this CTA's half (128 rows) of the W tile
+  static constexpr int kStageBytes = kABytes + kBBytes;        // 32 KB / 48 KB
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
-  static constexpr int kTmemCols = 2 * BN;                    // two accumulator stages of 256 fp32 columns
+  static constexpr int kAccStages = (MH == 1) ? 2 : 1;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kTileM = 2 * MH * GEMM_BM;              // rows per cluster tile
 };
 
+template <int MH>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const GemmParams p) {
-  using Cfg = Gemm2Cfg;
+  using Cfg = Gemm2Cfg<MH>;
   constexpr int kStages = Cfg::kStages;
   constexpr int BN = Cfg::BN;
+  constexpr int kAcc = Cfg::kAccStages;
   extern __shared__ uint8_t smem_raw[];
   uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint32_t bars = smem_base + kStages * Cfg::kStageBytes;
@@ -211,7 +220,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;  // tiles of 256 x 256
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;  // cluster tiles
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -246,15 +255,15 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         int mt, nt;
         tile_coords(tile, p.num_m_tiles, p.num_n_tiles, mt, nt);
-        const int row_a = mt * 2 * GEMM_BM + (int)cta_rank * GEMM_BM;
+        const int row_a = mt * Cfg::kTileM + (int)cta_rank * (MH * GEMM_BM);
         const int row_b = nt * BN + (int)cta_rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u, 100 + stage);
           uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
           uint32_t b_dst = a_dst + Cfg::kABytes;
           if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
-          tma_load_2d_2cta(a_dst, &tmap_a, full_bar(stage), kb * GEMM_BK, row_a);
-          tma_load_2d_2cta(b_dst, &tmap_b, full_bar(stage), kb * GEMM_BK, row_b);
+          tma_load_2d_2cta(a_dst, &tmap_a, full_bar(stage), kb * GEMM_BK, row_a);  // box {64, MH*128}
+          tma_load_2d_2cta(b_dst, &tmap_b, full_bar(stage), kb * GEMM_BK, row_b);  // box {64, 128}
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
@@ -270,11 +279,11 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       uint32_t phase = 0;
       int it = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
+        const int acc = (kAcc == 2) ? (it & 1) : 0;
+        const uint32_t acc_phase = (kAcc == 2) ? ((it >> 1) & 1) : (it & 1);
         mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u, 200 + acc);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
+        const uint32_t tmem_d = tmem_base + ((kAcc == 2) ? acc * BN : 0);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait_cluster(full_bar(stage), phase, 300 + stage);
           tc_fence_after();
@@ -282,9 +291,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           uint32_t b_addr = a_addr + Cfg::kABytes;
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
-            uint64_t adesc = make_sdesc_sw128(a_addr + k * 32, 16, 1024);
             uint64_t bdesc = make_sdesc_sw128(b_addr + k * 32, 16, 1024);
-            umma_ss_2cta(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int mh = 0; mh < MH; ++mh) {
+              uint64_t adesc = make_sdesc_sw128(a_addr + mh * (GEMM_BM * GEMM_BK * 2) + k * 32, 16, 1024);
+              umma_ss_2cta(tmem_d + mh * BN, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           tc_commit_2cta(empty_bar(stage), 0b11);  // frees this stage in BOTH CTAs
           if (++stage == kStages) {
@@ -292,32 +304,37 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             phase ^= 1u;
           }
         }
-        tc_commit_2cta(tfull_bar(acc), 0b11);  // accumulator halves ready in both CTAs
+        tc_commit_2cta(tfull_bar(acc), 0b11);  // accumulators ready in both CTAs
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    // ===================== epilogue (both CTAs, own MH*128 rows) =====================
     const int q = warp & 3;
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       int mt, nt;
       tile_coords(tile, p.num_m_tiles, p.num_n_tiles, mt, nt);
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = (kAcc == 2) ? (it & 1) : 0;
+      const uint32_t acc_phase = (kAcc == 2) ? ((it >> 1) & 1) : (it & 1);
       mbar_wait_cluster(tfull_bar(acc), acc_phase, 400 + acc);
       tc_fence_after();
-      const int64_t row = (int64_t)mt * 2 * GEMM_BM + (int64_t)cta_rank * GEMM_BM + q * 32 + lane;
-      const bool row_ok = row < p.M;
-      const float* gate_row = gate_row_ptr(p, row, row_ok);
-      const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col0 = nt * BN + c * 32;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr_row + c * 32, r);
-        tmem_wait_ld();
-        if (row_ok) epilogue_chunk(p, row, col0, gate_row, r);
+      for (int mh = 0; mh < MH; ++mh) {
+        const int64_t row =
+            (int64_t)mt * Cfg::kTileM + (int64_t)cta_rank * (MH * GEMM_BM) + mh * GEMM_BM + q * 32 + lane;
+        const bool row_ok = row < p.M;
+        const float* gate_row = gate_row_ptr(p, row, row_ok);
+        const uint32_t taddr_row =
+            tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ((kAcc == 2) ? acc * BN : mh * BN);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          const int col0 = nt * BN + c * 32;
+          if (col0 >= p.N) break;  // warp-uniform
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr_row + c * 32, r);
+          tmem_wait_ld();
+          if (row_ok) epilogue_chunk(p, row, col0, gate_row, r);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -353,23 +370,24 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   return FINO_OK;
 }
 
+template <int MH>
 static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = Gemm2Cfg;
+  using Cfg = Gemm2Cfg<MH>;
   static bool configured = false;
   if (!configured) {
     FINO_CHECK_CUDA(
-        cudaFuncSetAttribute(gemm2_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        cudaFuncSetAttribute(gemm2_bf16_kernel<MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int clusters = num_sms() / 2;
   if (tiles < clusters) clusters = tiles;
-  gemm2_bf16_kernel<<<2 * clusters, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  gemm2_bf16_kernel<MH><<<2 * clusters, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   FINO_CHECK_CUDA(cudaGetLastError());
   return FINO_OK;
 }
 
-// mode: 0 = auto, 1 = force the 1-CTA kernel, 2 = force the CTA-pair kernel
+// mode: 0 = auto, 1 = single-CTA kernel, 2 = CTA pair with 256x256 cluster tiles, 3 = CTA pair with 512x256 tiles
 static int g_gemm_mode = 0;
 void gemm_set_mode(int mode) { g_gemm_mode = mode; }
 
@@ -389,9 +407,13 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
     FINO_CHECK_ARG(gate == nullptr || row_index != nullptr || rows_per_group > 0,
                    "gemm: gate needs row_index or rows_per_group");
   }
-  const bool pair = g_gemm_mode == 2 || (g_gemm_mode == 0 && m > 256 && n > 128);
+  int mh = 0;  // 0 = single CTA, else M-halves per CTA of the pair kernel
+  if (g_gemm_mode == 2) mh = 1;
+  else if (g_gemm_mode == 3) mh = 2;
+  else if (g_gemm_mode == 0 && n > 128) mh = (m > 1024) ? 2 : (m > 256 ? 1 : 0);
+  const bool pair = mh != 0;
   const int BN = pair ? 256 : ((n > 128) ? 256 : 128);
-  const int BM = pair ? 2 * GEMM_BM : GEMM_BM;
+  const int BM = pair ? 2 * mh * GEMM_BM : GEMM_BM;
   GemmParams p;
   p.M = m;
   p.N = n;
@@ -415,7 +437,7 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
   {
     uint64_t dims[2] = {(uint64_t)k, (uint64_t)m};
     uint64_t strides[1] = {(uint64_t)lda * 2};
-    uint32_t box[2] = {GEMM_BK, GEMM_BM};
+    uint32_t box[2] = {GEMM_BK, (uint32_t)(mh == 2 ? 2 * GEMM_BM : GEMM_BM)};
     int r = encode_tmap_bf16(&ta, a, 2, dims, strides, box);
     if (r) return r;
   }
@@ -426,7 +448,8 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
     int r = encode_tmap_bf16(&tb, w, 2, dims, strides, box);
     if (r) return r;
   }
-  if (pair) return launch_gemm2(ta, tb, p, stream);
+  if (mh == 2) return launch_gemm2<2>(ta, tb, p, stream);
+  if (mh == 1) return launch_gemm2<1>(ta, tb, p, stream);
   if (BN == 256) return launch_gemm<256>(ta, tb, p, stream);
   return launch_gemm<128>(ta, tb, p, stream);
 }

@@ -47,8 +47,8 @@ int fino_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const
                    const float* gate, int64_t gate_row_stride, const int32_t* row_index, int64_t rows_per_group,
                    void* stream);
 
-/* Tuning / test hook: 0 = choose per shape (default), 1 = always the single-CTA kernel, 2 = always the CTA-pair
- * (cta_group::2, 256x256 tile) kernel. */
+/* Tuning / test hook: 0 = choose per shape (default), 1 = single-CTA kernel, 2 = CTA pair (cta_group::2) with
+ * 256x256 cluster tiles, 3 = CTA pair with 512x256 cluster tiles. */
 int fino_gemm_set_mode(int mode);
 
 /* O = softmax(Q K^T * scale) V, non-causal, no mask; tcgen05 flash attention, head_dim 64 or 128.

@@ -379,7 +379,7 @@ def check_gemm2():
         w = (torch.randn(n, k, device="cuda") / math.sqrt(k)).bfloat16()
         bias = torch.randn(n, device="cuda").bfloat16()
         ref = torch.nn.functional.linear(a, w, bias).float()
-        for mode in (1, 2):
+        for mode in (1, 2, 3):
             ops.gemm_set_mode(mode)
             y = ops.linear(a, w, bias)
             torch.cuda.synchronize()
@@ -402,7 +402,7 @@ def check_gemm2():
         w = (torch.randn(n, k, device="cuda") / math.sqrt(k)).bfloat16()
         bias = torch.randn(n, device="cuda").bfloat16()
         o = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
-        for mode in (1, 2):
+        for mode in (1, 2, 3):
             ops.gemm_set_mode(mode)
             ms = _time_ms(lambda: ops.linear(a, w, bias, out=o), iters=10, warmup=3)
             res[f"tflops_mode{mode}_{m}x{n}x{k}"] = 2.0 * m * n * k / ms / 1e9
