@@ -48,7 +48,9 @@ struct AttnCfg {
   static constexpr int kSmemBytes = kQBytes + 2 * kKVStages * kTileBytes + 1024 + 256;
 };
 
-template <int HD>
+// EMU   = exponentials per group of 8 computed on the FMA/ALU pipes (exp2_emu2) instead of MUFU ex2
+// SPLIT = P is published to the MMA warp in two 64-key halves so that P V starts while the second half is still in exp
+template <int HD, int EMU, bool SPLIT>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
@@ -60,7 +62,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const uint32_t k_smem = q_smem + Cfg::kQBytes;
   const uint32_t v_smem = k_smem + KST * Cfg::kTileBytes;
   const uint32_t bars = v_smem + KST * Cfg::kTileBytes;
-  // barriers: q_full, k_full[KST], k_empty[KST], v_full[KST], v_empty[KST], s_full[2], p_full[2], o_done[2]
+  // barriers: q_full, k_full[KST], k_empty[KST], v_full[KST], v_empty[KST], s_full[2], p_full[2], o_done[2], p_half[2]
   const uint32_t q_full = bars;
   auto k_full = [&](int s) { return bars + 8u * (1 + s); };
   auto k_empty = [&](int s) { return bars + 8u * (1 + KST + s); };
@@ -69,7 +71,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   auto s_full = [&](int i) { return bars + 8u * (1 + 4 * KST + i); };
   auto p_full = [&](int i) { return bars + 8u * (3 + 4 * KST + i); };
   auto o_done = [&](int i) { return bars + 8u * (5 + 4 * KST + i); };
-  const uint32_t tmem_ptr_smem = bars + 8u * (7 + 4 * KST);
+  auto p_half = [&](int i) { return bars + 8u * (7 + 4 * KST + i); };  // first 64 keys of P_i written (SPLIT)
+  const uint32_t tmem_ptr_smem = bars + 8u * (9 + 4 * KST);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -94,6 +97,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     for (int i = 0; i < 2; ++i) {
       mbar_init(s_full(i), 1);
       mbar_init(p_full(i), 128);
+      mbar_init(p_half(i), 128);
       mbar_init(o_done(i), 1);
     }
     fence_barrier_init();
@@ -160,10 +164,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                     ks != 0 ? 1u : 0u);
           }
         };
-        auto issue_pv = [&](int i, int vstage, bool accumulate) {
+        auto issue_pv = [&](int i, int vstage, bool accumulate, int ks0, int ks1) {
           const uint32_t va = v_smem + vstage * Cfg::kTileBytes;
 #pragma unroll
-          for (int ks = 0; ks < ATT_BN / 16; ++ks) {
+          for (int ks = ks0; ks < ks1; ++ks) {
             // 16 keys per MMA: advance 16 rows (2048 B) in the V panel; LBO = panel stride (d 64..127), SBO = 8 rows
             umma_ts(tmem_o[i], tmem_s[i] + ks * 8, make_sdesc_sw128(va + ks * 2048, Cfg::kPanelBytes, 1024), idesc_o,
                     (accumulate || ks != 0) ? 1u : 0u);
@@ -181,18 +185,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           issue_s(0, stage);
           tc_commit(s_full(0));
           if (j > 0) {
-            mbar_wait(p_full(1), (uint32_t)((j - 1) & 1), 51);
-            tc_fence_after();
-            issue_pv(1, pstage, j - 1 > 0);
+            if (SPLIT) {
+              mbar_wait(p_half(1), (uint32_t)((j - 1) & 1), 53);
+              tc_fence_after();
+              issue_pv(1, pstage, j - 1 > 0, 0, 4);
+              mbar_wait(p_full(1), (uint32_t)((j - 1) & 1), 51);
+              tc_fence_after();
+              issue_pv(1, pstage, true, 4, 8);
+            } else {
+              mbar_wait(p_full(1), (uint32_t)((j - 1) & 1), 51);
+              tc_fence_after();
+              issue_pv(1, pstage, j - 1 > 0, 0, 8);
+            }
             tc_commit(v_empty(pstage));
           }
           issue_s(1, stage);
           tc_commit(s_full(1));
           tc_commit(k_empty(stage));
           mbar_wait(v_full(stage), phase, 60 + stage);
-          mbar_wait(p_full(0), (uint32_t)(j & 1), 50);
-          tc_fence_after();
-          issue_pv(0, stage, j > 0);
+          if (SPLIT) {
+            mbar_wait(p_half(0), (uint32_t)(j & 1), 54);
+            tc_fence_after();
+            issue_pv(0, stage, j > 0, 0, 4);
+            mbar_wait(p_full(0), (uint32_t)(j & 1), 50);
+            tc_fence_after();
+            issue_pv(0, stage, true, 4, 8);
+          } else {
+            mbar_wait(p_full(0), (uint32_t)(j & 1), 50);
+            tc_fence_after();
+            issue_pv(0, stage, j > 0, 0, 8);
+          }
           pstage = stage;
           if (++stage == KST) {
             stage = 0;
@@ -200,9 +222,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           }
         }
         tc_commit(o_done(0));
-        mbar_wait(p_full(1), (uint32_t)((T - 1) & 1), 52);
-        tc_fence_after();
-        issue_pv(1, pstage, T - 1 > 0);
+        if (SPLIT) {
+          mbar_wait(p_half(1), (uint32_t)((T - 1) & 1), 55);
+          tc_fence_after();
+          issue_pv(1, pstage, T - 1 > 0, 0, 4);
+          mbar_wait(p_full(1), (uint32_t)((T - 1) & 1), 52);
+          tc_fence_after();
+          issue_pv(1, pstage, true, 4, 8);
+        } else {
+          mbar_wait(p_full(1), (uint32_t)((T - 1) & 1), 52);
+          tc_fence_after();
+          issue_pv(1, pstage, T - 1 > 0, 0, 8);
+        }
         tc_commit(v_empty(pstage));
         tc_commit(o_done(1));
       }
@@ -283,21 +314,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int c2 = 0; c2 < 2; ++c2) {
           const int c = half * 2 + c2;
 #pragma unroll
-          for (int e = 0; e < 32; e += 4) {
-            float p0 = ex2_approx(fmaf(__uint_as_float(s[c][e + 0]), sl2, neg_m));
-            float p1 = ex2_approx(fmaf(__uint_as_float(s[c][e + 1]), sl2, neg_m));
-            float p2 = ex2_approx(fmaf(__uint_as_float(s[c][e + 2]), sl2, neg_m));
-            float p3 = ex2_approx(fmaf(__uint_as_float(s[c][e + 3]), sl2, neg_m));
-            sum0 += p0;
-            sum1 += p1;
-            sum2 += p2;
-            sum3 += p3;
-            pk[c2 * 16 + e / 2 + 0] = pack_bf16x2(p0, p1);
-            pk[c2 * 16 + e / 2 + 1] = pack_bf16x2(p2, p3);
+          for (int e = 0; e < 32; e += 8) {
+            float x[8], pv[8];
+#pragma unroll
+            for (int i = 0; i < 8; i += 2)  // x = s * scale_log2 - m * scale_log2 (packed FFMA2)
+              ffma2(x[i], x[i + 1], __uint_as_float(s[c][e + i]), __uint_as_float(s[c][e + i + 1]), sl2, sl2, neg_m,
+                    neg_m);
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              if (i < EMU) {
+                exp2_emu2(pv[i], pv[i + 1], x[i], x[i + 1]);
+              } else {
+                pv[i] = ex2_approx(x[i]);
+                pv[i + 1] = ex2_approx(x[i + 1]);
+              }
+            }
+            fadd2(sum0, sum1, sum0, sum1, pv[0], pv[1]);
+            fadd2(sum2, sum3, sum2, sum3, pv[2], pv[3]);
+            fadd2(sum0, sum1, sum0, sum1, pv[4], pv[5]);
+            fadd2(sum2, sum3, sum2, sum3, pv[6], pv[7]);
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) pk[c2 * 16 + (e + i) / 2] = pack_bf16x2(pv[i], pv[i + 1]);
           }
         }
         // P (bf16, 2 keys per 32-bit column) aliases S_i columns [0,64)
         tmem_st_32x32b_x32(t_s + half * 32, pk);
+        if (SPLIT && half == 0) {
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(p_half(wg));
+        }
       }
       l_sum += (sum0 + sum1) + (sum2 + sum3);
       tmem_wait_st();
@@ -339,20 +385,38 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
 }
 
-template <int HD>
+template <int HD, int EMU, bool SPLIT>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        int batch, cudaStream_t stream) {
   using Cfg = AttnCfg<HD>;
   static bool configured = false;
   if (!configured) {
-    FINO_CHECK_CUDA(
-        cudaFuncSetAttribute(attn_fwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    FINO_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HD, EMU, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes));
     configured = true;
   }
   dim3 grid((p.nq + 2 * ATT_BM - 1) / (2 * ATT_BM), p.heads, batch);
-  attn_fwd_kernel<HD><<<grid, ATT_THREADS, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
+  attn_fwd_kernel<HD, EMU, SPLIT><<<grid, ATT_THREADS, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
   FINO_CHECK_CUDA(cudaGetLastError());
   return FINO_OK;
+}
+
+// Tuning hook (fino_attention_set_variant): 0 = default. Variants differ only in scheduling / which pipe computes
+// the exponentials; results agree to bf16 rounding.
+static int g_attn_variant = 0;
+void attention_set_variant(int v) { g_attn_variant = v; }
+
+template <int HD>
+static int dispatch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                         int batch, cudaStream_t stream) {
+  switch (g_attn_variant) {
+    case 1: return launch_attn<HD, 0, false>(tq, tk, tv, p, batch, stream);  // all MUFU, P published once
+    case 2: return launch_attn<HD, 0, true>(tq, tk, tv, p, batch, stream);   // all MUFU, split P
+    case 3: return launch_attn<HD, 2, false>(tq, tk, tv, p, batch, stream);  // 2/8 emulated
+    case 4: return launch_attn<HD, 2, true>(tq, tk, tv, p, batch, stream);
+    case 5: return launch_attn<HD, 4, true>(tq, tk, tv, p, batch, stream);   // 4/8 emulated
+    default: return launch_attn<HD, 2, true>(tq, tk, tv, p, batch, stream);
+  }
 }
 
 int attention_fwd(const void* q, const void* k, const void* v, void* o, int batch, int heads, int64_t nq, int64_t nk,
@@ -393,8 +457,8 @@ int attention_fwd(const void* q, const void* k, const void* v, void* o, int batc
   p.heads = heads;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.num_kv_tiles = (int)((nk + ATT_BN - 1) / ATT_BN);
-  if (head_dim == 128) return launch_attn<128>(tq, tk, tv, p, batch, stream);
-  return launch_attn<64>(tq, tk, tv, p, batch, stream);
+  if (head_dim == 128) return dispatch_attn<128>(tq, tk, tv, p, batch, stream);
+  return dispatch_attn<64>(tq, tk, tv, p, batch, stream);
 }
 
 }  // namespace fino

@@ -34,6 +34,7 @@ int build_mod_table(const float* table, const float* proj, float* out, int layer
                     int64_t table_layer_stride, cudaStream_t stream);
 int swap01(const void* in, void* out, int64_t A, int64_t B, int64_t inner, cudaStream_t stream);
 void gemm_set_mode(int mode);
+void attention_set_variant(int v);
 }  // namespace fino
 
 static std::atomic<int64_t> g_launches{0};
@@ -158,6 +159,15 @@ int fino_gemm_set_mode(int mode) {
     return fino::FINO_ERR_INVALID;
   }
   fino::gemm_set_mode(mode);
+  return 0;
+}
+
+int fino_attention_set_variant(int variant) {
+  if (variant < 0 || variant > 5) {
+    fino::set_last_error("fino_attention_set_variant: variant %d out of range (0..5)", variant);
+    return fino::FINO_ERR_INVALID;
+  }
+  fino::attention_set_variant(variant);
   return 0;
 }
 

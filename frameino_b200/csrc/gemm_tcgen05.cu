@@ -410,7 +410,9 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
   int mh = 0;  // 0 = single CTA, else M-halves per CTA of the pair kernel
   if (g_gemm_mode == 2) mh = 1;
   else if (g_gemm_mode == 3) mh = 2;
-  else if (g_gemm_mode == 0 && n > 128) mh = (m > 1024) ? 2 : (m > 256 ? 1 : 0);
+  // auto: the 256x256 pair kernel wins on every large shape measured (profiles/r01_gemm_modes.json); the 512x256
+  // variant moves fewer bytes per FLOP but exposes its un-overlapped epilogue and is slower today.
+  else if (g_gemm_mode == 0 && n > 128 && m > 256) mh = 1;
   const bool pair = mh != 0;
   const int BN = pair ? 256 : ((n > 128) ? 256 : 128);
   const int BM = pair ? 2 * mh * GEMM_BM : GEMM_BM;

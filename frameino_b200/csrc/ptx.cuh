@@ -356,6 +356,51 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// Packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100): two lanes per issue slot.
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0,
+                                      float c1) {
+  asm("{\n\t"
+      ".reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %5};\n\t"
+      "mov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t"
+      "}\n"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t"
+      ".reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t"
+      "}\n"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// 2^x for two values on the FMA/ALU pipes (no MUFU): Cody-Waite split x = n + f with the round-to-minus-infinity
+// magic-add trick, cubic minimax polynomial for 2^f on [0,1) (max rel. error ~9e-5, far below bf16's 3.9e-3), and the
+// integer n added straight into the exponent field. x is clamped to >= -126 (so -inf gives ~1e-38, not NaN).
+__device__ __forceinline__ void exp2_emu2(float& y0, float& y1, float x0, float x1) {
+  const float kMagic = 12582912.f;  // 1.5 * 2^23
+  x0 = fmaxf(x0, -126.f);
+  x1 = fmaxf(x1, -126.f);
+  float r0, r1;
+  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(r0) : "f"(x0), "f"(kMagic));
+  asm("add.rm.ftz.f32 %0, %1, %2;" : "=f"(r1) : "f"(x1), "f"(kMagic));
+  float n0, n1, f0, f1;
+  fadd2(n0, n1, r0, r1, -kMagic, -kMagic);   // floor(x)
+  fadd2(f0, f1, x0, x1, -n0, -n1);           // fractional part in [0,1)
+  float p0, p1;
+  ffma2(p0, p1, f0, f1, 0.077119089663028717f, 0.077119089663028717f, 0.227564394474029541f, 0.227564394474029541f);
+  ffma2(p0, p1, p0, p1, f0, f1, 0.695146143436431885f, 0.695146143436431885f);
+  ffma2(p0, p1, p0, p1, f0, f1, 1.0f, 1.0f);
+  y0 = __int_as_float(__float_as_int(p0) + (__float_as_int(r0) << 23));
+  y1 = __int_as_float(__float_as_int(p1) + (__float_as_int(r1) << 23));
+}
 __device__ __forceinline__ float bf16_lo_to_f32(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi_to_f32(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 

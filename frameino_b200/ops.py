@@ -335,5 +335,9 @@ def gemm_set_mode(mode: int) -> None:
     _lib.check(_lib.load().fino_gemm_set_mode(mode), "fino_gemm_set_mode")
 
 
+def attention_set_variant(variant: int) -> None:
+    _lib.check(_lib.load().fino_attention_set_variant(variant), "fino_attention_set_variant")
+
+
 def launch_count() -> int:
     return int(_lib.load().fino_launch_count())

@@ -59,6 +59,9 @@ int fino_attention_fwd(const void* q, const void* k, const void* v, void* o, int
                        int64_t o_row_stride, int64_t q_batch_stride, int64_t k_batch_stride, int64_t v_batch_stride,
                        int64_t o_batch_stride, float scale, void* stream);
 
+/* Tuning / test hook: scheduling variant of the attention kernel (0 = default; 1..5 see attention_tcgen05.cu). */
+int fino_attention_set_variant(int variant);
+
 #define FINO_LN_FLAG_BF16_STEPS 1 /* emulate the bf16 module flow of CogVideoXLayerNormZero / AdaLayerNorm */
 
 /* out = LayerNorm(x) [*gamma + beta] [*(1+scale) + shift], fp32 math, one rounding.

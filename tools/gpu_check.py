@@ -412,7 +412,35 @@ def check_gemm2():
     return res
 
 
+def check_attn_variants():
+    """Scheduling variants of the attention kernel: accuracy vs fp32 SDPA and throughput at the config-2/3 shapes."""
+    import torch
+    from frameino_b200 import ops
+
+    torch.manual_seed(7)
+    res = {}
+    for hd, h, n in [(128, 24, 28160), (64, 48, 19126)]:
+        D = h * hd
+        qkv = torch.randn(1, n, 3 * D, device="cuda").bfloat16()
+        o = torch.empty(1, n, D, device="cuda", dtype=torch.bfloat16)
+        # accuracy on a smaller, peaky problem
+        b2, h2, n2 = 1, 3, 1500
+        small = (torch.randn(b2, n2, 3 * h2 * hd, device="cuda") * 2.0).bfloat16()
+        D2 = h2 * hd
+        ref = _attn_ref(small[..., :D2], small[..., D2:2 * D2], small[..., 2 * D2:], h2)
+        for v in (1, 2, 3, 4, 5):
+            ops.attention_set_variant(v)
+            out = ops.attention(small[..., :D2], small[..., D2:2 * D2], small[..., 2 * D2:], h2)
+            res[f"d{hd}_v{v}_rel"] = _rel(out, ref)
+            f = lambda: ops.attention(qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:], h, out=o)
+            ms = _time_ms(f, iters=4, warmup=1)
+            res[f"d{hd}_v{v}_tflops"] = 4.0 * n * n * D / ms / 1e9
+    ops.attention_set_variant(0)
+    return res
+
+
 CHECKS = {
+    "attn_variants": check_attn_variants,
     "gemm2": check_gemm2,
     "ln": check_ln,
     "gate": check_gate,
