@@ -144,6 +144,100 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
   }
 }
 
+// Block-per-row variant for wide rows: thread c owns 16-byte chunk c of every row the CTA processes, so the LayerNorm
+// affine and the AdaLN shift / scale values for its 8 columns stay in REGISTERS across rows and are re-read only when
+// the modulation row changes (with the warp-per-row kernel every row pulled 24 KB of fp32 modulation through L1 for
+// 12 KB of activation traffic, and L1 bandwidth, not HBM, set the pace: profiles/r01_rows_ncu.txt).
+constexpr int LN_ROWS_PER_BLOCK = 16;
+
+__global__ void __launch_bounds__(1024)
+ln_modulate_block_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t rows, int dim,
+                         int64_t x_stride, int64_t out_stride, float eps, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, const float* __restrict__ shift,
+                         const float* __restrict__ scale, int64_t mod_row_stride,
+                         const int32_t* __restrict__ row_index, int64_t rows_per_group, int flags) {
+  __shared__ float red[2][32];
+  const int c = threadIdx.x;
+  const int lane = c & 31, warp = c >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int nchunks = dim >> 3;
+  const bool active = c < nchunks;
+  const bool steps = (flags & LN_FLAG_BF16_STEPS) != 0;
+  const float inv_dim = 1.0f / (float)dim;
+  float g8[8], b8[8], sc8[8], sh8[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    g8[e] = 1.f;
+    b8[e] = 0.f;
+    sc8[e] = 0.f;
+    sh8[e] = 0.f;
+  }
+  if (active && gamma != nullptr) ld8f(gamma + c * 8, g8);
+  if (active && beta != nullptr) ld8f(beta + c * 8, b8);
+  int64_t cached_g = -1;
+  const int64_t r0 = (int64_t)blockIdx.x * LN_ROWS_PER_BLOCK;
+  const int64_t r1 = min(rows, r0 + (int64_t)LN_ROWS_PER_BLOCK);
+  uint4 cur = make_uint4(0, 0, 0, 0);
+  if (active && r0 < r1) cur = ld_stream(reinterpret_cast<const uint4*>(x + r0 * x_stride) + c);
+  for (int64_t row = r0; row < r1; ++row) {
+    float v[8];
+    unpack8(cur, v);
+    if (active && row + 1 < r1) cur = ld_stream(reinterpret_cast<const uint4*>(x + (row + 1) * x_stride) + c);  // prefetch
+    float s = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s += v[e];
+    s = warp_sum(s);
+    if (lane == 0) red[0][warp] = s;
+    __syncthreads();
+    float tot = 0.f;
+    for (int w = 0; w < nwarps; ++w) tot += red[0][w];
+    const float mean = tot * inv_dim;
+    float sq = 0.f;
+    if (active) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = v[e] - mean;
+        sq += d * d;
+      }
+    }
+    sq = warp_sum(sq);
+    if (lane == 0) red[1][warp] = sq;
+    __syncthreads();
+    float tsq = 0.f;
+    for (int w = 0; w < nwarps; ++w) tsq += red[1][w];
+    const float rstd = rsqrtf(tsq * inv_dim + eps);
+    if (shift != nullptr) {
+      const int64_t g = row_index ? (int64_t)row_index[row] : row / rows_per_group;
+      if (g != cached_g) {  // block-uniform
+        cached_g = g;
+        if (active) {
+          ld8f(scale + g * mod_row_stride + c * 8, sc8);
+          ld8f(shift + g * mod_row_stride + c * 8, sh8);
+        }
+      }
+    }
+    if (active) {
+      float y[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) y[e] = (v[e] - mean) * rstd;
+      if (gamma != nullptr) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = y[e] * g8[e] + b8[e];
+      }
+      if (shift != nullptr) {
+        if (steps) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) y[e] = rbf(rbf(y[e]) * rbf(1.0f + sc8[e])) + sh8[e];
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) y[e] = y[e] * (1.0f + sc8[e]) + sh8[e];
+        }
+      }
+      reinterpret_cast<uint4*>(out + row * out_stride)[c] = pack8(y);
+    }
+  }
+}
+
 int ln_modulate(const void* x, void* out, int64_t rows, int dim, int64_t x_stride, int64_t out_stride, float eps,
                 const float* gamma, const float* beta, const float* shift, const float* scale, int64_t mod_row_stride,
                 const int32_t* row_index, int64_t rows_per_group, int flags, cudaStream_t stream) {
@@ -158,6 +252,15 @@ int ln_modulate(const void* x, void* out, int64_t rows, int dim, int64_t x_strid
   const int cpl = (dim / 8 + 31) / 32;
   dim3 grid((unsigned)((rows + ROW_WARPS - 1) / ROW_WARPS));
   if (rows_per_group <= 0) rows_per_group = (int64_t)1 << 62;
+  if (dim >= 1024 && rows >= 64) {  // wide rows: block-per-row kernel, modulation held in registers
+    const int threads = ((dim / 8 + 31) / 32) * 32;
+    dim3 bgrid((unsigned)((rows + LN_ROWS_PER_BLOCK - 1) / LN_ROWS_PER_BLOCK));
+    ln_modulate_block_kernel<<<bgrid, threads, 0, stream>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)out, rows, dim, x_stride, out_stride, eps, gamma, beta, shift, scale,
+        mod_row_stride, row_index, rows_per_group, flags);
+    FINO_CHECK_CUDA(cudaGetLastError());
+    return FINO_OK;
+  }
 #define LAUNCH_LN(C)                                                                                                 \
   ln_modulate_kernel<C><<<grid, ROW_WARPS * 32, 0, stream>>>(                                                        \
       (const __nv_bfloat16*)x, (__nv_bfloat16*)out, rows, dim, x_stride, out_stride, eps, gamma, beta, shift, scale, \

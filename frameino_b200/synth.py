@@ -240,3 +240,49 @@ def build_wan_on_device(cfg: dict, seed: int = 0, device="cuda", dtype: torch.dt
             p.data = t.to(torch.float32 if keep else dtype)
     model.rope = WanRotaryPosEmbed(cfg["attention_head_dim"], cfg["patch_size"], cfg["rope_max_seq_len"]).to(device)
     return model.eval()
+
+
+def build_cog_on_device(cfg: dict, seed: int = 0, device="cuda", dtype: torch.dtype = torch.bfloat16):
+    """Random-init ``frameino_b200.CogVideoXTransformer3DModel`` materialised directly on ``device``."""
+    from .cogvideox import CogVideoXTransformer3DModel
+
+    with torch.device("meta"):
+        model = CogVideoXTransformer3DModel(**cfg)
+    shapes = cog_param_shapes(cfg)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    model.to_empty(device=device)
+    tensors = dict(model.named_parameters())
+    tensors.update(dict(model.named_buffers()))
+    assert set(shapes) <= set(tensors), "state-dict layout drifted from synth.cog_param_shapes"
+    with torch.no_grad():
+        for name in sorted(shapes):
+            t = _fill(name, shapes[name], gen, device).to(dtype)
+            if name == "patch_embed.pos_embedding":
+                t[:, : cfg["max_text_seq_length"]] = 0
+            tensors[name].data = t
+    return model.eval()
+
+
+def cog_rope_tables(head_dim: int, grid_h: int, grid_w: int, frames: int, n_id: int = 1, device="cpu"):
+    """(cos, sin) [frames*gh*gw + n_id*gh*gw, head_dim] fp32 as the FrameINO CogVideoX pipeline builds them
+    (pipelines/pipeline_cogvideox_i2v_motion_FrameINO.py:540-584, :834-839; embeddings.py:864-962): linspace grids,
+    bands t d/4 | h 3d/8 | w 3d/8, interleaved-repeated, ID frames = copies of frame 0."""
+    def band(dim, pos):
+        freqs = 1.0 / (10000.0 ** (torch.arange(0, dim, 2, dtype=torch.float32)[: dim // 2] / dim))
+        ang = torch.outer(pos, freqs)
+        return ang.cos().repeat_interleave(2, dim=1), ang.sin().repeat_interleave(2, dim=1)
+
+    gh = torch.linspace(0, grid_h * (grid_h - 1) / grid_h, grid_h, dtype=torch.float32)
+    gw = torch.linspace(0, grid_w * (grid_w - 1) / grid_w, grid_w, dtype=torch.float32)
+    gt = torch.linspace(0, frames * (frames - 1) / frames, frames, dtype=torch.float32)
+    t, h, w = band(head_dim // 4, gt), band(head_dim // 8 * 3, gh), band(head_dim // 8 * 3, gw)
+    out = []
+    for i in (0, 1):
+        tab = torch.cat([t[i][:, None, None, :].expand(-1, grid_h, grid_w, -1),
+                         h[i][None, :, None, :].expand(frames, -1, grid_w, -1),
+                         w[i][None, None, :, :].expand(frames, grid_h, -1, -1)], dim=-1).reshape(frames * grid_h * grid_w, -1)
+        if n_id:
+            tab = torch.cat([tab] + [tab[: grid_h * grid_w]] * n_id, dim=0)
+        out.append(tab.contiguous().to(device))
+    return out[0], out[1]
