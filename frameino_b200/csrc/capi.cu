@@ -35,6 +35,7 @@ int build_mod_table(const float* table, const float* proj, float* out, int layer
 int swap01(const void* in, void* out, int64_t A, int64_t B, int64_t inner, cudaStream_t stream);
 void gemm_set_mode(int mode);
 void attention_set_variant(int v);
+void rows_set_variant(int ln_block, int qk_block);
 }  // namespace fino
 
 static std::atomic<int64_t> g_launches{0};
@@ -168,6 +169,11 @@ int fino_attention_set_variant(int variant) {
     return fino::FINO_ERR_INVALID;
   }
   fino::attention_set_variant(variant);
+  return 0;
+}
+
+int fino_rows_set_variant(int ln_block, int qk_block) {
+  fino::rows_set_variant(ln_block, qk_block);
   return 0;
 }
 

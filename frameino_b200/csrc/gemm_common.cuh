@@ -67,19 +67,19 @@ __device__ __forceinline__ const float* gate_row_ptr(const GemmParams& p, int64_
 }
 
 // One 32-column chunk of one accumulator row: bias, activation / gated residual, convert, 16-byte stores.
+// `bias32`: pointer to the 32 bias values of this chunk (global or shared memory), or null.
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int64_t row, int col0, const float* gate_row,
-                                               const uint32_t (&r)[32]) {
+                                               const uint32_t (&r)[32], const __nv_bfloat16* bias32) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
   const int ncol = min(32, p.N - col0);
-  const __nv_bfloat16* __restrict__ bias = p.bias;
-  if (bias != nullptr) {
+  if (bias32 != nullptr) {
     if (ncol == 32) {
-      const uint4* bp = reinterpret_cast<const uint4*>(bias + col0);
+      const uint4* bp = reinterpret_cast<const uint4*>(bias32);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        uint4 b = __ldg(bp + j);
+        uint4 b = bp[j];
         v[8 * j + 0] += bf16_lo_to_f32(b.x);
         v[8 * j + 1] += bf16_hi_to_f32(b.x);
         v[8 * j + 2] += bf16_lo_to_f32(b.y);
@@ -90,7 +90,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int64_t row,
         v[8 * j + 7] += bf16_hi_to_f32(b.w);
       }
     } else {
-      for (int j = 0; j < ncol; ++j) v[j] += __bfloat162float(bias[col0 + j]);
+      for (int j = 0; j < ncol; ++j) v[j] += __bfloat162float(bias32[j]);
     }
   }
   if (p.epilogue == EPI_GELU_TANH) {

@@ -161,7 +161,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr_row + c * 32, r);
         tmem_wait_ld();
-        if (row_ok) epilogue_chunk(p, row, col0, gate_row, r);
+        if (row_ok) epilogue_chunk(p, row, col0, gate_row, r, p.bias ? p.bias + col0 : nullptr);
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
@@ -190,14 +190,16 @@ struct Gemm2Cfg {
   static constexpr int kABytes = MH * GEMM_BM * GEMM_BK * 2;   // this CTA's MH*128 rows of A
   static constexpr int kBBytes = (BN / 2) * GEMM_BK * 2;       // this CTA's half (128 rows) of the W tile
   static constexpr int kStageBytes = kABytes + kBBytes;        // 32 KB / 48 KB
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + 8 * 512;  // + per-warp bias staging
   static constexpr int kAccStages = (MH == 1) ? 2 : 1;
   static constexpr int kTmemCols = 512;
   static constexpr int kTileM = 2 * MH * GEMM_BM;              // rows per cluster tile
+  static constexpr int kEpiWarps = 4 * MH;                     // one epilogue warp per (M-half, TMEM lane quadrant)
+  static constexpr int kThreads = 128 + 32 * kEpiWarps;        // 256 / 384
 };
 
 template <int MH>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg<MH>::kThreads, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const GemmParams p) {
   using Cfg = Gemm2Cfg<MH>;
@@ -233,7 +235,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 8);  // 4 epilogue warps x 2 CTAs
+      mbar_init(tempty_bar(s), 2 * Cfg::kEpiWarps);  // every epilogue warp of both CTAs
     }
     fence_barrier_init();
   }
@@ -308,37 +310,59 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (both CTAs, own MH*128 rows) =====================
+    // ===================== epilogue (both CTAs; warp -> (M-half, TMEM lane quadrant)) =====================
+    // Software-pipelined drain: the tcgen05.ld of chunk c+1 is in flight while chunk c is converted and stored, the
+    // tile's bias slice is staged in shared memory before the accumulator is ready, and the accumulator is handed
+    // back to the MMA warp as soon as the last TMEM read has landed (before the last chunk is written out).
     const int q = warp & 3;
+    const int ew = warp - 4;
+    const int mh = (MH == 2) ? (ew >> 2) : 0;
+    const uint32_t bias_s_u32 = bars + 8u * (2 * kStages + 6) + ew * 512u;  // 512 B per epilogue warp
+    const __nv_bfloat16* bias_s = reinterpret_cast<const __nv_bfloat16*>(
+        smem_raw + (bias_s_u32 - smem_u32(smem_raw)));
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
       int mt, nt;
       tile_coords(tile, p.num_m_tiles, p.num_n_tiles, mt, nt);
       const int acc = (kAcc == 2) ? (it & 1) : 0;
       const uint32_t acc_phase = (kAcc == 2) ? ((it >> 1) & 1) : (it & 1);
+      if (p.bias != nullptr) {  // stage bias[nt*256 .. +256) while the main loop is still running
+        const int colb = nt * BN + lane * 8;
+        uint4 b = make_uint4(0, 0, 0, 0);
+        if (colb + 8 <= p.N) b = __ldg(reinterpret_cast<const uint4*>(p.bias + colb));
+        else
+          for (int j = 0; j < 8; ++j)
+            if (colb + j < p.N) reinterpret_cast<__nv_bfloat16*>(&b)[j] = p.bias[colb + j];
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(bias_s_u32 + lane * 16), "r"(b.x), "r"(b.y),
+                     "r"(b.z), "r"(b.w)
+                     : "memory");
+        __syncwarp();
+      }
+      const int64_t row = (int64_t)mt * Cfg::kTileM + (int64_t)cta_rank * (MH * GEMM_BM) + mh * GEMM_BM + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      const float* gate_row = gate_row_ptr(p, row, row_ok);
+      const uint32_t taddr_row =
+          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ((kAcc == 2) ? acc * BN : mh * BN);
+      const int nchunk = min(BN / 32, (p.N - nt * BN + 31) / 32);  // warp-uniform
       mbar_wait_cluster(tfull_bar(acc), acc_phase, 400 + acc);
       tc_fence_after();
-#pragma unroll 1
-      for (int mh = 0; mh < MH; ++mh) {
-        const int64_t row =
-            (int64_t)mt * Cfg::kTileM + (int64_t)cta_rank * (MH * GEMM_BM) + mh * GEMM_BM + q * 32 + lane;
-        const bool row_ok = row < p.M;
-        const float* gate_row = gate_row_ptr(p, row, row_ok);
-        const uint32_t taddr_row =
-            tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ((kAcc == 2) ? acc * BN : mh * BN);
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          const int col0 = nt * BN + c * 32;
-          if (col0 >= p.N) break;  // warp-uniform
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(taddr_row + c * 32, r);
-          tmem_wait_ld();
-          if (row_ok) epilogue_chunk(p, row, col0, gate_row, r);
+      uint32_t buf[2][32];
+      tmem_ld_32x32b_x32(taddr_row, buf[0]);
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        if (c < nchunk) {
+          tmem_wait_ld();  // chunk c has landed
+          if (c + 1 < nchunk) tmem_ld_32x32b_x32(taddr_row + (c + 1) * 32, buf[(c + 1) & 1]);
+          if (c + 1 == nchunk) {  // every TMEM read of this warp is done: release the accumulator early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
+          }
+          if (row_ok)
+            epilogue_chunk(p, row, nt * BN + c * 32, gate_row, buf[c & 1], p.bias ? bias_s + c * 32 : nullptr);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);  // to the leader's barrier
+      __syncwarp();  // bias_s is rewritten for the next tile
     }
   }
 
@@ -382,7 +406,7 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int clusters = num_sms() / 2;
   if (tiles < clusters) clusters = tiles;
-  gemm2_bf16_kernel<MH><<<2 * clusters, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  gemm2_bf16_kernel<MH><<<2 * clusters, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   FINO_CHECK_CUDA(cudaGetLastError());
   return FINO_OK;
 }

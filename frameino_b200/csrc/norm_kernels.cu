@@ -149,6 +149,12 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
 // the modulation row changes (with the warp-per-row kernel every row pulled 24 KB of fp32 modulation through L1 for
 // 12 KB of activation traffic, and L1 bandwidth, not HBM, set the pace: profiles/r01_rows_ncu.txt).
 constexpr int LN_ROWS_PER_BLOCK = 16;
+static bool g_ln_block_kernel = false;  // measured 2.4 TB/s vs 3.6 TB/s for the warp-per-row kernel (r01)
+static bool g_qk_block_kernel = true;
+void rows_set_variant(int ln_block, int qk_block) {
+  g_ln_block_kernel = ln_block != 0;
+  g_qk_block_kernel = qk_block != 0;
+}
 
 __global__ void __launch_bounds__(1024)
 ln_modulate_block_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t rows, int dim,
@@ -252,7 +258,7 @@ int ln_modulate(const void* x, void* out, int64_t rows, int dim, int64_t x_strid
   const int cpl = (dim / 8 + 31) / 32;
   dim3 grid((unsigned)((rows + ROW_WARPS - 1) / ROW_WARPS));
   if (rows_per_group <= 0) rows_per_group = (int64_t)1 << 62;
-  if (dim >= 1024 && rows >= 64) {  // wide rows: block-per-row kernel, modulation held in registers
+  if (g_ln_block_kernel && dim >= 1024 && rows >= 64) {  // experimental block-per-row kernel (slower today)
     const int threads = ((dim / 8 + 31) / 32) * 32;
     dim3 bgrid((unsigned)((rows + LN_ROWS_PER_BLOCK - 1) / LN_ROWS_PER_BLOCK));
     ln_modulate_block_kernel<<<bgrid, threads, 0, stream>>>(
@@ -479,6 +485,109 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) qk_norm_rope_kernel(const QkPa
   }
 }
 
+// Block-per-token variant of the RMS-across-heads path (Wan self-attention): thread c owns 16-byte chunk c of the q
+// row AND of the k row of each token the CTA processes. The RMSNorm weights of its 8 columns live in registers for
+// the whole CTA, the cos/sin values of the token are fetched once and used for both q and k, and the two
+// sum-of-squares reductions share one __syncthreads per token.
+constexpr int QK_TOKENS_PER_BLOCK = 8;
+
+__global__ void __launch_bounds__(512) qk_rms_rope_block_kernel(const QkParams p) {
+  __shared__ float red[2][2][32];
+  const int c = threadIdx.x;
+  const int lane = c & 31, warp = c >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int dim = p.heads * p.head_dim;
+  const int nchunks = dim >> 3;
+  const bool active = c < nchunks;
+  const float inv_dim = 1.0f / (float)dim;
+  const QkTensor& tq = p.t[0];
+  const QkTensor& tk = p.t[1];
+  float wq[8], wk[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) wq[e] = wk[e] = 1.f;
+  if (active && tq.weight != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(tq.weight) + c), wq);
+  if (active && tk.weight != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(tk.weight) + c), wk);
+  const int off = (c * 8) % p.head_dim;
+  const int64_t t0 = (int64_t)blockIdx.x * QK_TOKENS_PER_BLOCK;
+  const int64_t t1 = min(tq.rows, t0 + (int64_t)QK_TOKENS_PER_BLOCK);
+  uint4 uq = make_uint4(0, 0, 0, 0), uk = make_uint4(0, 0, 0, 0);
+  if (active && t0 < t1) {
+    uq = reinterpret_cast<const uint4*>(tq.ptr + t0 * tq.row_stride)[c];
+    uk = reinterpret_cast<const uint4*>(tk.ptr + t0 * tk.row_stride)[c];
+  }
+  int it = 0;
+  for (int64_t tok = t0; tok < t1; ++tok, ++it) {
+    float q[8], k[8];
+    unpack8(uq, q);
+    unpack8(uk, k);
+    uint4* qrow = reinterpret_cast<uint4*>(tq.ptr + tok * tq.row_stride);
+    uint4* krow = reinterpret_cast<uint4*>(tk.ptr + tok * tk.row_stride);
+    if (active && tok + 1 < t1) {  // prefetch the next token's rows
+      uq = reinterpret_cast<const uint4*>(tq.ptr + (tok + 1) * tq.row_stride)[c];
+      uk = reinterpret_cast<const uint4*>(tk.ptr + (tok + 1) * tk.row_stride)[c];
+    }
+    const int64_t s_in_seq = tok % p.seq_len;
+    const bool do_rope = p.rope_mode != ROPE_NONE && s_in_seq >= p.rope_skip;
+    float cs[8], sn[8];
+    if (do_rope && active) {
+      ld8f(p.cos + (s_in_seq - p.rope_skip) * p.head_dim + off, cs);
+      ld8f(p.sin + (s_in_seq - p.rope_skip) * p.head_dim + off, sn);
+    }
+    float sq = 0.f, sk = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sq += q[e] * q[e];
+      sk += k[e] * k[e];
+    }
+    sq = warp_sum(sq);
+    sk = warp_sum(sk);
+    if (lane == 0) {
+      red[it & 1][0][warp] = sq;
+      red[it & 1][1][warp] = sk;
+    }
+    __syncthreads();
+    float tq2 = 0.f, tk2 = 0.f;
+    for (int w = 0; w < nwarps; ++w) {
+      tq2 += red[it & 1][0][w];
+      tk2 += red[it & 1][1][w];
+    }
+    const float rq = rsqrtf(tq2 * inv_dim + p.eps);
+    const float rk = rsqrtf(tk2 * inv_dim + p.eps);
+    if (active) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        q[e] = tq.weight ? rbf(rbf(q[e] * rq) * wq[e]) : rbf(q[e] * rq);
+        k[e] = tk.weight ? rbf(rbf(k[e] * rk) * wk[e]) : rbf(k[e] * rk);
+      }
+      if (do_rope) {
+        float oq[8], ok[8];
+        if (p.rope_mode == ROPE_WAN) {
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            oq[e] = __fsub_rn(__fmul_rn(q[e], cs[e]), __fmul_rn(q[e + 1], sn[e + 1]));
+            oq[e + 1] = __fadd_rn(__fmul_rn(q[e], sn[e + 1]), __fmul_rn(q[e + 1], cs[e]));
+            ok[e] = __fsub_rn(__fmul_rn(k[e], cs[e]), __fmul_rn(k[e + 1], sn[e + 1]));
+            ok[e + 1] = __fadd_rn(__fmul_rn(k[e], sn[e + 1]), __fmul_rn(k[e + 1], cs[e]));
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; e += 2) {
+            oq[e] = __fadd_rn(__fmul_rn(q[e], cs[e]), __fmul_rn(-q[e + 1], sn[e]));
+            oq[e + 1] = __fadd_rn(__fmul_rn(q[e + 1], cs[e + 1]), __fmul_rn(q[e], sn[e + 1]));
+            ok[e] = __fadd_rn(__fmul_rn(k[e], cs[e]), __fmul_rn(-k[e + 1], sn[e]));
+            ok[e + 1] = __fadd_rn(__fmul_rn(k[e + 1], cs[e + 1]), __fmul_rn(k[e], sn[e + 1]));
+          }
+        }
+        qrow[c] = pack8(oq);
+        krow[c] = pack8(ok);
+      } else {
+        qrow[c] = pack8(q);
+        krow[c] = pack8(k);
+      }
+    }
+  }
+}
+
 int qk_norm_rope(void* x0, int64_t rows0, int64_t stride0, const void* w0, const void* b0, int rope0, void* x1,
                  int64_t rows1, int64_t stride1, const void* w1, const void* b1, int rope1, int heads, int head_dim,
                  int norm_mode, float eps, int rope_mode, const float* cos, const float* sin, int64_t seq_len,
@@ -510,6 +619,14 @@ int qk_norm_rope(void* x0, int64_t rows0, int64_t stride0, const void* w0, const
   p.rope_skip = rope_skip;
   p.blocks0 = (rows0 + ROW_WARPS - 1) / ROW_WARPS;
   const int64_t blocks1 = x1 ? (rows1 + ROW_WARPS - 1) / ROW_WARPS : 0;
+  if (g_qk_block_kernel && norm_mode == QK_RMS_ACROSS_HEADS && x1 != nullptr && rows0 == rows1 && rows0 >= 64 && dim >= 1024 && dim <= 4096 &&
+      (p.rope_mode == ROPE_NONE || (rope0 && rope1))) {
+    const int threads = ((dim / 8 + 31) / 32) * 32;
+    dim3 bgrid((unsigned)((rows0 + QK_TOKENS_PER_BLOCK - 1) / QK_TOKENS_PER_BLOCK));
+    qk_rms_rope_block_kernel<<<bgrid, threads, 0, stream>>>(p);
+    FINO_CHECK_CUDA(cudaGetLastError());
+    return FINO_OK;
+  }
   const int cpl = (dim / 8 + 31) / 32;
   dim3 grid((unsigned)(p.blocks0 + blocks1));
 #define LAUNCH_QK(C) qk_norm_rope_kernel<C><<<grid, ROW_WARPS * 32, 0, stream>>>(p)

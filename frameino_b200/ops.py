@@ -339,5 +339,9 @@ def attention_set_variant(variant: int) -> None:
     _lib.check(_lib.load().fino_attention_set_variant(variant), "fino_attention_set_variant")
 
 
+def rows_set_variant(ln_block: bool, qk_block: bool) -> None:
+    _lib.check(_lib.load().fino_rows_set_variant(int(ln_block), int(qk_block)), "fino_rows_set_variant")
+
+
 def launch_count() -> int:
     return int(_lib.load().fino_launch_count())

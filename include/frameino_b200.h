@@ -62,6 +62,9 @@ int fino_attention_fwd(const void* q, const void* k, const void* v, void* o, int
 /* Tuning / test hook: scheduling variant of the attention kernel (0 = default; 1..5 see attention_tcgen05.cu). */
 int fino_attention_set_variant(int variant);
 
+/* Tuning / test hook: choose the block-per-row variants of the LayerNorm / qk-norm kernels (0 = warp-per-row). */
+int fino_rows_set_variant(int ln_block, int qk_block);
+
 #define FINO_LN_FLAG_BF16_STEPS 1 /* emulate the bf16 module flow of CogVideoXLayerNormZero / AdaLayerNorm */
 
 /* out = LayerNorm(x) [*gamma + beta] [*(1+scale) + shift], fp32 math, one rounding.
