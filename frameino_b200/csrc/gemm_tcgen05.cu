@@ -283,11 +283,12 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
         const int acc = (kAcc == 2) ? (it & 1) : 0;
         const uint32_t acc_phase = (kAcc == 2) ? ((it >> 1) & 1) : (it & 1);
-        mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u, 200 + acc);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 200 + acc);
+        fence_acq_rel_cluster();  // the arrivals are remote (peer epilogue warps, release.cluster)
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + ((kAcc == 2) ? acc * BN : 0);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait_cluster(full_bar(stage), phase, 300 + stage);
+          mbar_wait(full_bar(stage), phase, 300 + stage);
           tc_fence_after();
           uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
           uint32_t b_addr = a_addr + Cfg::kABytes;
@@ -344,7 +345,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const uint32_t taddr_row =
           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ((kAcc == 2) ? acc * BN : mh * BN);
       const int nchunk = min(BN / 32, (p.N - nt * BN + 31) / 32);  // warp-uniform
-      mbar_wait_cluster(tfull_bar(acc), acc_phase, 400 + acc);
+      mbar_wait(tfull_bar(acc), acc_phase, 400 + acc);
       tc_fence_after();
       uint32_t buf[2][32];
       tmem_ld_32x32b_x32(taddr_row, buf[0]);

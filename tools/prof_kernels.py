@@ -11,6 +11,10 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from frameino_b200 import ops  # noqa: E402
 
 which = sys.argv[1:] or ["attn", "gemm", "ln", "qk"]
+if os.environ.get("FINO_GEMM_MODE"):
+    ops.gemm_set_mode(int(os.environ["FINO_GEMM_MODE"]))
+if os.environ.get("FINO_ATTN_VARIANT"):
+    ops.attention_set_variant(int(os.environ["FINO_ATTN_VARIANT"]))
 n, h, hd = 28160, 24, 128
 d = h * hd
 torch.manual_seed(0)
