@@ -34,10 +34,11 @@ METRIC = "wan22_5b_frameino_denoise_step_ms"
 UNIT = "ms"
 
 
-def workload(frames: int):
-    """Latent geometry of a 704x1280 canvas with `frames` pixel frames + 1 ID frame."""
+def workload(frames: int, height: int = 704, width: int = 1280):
+    """Latent geometry of a height x width canvas with `frames` pixel frames + 1 ID frame (SURVEY.md §8d config 2;
+    832 x 1536 is config 5, the expanded canvas)."""
     lat_f = (frames - 1) // 4 + 1
-    h, w = 704 // 16, 1280 // 16
+    h, w = height // 16, width // 16
     tokens = (lat_f + 1) * (h // 2) * (w // 2)
     return lat_f, h, w, tokens
 
@@ -175,7 +176,7 @@ def run_reference(args, tokens):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": v, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"Wan2.2-TI2V-5B FrameINO one denoise-step forward, 704x1280x{args.frames} + 1 ID frame, "
+        "config": {"workload": f"Wan2.2-TI2V-5B FrameINO one denoise-step forward, {args.height}x{args.width}x{args.frames} + 1 ID frame, "
                                f"{tokens} tokens, B=1 (CPU oracle port)"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample.describe()},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -301,7 +302,7 @@ def run_native(args, lat_f, h, w, tokens):
         "metric": METRIC, "value": ms, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"Wan2.2-TI2V-5B FrameINO one denoise-step forward, 704x1280x{args.frames} + 1 ID frame, "
+        "config": {"workload": f"Wan2.2-TI2V-5B FrameINO one denoise-step forward, {args.height}x{args.width}x{args.frames} + 1 ID frame, "
                                f"{tokens} tokens, B=1, per-token timesteps, 512 text tokens",
                    "parallelism": "single GPU" if world == 1 else f"ulysses sequence parallel x{world}",
                    "l2": "inputs larger than L2 (activations 173 MB per [N,D] tensor, weights 10 GB per forward)"},
@@ -335,9 +336,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--frames", type=int, default=121, help="pixel frames of the canvas (121 = BASELINE config 2)")
+    ap.add_argument("--height", type=int, default=704, help="canvas height in pixels (multiple of 32)")
+    ap.add_argument("--width", type=int, default=1280, help="canvas width in pixels (multiple of 32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    lat_f, h, w, tokens = workload(args.frames)
+    lat_f, h, w, tokens = workload(args.frames, args.height, args.width)
     if args.impl == "reference":
         run_reference(args, tokens)
     else:
