@@ -49,13 +49,19 @@ __device__ __forceinline__ void tile_coords(int tile, int num_m, int num_n, int&
   mt = first_m + (r - nt * gm);
 }
 
-__device__ __forceinline__ float gelu_tanh_f(float x) {
-  // 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715x^3)))  (torch GELU(approximate="tanh"))
-  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
-  float inner = k0 * (x + k1 * x * x * x);
-  return 0.5f * x * (1.0f + tanhf(inner));
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// 0.5*x*(1+tanh(u)), u = sqrt(2/pi)*(x+0.044715x^3)  (torch GELU(approximate="tanh")), written as x*sigmoid(2u) =
+// x / (1 + 2^(-2u*log2e)): two MUFU ops (ex2, rcp), absolute error ~1e-7 * |x| — far below the bf16 rounding that follows.
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  const float u = k0 * (x + k1 * x * x * x);
+  return x * rcp_approx(1.0f + ex2_approx(-2.885390081777927f * u));
+}
+__device__ __forceinline__ float silu_f(float x) { return x * rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 __device__ __forceinline__ const float* gate_row_ptr(const GemmParams& p, int64_t row, bool row_ok) {
@@ -66,102 +72,85 @@ __device__ __forceinline__ const float* gate_row_ptr(const GemmParams& p, int64_
   return nullptr;
 }
 
-// One 32-column chunk of one accumulator row: bias, activation / gated residual, convert, 16-byte stores.
-// `bias32`: pointer to the 32 bias values of this chunk (global or shared memory), or null.
+// Residual values of one 32-column chunk of one row, fetched one chunk ahead of their use (EPI_GATE_RESIDUAL only).
+struct ResidualChunk {
+  uint4 v[4];
+};
+template <int EPI>
+__device__ __forceinline__ void load_residual_chunk(const GemmParams& p, int64_t row, int col0, bool row_ok,
+                                                    ResidualChunk& rc) {
+  if (EPI != EPI_GATE_RESIDUAL) return;
+  const int ngrp = row_ok ? min(4, (p.N - col0) >> 3) : 0;
+  const uint4* rp4 = reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col0);
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    if (g < ngrp) rc.v[g] = __ldg(rp4 + g);
+}
+
+// One 32-column chunk of one accumulator row: bias, activation / gated residual, convert, 16-byte stores. N is a
+// multiple of 8 (checked by the launcher), so a ragged chunk is handled as whole 8-column groups: everything stays in
+// registers with static indices. `bias32`: the 32 bias values of this chunk (global or shared memory), or null.
+template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int64_t row, int col0, const float* gate_row,
-                                               const uint32_t (&r)[32], const __nv_bfloat16* bias32) {
-  float v[32];
+                                               const uint32_t (&r)[32], const __nv_bfloat16* bias32,
+                                               const ResidualChunk& rc) {
+  const int ngrp = min(4, (p.N - col0) >> 3);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-  const int ncol = min(32, p.N - col0);
-  if (bias32 != nullptr) {
-    if (ncol == 32) {
-      const uint4* bp = reinterpret_cast<const uint4*>(bias32);
+  for (int g = 0; g < 4; ++g) {
+    if (g < ngrp) {
+      float v[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 b = bp[j];
-        v[8 * j + 0] += bf16_lo_to_f32(b.x);
-        v[8 * j + 1] += bf16_hi_to_f32(b.x);
-        v[8 * j + 2] += bf16_lo_to_f32(b.y);
-        v[8 * j + 3] += bf16_hi_to_f32(b.y);
-        v[8 * j + 4] += bf16_lo_to_f32(b.z);
-        v[8 * j + 5] += bf16_hi_to_f32(b.z);
-        v[8 * j + 6] += bf16_lo_to_f32(b.w);
-        v[8 * j + 7] += bf16_hi_to_f32(b.w);
+      for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * g + e]);
+      if (bias32 != nullptr) {
+        const uint4 b = reinterpret_cast<const uint4*>(bias32)[g];
+        v[0] += bf16_lo_to_f32(b.x);
+        v[1] += bf16_hi_to_f32(b.x);
+        v[2] += bf16_lo_to_f32(b.y);
+        v[3] += bf16_hi_to_f32(b.y);
+        v[4] += bf16_lo_to_f32(b.z);
+        v[5] += bf16_hi_to_f32(b.z);
+        v[6] += bf16_lo_to_f32(b.w);
+        v[7] += bf16_hi_to_f32(b.w);
       }
-    } else {
-      for (int j = 0; j < ncol; ++j) v[j] += __bfloat162float(bias32[j]);
-    }
-  }
-  if (p.epilogue == EPI_GELU_TANH) {
+      if (EPI == EPI_GELU_TANH) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_tanh_f(round_bf16(v[j]));
-  } else if (p.epilogue == EPI_SILU) {
+        for (int e = 0; e < 8; ++e) v[e] = gelu_tanh_f(round_bf16(v[e]));
+      } else if (EPI == EPI_SILU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = silu_f(round_bf16(v[j]));
-  } else if (p.epilogue == EPI_GATE_RESIDUAL) {
-    const __nv_bfloat16* rp = p.residual + row * p.ldr + col0;
-    if (ncol == 32) {
-      float g[32];
-      if (gate_row != nullptr) {
-        const float4* gp = reinterpret_cast<const float4*>(gate_row + col0);
+        for (int e = 0; e < 8; ++e) v[e] = silu_f(round_bf16(v[e]));
+      } else if (EPI == EPI_GATE_RESIDUAL) {
+        float gt[8];
+        if (gate_row != nullptr) {
+          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate_row + col0) + 2 * g);
+          const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate_row + col0) + 2 * g + 1);
+          gt[0] = g0.x, gt[1] = g0.y, gt[2] = g0.z, gt[3] = g0.w;
+          gt[4] = g1.x, gt[5] = g1.y, gt[6] = g1.z, gt[7] = g1.w;
+        } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 t = __ldg(gp + j);
-          g[4 * j + 0] = t.x;
-          g[4 * j + 1] = t.y;
-          g[4 * j + 2] = t.z;
-          g[4 * j + 3] = t.w;
+          for (int e = 0; e < 8; ++e) gt[e] = 1.0f;
         }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) g[j] = 1.0f;
-      }
-      const uint4* rp4 = reinterpret_cast<const uint4*>(rp);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 x = __ldg(rp4 + j);
-        float xr[8] = {bf16_lo_to_f32(x.x), bf16_hi_to_f32(x.x), bf16_lo_to_f32(x.y), bf16_hi_to_f32(x.y),
-                       bf16_lo_to_f32(x.z), bf16_hi_to_f32(x.z), bf16_lo_to_f32(x.w), bf16_hi_to_f32(x.w)};
+        const uint4 x = rc.v[g];
+        const float xr[8] = {bf16_lo_to_f32(x.x), bf16_hi_to_f32(x.x), bf16_lo_to_f32(x.y), bf16_hi_to_f32(x.y),
+                             bf16_lo_to_f32(x.z), bf16_hi_to_f32(x.z), bf16_lo_to_f32(x.w), bf16_hi_to_f32(x.w)};
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          float y = round_bf16(v[8 * j + e]) * g[8 * j + e];
+          float y = round_bf16(v[e]) * gt[e];
           if (p.flags & GEMM_FLAG_ROUND_PRODUCT) y = round_bf16(y);
-          v[8 * j + e] = xr[e] + y;
+          v[e] = xr[e] + y;
         }
       }
-    } else {
-      for (int j = 0; j < ncol; ++j) {
-        float g = gate_row ? gate_row[col0 + j] : 1.0f;
-        float y = round_bf16(v[j]) * g;
-        if (p.flags & GEMM_FLAG_ROUND_PRODUCT) y = round_bf16(y);
-        v[j] = __bfloat162float(rp[j]) + y;
-      }
-    }
-  }
-  if (p.out_fp32) {
-    float* cp = reinterpret_cast<float*>(p.C) + row * p.ldc + col0;
-    if (ncol == 32) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        reinterpret_cast<float4*>(cp)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    } else {
-      for (int j = 0; j < ncol; ++j) cp[j] = v[j];
-    }
-  } else {
-    __nv_bfloat16* cp = reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0;
-    if (ncol == 32) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      if (p.out_fp32) {
+        float4* cp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + row * p.ldc + col0) + 2 * g;
+        cp[0] = make_float4(v[0], v[1], v[2], v[3]);
+        cp[1] = make_float4(v[4], v[5], v[6], v[7]);
+      } else {
         uint4 o;
-        o.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-        o.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-        o.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-        o.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-        reinterpret_cast<uint4*>(cp)[j] = o;
+        o.x = pack_bf16x2(v[0], v[1]);
+        o.y = pack_bf16x2(v[2], v[3]);
+        o.z = pack_bf16x2(v[4], v[5]);
+        o.w = pack_bf16x2(v[6], v[7]);
+        reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0)[g] = o;
       }
-    } else {
-      for (int j = 0; j < ncol; ++j) cp[j] = __float2bfloat16_rn(v[j]);
     }
   }
 }

@@ -37,7 +37,7 @@ struct GemmCfg {
   static constexpr int kTmemCols = 2 * BN;  // 512 or 256 (power of two)
 };
 
-template <int BN>
+template <int BN, int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmParams p) {
@@ -159,9 +159,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int col0 = nt * BN + c * 32;
         if (col0 >= p.N) break;  // warp-uniform
         uint32_t r[32];
+        ResidualChunk rc;
         tmem_ld_32x32b_x32(taddr_row + c * 32, r);
+        load_residual_chunk<EPI>(p, row, col0, row_ok, rc);
         tmem_wait_ld();
-        if (row_ok) epilogue_chunk(p, row, col0, gate_row, r, p.bias ? p.bias + col0 : nullptr);
+        if (row_ok) epilogue_chunk<EPI>(p, row, col0, gate_row, r, p.bias ? p.bias + col0 : nullptr, rc);
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
@@ -198,7 +200,7 @@ struct Gemm2Cfg {
   static constexpr int kThreads = 128 + 32 * kEpiWarps;        // 256 / 384
 };
 
-template <int MH>
+template <int MH, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg<MH>::kThreads, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const GemmParams p) {
@@ -347,20 +349,38 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int nchunk = min(BN / 32, (p.N - nt * BN + 31) / 32);  // warp-uniform
       mbar_wait(tfull_bar(acc), acc_phase, 400 + acc);
       tc_fence_after();
-      uint32_t buf[2][32];
-      tmem_ld_32x32b_x32(taddr_row, buf[0]);
-#pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
-        if (c < nchunk) {
-          tmem_wait_ld();  // chunk c has landed
-          if (c + 1 < nchunk) tmem_ld_32x32b_x32(taddr_row + (c + 1) * 32, buf[(c + 1) & 1]);
-          if (c + 1 == nchunk) {  // every TMEM read of this warp is done: release the accumulator early
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
+      uint32_t buf0[32], buf1[32];
+      ResidualChunk rc0, rc1;
+      const int colt = nt * BN;
+      auto release_acc = [&]() {  // every TMEM read of this warp is done: hand the accumulator back early
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
+      };
+      tmem_ld_32x32b_x32(taddr_row, buf0);
+      load_residual_chunk<EPI>(p, row, colt, row_ok, rc0);
+      // Two chunks per iteration (static register buffers), not unrolled further: the epilogue body exists twice in
+      // the instruction stream instead of eight times (the 8x unrolled version thrashed the instruction cache).
+#pragma unroll 1
+      for (int c = 0; c < nchunk; c += 2) {
+        tmem_wait_ld();  // chunk c has landed in buf0
+        if (c + 1 < nchunk) {
+          tmem_ld_32x32b_x32(taddr_row + (c + 1) * 32, buf1);
+          load_residual_chunk<EPI>(p, row, colt + (c + 1) * 32, row_ok, rc1);
+        } else {
+          release_acc();
+        }
+        if (row_ok) epilogue_chunk<EPI>(p, row, colt + c * 32, gate_row, buf0, p.bias ? bias_s + c * 32 : nullptr, rc0);
+        if (c + 1 < nchunk) {
+          tmem_wait_ld();  // chunk c+1 has landed in buf1
+          if (c + 2 < nchunk) {
+            tmem_ld_32x32b_x32(taddr_row + (c + 2) * 32, buf0);
+            load_residual_chunk<EPI>(p, row, colt + (c + 2) * 32, row_ok, rc0);
+          } else {
+            release_acc();
           }
           if (row_ok)
-            epilogue_chunk(p, row, nt * BN + c * 32, gate_row, buf[c & 1], p.bias ? bias_s + c * 32 : nullptr);
+            epilogue_chunk<EPI>(p, row, colt + (c + 1) * 32, gate_row, buf1, p.bias ? bias_s + (c + 1) * 32 : nullptr, rc1);
         }
       }
       __syncwarp();  // bias_s is rewritten for the next tile
@@ -379,37 +399,48 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 // ================================================================================================
 // host side
 // ================================================================================================
-template <int BN>
+template <int BN, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    FINO_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FINO_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes));
     configured = true;
   }
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
-  gemm_bf16_kernel<BN><<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  gemm_bf16_kernel<BN, EPI><<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   FINO_CHECK_CUDA(cudaGetLastError());
   return FINO_OK;
 }
 
-template <int MH>
+template <int MH, int EPI>
 static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<MH>;
   static bool configured = false;
   if (!configured) {
-    FINO_CHECK_CUDA(
-        cudaFuncSetAttribute(gemm2_bf16_kernel<MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    FINO_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<MH, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes));
     configured = true;
   }
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int clusters = num_sms() / 2;
   if (tiles < clusters) clusters = tiles;
-  gemm2_bf16_kernel<MH><<<2 * clusters, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  gemm2_bf16_kernel<MH, EPI><<<2 * clusters, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   FINO_CHECK_CUDA(cudaGetLastError());
   return FINO_OK;
+}
+
+// The epilogue is a template parameter: one fused tail per kernel instance keeps the epilogue loop small enough for
+// the instruction cache (the run-time switch over four inlined tails did not).
+template <int EPI>
+static int launch_by_shape(int mh, int BN, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                           cudaStream_t stream) {
+  if (mh == 2) return launch_gemm2<2, EPI>(ta, tb, p, stream);
+  if (mh == 1) return launch_gemm2<1, EPI>(ta, tb, p, stream);
+  if (BN == 256) return launch_gemm<256, EPI>(ta, tb, p, stream);
+  return launch_gemm<128, EPI>(ta, tb, p, stream);
 }
 
 // mode: 0 = auto, 1 = single-CTA kernel, 2 = CTA pair with 256x256 cluster tiles, 3 = CTA pair with 512x256 tiles
@@ -425,6 +456,9 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
   FINO_CHECK_ARG(k % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0, "gemm: k/lda/ldw must be multiples of 8 (16-byte rows)");
   FINO_CHECK_ARG(ldc % 8 == 0, "gemm: ldc must be a multiple of 8");
   FINO_CHECK_ARG(n % 8 == 0, "gemm: n must be a multiple of 8");
+  FINO_CHECK_ARG((reinterpret_cast<uintptr_t>(c) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(bias) & 15) == 0 && (reinterpret_cast<uintptr_t>(gate) & 15) == 0,
+                 "gemm: c / residual / bias / gate must be 16-byte aligned");
   FINO_CHECK_ARG(epilogue >= EPI_NONE && epilogue <= EPI_GATE_RESIDUAL, "gemm: unknown epilogue %d", epilogue);
   if (epilogue == EPI_GATE_RESIDUAL) {
     FINO_CHECK_ARG(residual != nullptr && ldr % 8 == 0, "gemm: gate-residual epilogue needs a 16B-aligned residual");
@@ -475,10 +509,12 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
     int r = encode_tmap_bf16(&tb, w, 2, dims, strides, box);
     if (r) return r;
   }
-  if (mh == 2) return launch_gemm2<2>(ta, tb, p, stream);
-  if (mh == 1) return launch_gemm2<1>(ta, tb, p, stream);
-  if (BN == 256) return launch_gemm<256>(ta, tb, p, stream);
-  return launch_gemm<128>(ta, tb, p, stream);
+  switch (epilogue) {
+    case EPI_GELU_TANH: return launch_by_shape<EPI_GELU_TANH>(mh, BN, ta, tb, p, stream);
+    case EPI_SILU: return launch_by_shape<EPI_SILU>(mh, BN, ta, tb, p, stream);
+    case EPI_GATE_RESIDUAL: return launch_by_shape<EPI_GATE_RESIDUAL>(mh, BN, ta, tb, p, stream);
+    default: return launch_by_shape<EPI_NONE>(mh, BN, ta, tb, p, stream);
+  }
 }
 
 }  // namespace fino
