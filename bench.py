@@ -207,7 +207,7 @@ def run_native(args, lat_f, h, w, tokens):
     if world > 1:
         from frameino_b200.ulysses import enable_sequence_parallel
 
-        enable_sequence_parallel(model)
+        enable_sequence_parallel(model, mode=args.sp_mode)
     hidden, ts, text = synth.make_wan_inputs(cfg, lat_f, h, w, n_id=1, text_len=512, text_true_len=120,
                                              dtype=torch.bfloat16)
     host = [t.pin_memory() for t in (hidden, ts, text)]
@@ -244,12 +244,22 @@ def run_native(args, lat_f, h, w, tokens):
         attn_events.append((s, e, q.shape[1], k.shape[1], heads, q.shape[2] // heads))
         return o
 
+    real_attention_scatter = ops.attention_scatter
+
+    def timed_attention_scatter(q, k, v, heads, *rest):  # the same kernel with the peer-scatter epilogue (N > 1)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        real_attention_scatter(q, k, v, heads, *rest)
+        e.record()
+        attn_events.append((s, e, q.shape[1], k.shape[1], heads, q.shape[2] // heads))
+
     def timed_region(fn, steps, instrument):
         barrier()
         if instrument:
             ops.attention = timed_attention
             if model.sequence_parallel is not None:
                 model.sequence_parallel._attention = timed_attention
+                model.sequence_parallel._attention_scatter = timed_attention_scatter
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = ops.launch_count()
         s.record()
@@ -260,6 +270,7 @@ def run_native(args, lat_f, h, w, tokens):
         ops.attention = real_attention
         if model.sequence_parallel is not None:
             model.sequence_parallel._attention = real_attention
+            model.sequence_parallel._attention_scatter = real_attention_scatter
         ms = s.elapsed_time(e) / steps
         if world > 1:
             t = torch.tensor([ms], device=dev)
@@ -278,6 +289,8 @@ def run_native(args, lat_f, h, w, tokens):
     step_e2e()
     barrier()
     e2e_ms, _ = timed_region(step_e2e, args.steps, instrument=False)
+    if model.sequence_parallel is not None:
+        model.sequence_parallel.close()  # collective: unmaps the peer buffers on every rank
 
     if rank != 0:
         if world > 1:
@@ -304,7 +317,10 @@ def run_native(args, lat_f, h, w, tokens):
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"Wan2.2-TI2V-5B FrameINO one denoise-step forward, {args.height}x{args.width}x{args.frames} + 1 ID frame, "
                                f"{tokens} tokens, B=1, per-token timesteps, 512 text tokens",
-                   "parallelism": "single GPU" if world == 1 else f"ulysses sequence parallel x{world}",
+                   "parallelism": "single GPU" if world == 1 else
+                   f"ulysses sequence parallel x{world}, exchange={args.sp_mode}"
+                   + (" (fused into the RoPE-prologue / attention-epilogue stores over NVLink peer memory)"
+                      if args.sp_mode == "peer" else " (all_to_all_single)"),
                    "l2": "inputs larger than L2 (activations 173 MB per [N,D] tensor, weights 10 GB per forward)"},
         "e2e": {"value": e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
@@ -339,6 +355,8 @@ def main():
     ap.add_argument("--height", type=int, default=704, help="canvas height in pixels (multiple of 32)")
     ap.add_argument("--width", type=int, default=1280, help="canvas width in pixels (multiple of 32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sp-mode", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: Ulysses exchange fused over NVLink peer memory (default) or NCCL all_to_all_single")
     args = ap.parse_args()
     lat_f, h, w, tokens = workload(args.frames, args.height, args.width)
     if args.impl == "reference":

@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libframeino_b200.so")
@@ -39,6 +39,15 @@ SIGNATURES = {
     "fino_linear_small_m": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "fino_build_mod_table": (_I, [_P, _P, _P, _I, _I, _I, _L, _P]),
     "fino_swap01": (_I, [_P, _P, _L, _L, _L, _P]),
+    "fino_peer_alloc": (_I, [_L, _P]),
+    "fino_peer_free": (_I, [_P]),
+    "fino_peer_export": (_I, [_P, _P]),
+    "fino_peer_import": (_I, [_P, _P]),
+    "fino_peer_release": (_I, [_P]),
+    "fino_peer_barrier": (_I, [_P, _I, _I, c_uint32, _P]),
+    "fino_qkv_norm_rope_scatter": (_I, [_P, _L, _L, _P, _P, _I, _I, _F, _P, _P, _P, _I, _I, _L, _L, _P]),
+    "fino_attention_fwd_scatter": (_I, [_P, _P, _P, _P, _I, _L, _I, _I, _L, _L, _I, _L, _L, _L, _L, _L, _L, _L, _L, _F,
+                                        _P]),
 }
 
 

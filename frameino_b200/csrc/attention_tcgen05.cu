@@ -29,8 +29,13 @@ constexpr int ATT_BN = 128;        // keys per KV tile
 constexpr int ATT_THREADS = 384;
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;  // log2 units
 
+constexpr int ATT_MAX_OWNERS = 8;
+
 struct AttnParams {
-  __nv_bfloat16* o;
+  // Output rows [g*rows_per_owner, (g+1)*rows_per_owner) live in o[g] (local row = row % rows_per_owner). The plain
+  // call uses one owner holding every row; the Ulysses scatter variant passes the peer-mapped O buffers of all ranks.
+  __nv_bfloat16* o[ATT_MAX_OWNERS];
+  int64_t rows_per_owner;
   int64_t o_row_stride, o_batch_stride;  // elements
   int nq, nk;
   int heads;
@@ -53,7 +58,7 @@ struct AttnCfg {
 template <int HD, int EMU, bool SPLIT>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                const __grid_constant__ CUtensorMap tmap_v, const AttnParams p) {
+                const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ AttnParams p) {
   using Cfg = AttnCfg<HD>;
   constexpr int KST = Cfg::kKVStages;
   extern __shared__ uint8_t smem_raw[];
@@ -351,28 +356,51 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_arrive(p_full(wg));
     }
 
-    // ---------------- epilogue: O / l -> bf16 -> global ----------------
+    // ---------------- epilogue: O / l -> bf16 -> shared (swizzled) -> coalesced global rows ----------------
+    // Every S_i MMA has retired when o_done(i) fires, so the Q_i tile in shared memory is dead: each warp stages its
+    // 32 output rows there (16-byte chunks XOR-swizzled by row, conflict-free both ways) and then writes whole
+    // head_dim*2-byte row segments with consecutive lanes — 256-byte (d=128) contiguous stores instead of 32 scattered
+    // 16-byte ones, which matters doubly when the destination is a peer GPU's buffer behind NVLink.
     mbar_wait(o_done(wg), 0, 80 + wg);
     tc_fence_after();
     const float inv_l = 1.0f / l_sum;
-    const int qrow = q0 + wg * ATT_BM + row_in_tile;
-    __nv_bfloat16* orow =
-        p.o + (int64_t)batch * p.o_batch_stride + (int64_t)qrow * p.o_row_stride + (int64_t)head * HD;
+    constexpr int CH = HD / 8;            // 16-byte chunks per output row
+    constexpr int RPI = 32 / CH;          // rows per store instruction
+    const uint32_t stage = q_smem + wg * Cfg::kTileBytes + (uint32_t)(quad * 32) * (HD * 2);
+    const uint32_t my_row = stage + (uint32_t)lane * (HD * 2);
 #pragma unroll
     for (int c = 0; c < HD / 32; ++c) {
       uint32_t o[32];
       tmem_ld_32x32b_x32(t_o + c * 32, o);
       tmem_wait_ld();
-      if (qrow < p.nq) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(o[8 * e + 0]) * inv_l, __uint_as_float(o[8 * e + 1]) * inv_l);
-          w.y = pack_bf16x2(__uint_as_float(o[8 * e + 2]) * inv_l, __uint_as_float(o[8 * e + 3]) * inv_l);
-          w.z = pack_bf16x2(__uint_as_float(o[8 * e + 4]) * inv_l, __uint_as_float(o[8 * e + 5]) * inv_l);
-          w.w = pack_bf16x2(__uint_as_float(o[8 * e + 6]) * inv_l, __uint_as_float(o[8 * e + 7]) * inv_l);
-          reinterpret_cast<uint4*>(orow + c * 32)[e] = w;
-        }
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t w0 = pack_bf16x2(__uint_as_float(o[8 * e + 0]) * inv_l, __uint_as_float(o[8 * e + 1]) * inv_l);
+        const uint32_t w1 = pack_bf16x2(__uint_as_float(o[8 * e + 2]) * inv_l, __uint_as_float(o[8 * e + 3]) * inv_l);
+        const uint32_t w2 = pack_bf16x2(__uint_as_float(o[8 * e + 4]) * inv_l, __uint_as_float(o[8 * e + 5]) * inv_l);
+        const uint32_t w3 = pack_bf16x2(__uint_as_float(o[8 * e + 6]) * inv_l, __uint_as_float(o[8 * e + 7]) * inv_l);
+        const uint32_t chunk = (uint32_t)(c * 4 + e) ^ (uint32_t)(lane & (CH - 1) & 7);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + chunk * 16), "r"(w0), "r"(w1), "r"(w2),
+                     "r"(w3)
+                     : "memory");
+      }
+    }
+    __syncwarp();
+    const int sub = lane / CH;   // row inside the group of RPI rows written by one instruction
+    const int ch = lane % CH;    // 16-byte chunk inside the row
+#pragma unroll 4
+    for (int it = 0; it < 32 / RPI; ++it) {
+      const int r = it * RPI + sub;  // row inside this warp's 32
+      const int qrow = q0 + wg * ATT_BM + quad * 32 + r;
+      uint4 w;
+      const uint32_t src = stage + (uint32_t)r * (HD * 2) + (((uint32_t)ch ^ (uint32_t)(r & (CH - 1) & 7)) * 16);
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(src));
+      if (qrow < p.nq) {
+        const int64_t owner = (int64_t)qrow / p.rows_per_owner;
+        const int64_t lrow = (int64_t)qrow - owner * p.rows_per_owner;
+        __nv_bfloat16* dst =
+            p.o[owner] + (int64_t)batch * p.o_batch_stride + lrow * p.o_row_stride + (int64_t)head * HD + ch * 8;
+        *reinterpret_cast<uint4*>(dst) = w;
       }
     }
   }
@@ -419,11 +447,18 @@ static int dispatch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
   }
 }
 
-int attention_fwd(const void* q, const void* k, const void* v, void* o, int batch, int heads, int64_t nq, int64_t nk,
-                  int head_dim, int64_t q_row_stride, int64_t k_row_stride, int64_t v_row_stride, int64_t o_row_stride,
-                  int64_t q_batch_stride, int64_t k_batch_stride, int64_t v_batch_stride, int64_t o_batch_stride,
-                  float scale, cudaStream_t stream) {
-  FINO_CHECK_ARG(q && k && v && o, "attention: null pointer");
+// o_owners[num_owners]: output buffers; rows [g*rows_per_owner, (g+1)*rows_per_owner) go to owner g (see AttnParams).
+int attention_fwd_owners(const void* q, const void* k, const void* v, void* const* o_owners, int num_owners,
+                         int64_t rows_per_owner, int batch, int heads, int64_t nq, int64_t nk, int head_dim,
+                         int64_t q_row_stride, int64_t k_row_stride, int64_t v_row_stride, int64_t o_row_stride,
+                         int64_t q_batch_stride, int64_t k_batch_stride, int64_t v_batch_stride,
+                         int64_t o_batch_stride, float scale, cudaStream_t stream) {
+  FINO_CHECK_ARG(q && k && v && o_owners, "attention: null pointer");
+  FINO_CHECK_ARG(num_owners >= 1 && num_owners <= ATT_MAX_OWNERS, "attention: 1..%d output owners", ATT_MAX_OWNERS);
+  FINO_CHECK_ARG(rows_per_owner > 0 && rows_per_owner * num_owners >= nq, "attention: owners do not cover nq rows");
+  for (int g = 0; g < num_owners; ++g)
+    FINO_CHECK_ARG(o_owners[g] != nullptr && (reinterpret_cast<uintptr_t>(o_owners[g]) & 15) == 0,
+                   "attention: output pointer %d null or not 16-byte aligned", g);
   FINO_CHECK_ARG(head_dim == 128 || head_dim == 64, "attention: head_dim %d unsupported (64 or 128)", head_dim);
   FINO_CHECK_ARG(batch > 0 && heads > 0 && nq > 0 && nk > 0, "attention: non-positive shape");
   FINO_CHECK_ARG(batch <= 65535 && heads <= 65535, "attention: batch/heads exceed grid limits");
@@ -432,7 +467,6 @@ int attention_fwd(const void* q, const void* k, const void* v, void* o, int batc
   FINO_CHECK_ARG(q_batch_stride % 8 == 0 && k_batch_stride % 8 == 0 && v_batch_stride % 8 == 0 &&
                      o_batch_stride % 8 == 0,
                  "attention: batch strides must be multiples of 8 elements");
-  FINO_CHECK_ARG((reinterpret_cast<uintptr_t>(o) & 15) == 0, "attention: output pointer must be 16-byte aligned");
 
   CUtensorMap tq, tk, tv;
   const uint64_t inner = (uint64_t)heads * head_dim;
@@ -449,7 +483,9 @@ int attention_fwd(const void* q, const void* k, const void* v, void* o, int batc
   if ((r = enc(&tv, v, nk, v_row_stride, v_batch_stride))) return r;
 
   AttnParams p;
-  p.o = reinterpret_cast<__nv_bfloat16*>(o);
+  for (int g = 0; g < ATT_MAX_OWNERS; ++g)
+    p.o[g] = reinterpret_cast<__nv_bfloat16*>(o_owners[g < num_owners ? g : 0]);
+  p.rows_per_owner = rows_per_owner;
   p.o_row_stride = o_row_stride;
   p.o_batch_stride = o_batch_stride;
   p.nq = (int)nq;
@@ -459,6 +495,16 @@ int attention_fwd(const void* q, const void* k, const void* v, void* o, int batc
   p.num_kv_tiles = (int)((nk + ATT_BN - 1) / ATT_BN);
   if (head_dim == 128) return dispatch_attn<128>(tq, tk, tv, p, batch, stream);
   return dispatch_attn<64>(tq, tk, tv, p, batch, stream);
+}
+
+int attention_fwd(const void* q, const void* k, const void* v, void* o, int batch, int heads, int64_t nq, int64_t nk,
+                  int head_dim, int64_t q_row_stride, int64_t k_row_stride, int64_t v_row_stride, int64_t o_row_stride,
+                  int64_t q_batch_stride, int64_t k_batch_stride, int64_t v_batch_stride, int64_t o_batch_stride,
+                  float scale, cudaStream_t stream) {
+  void* owners[1] = {o};
+  return attention_fwd_owners(q, k, v, owners, 1, nq, batch, heads, nq, nk, head_dim, q_row_stride, k_row_stride,
+                              v_row_stride, o_row_stride, q_batch_stride, k_batch_stride, v_batch_stride,
+                              o_batch_stride, scale, stream);
 }
 
 }  // namespace fino

@@ -33,6 +33,21 @@ int linear_small_m(const float* x, const void* w, const void* b, float* y, int m
 int build_mod_table(const float* table, const float* proj, float* out, int layers, int r, int cols,
                     int64_t table_layer_stride, cudaStream_t stream);
 int swap01(const void* in, void* out, int64_t A, int64_t B, int64_t inner, cudaStream_t stream);
+int attention_fwd_owners(const void* q, const void* k, const void* v, void* const* o_owners, int num_owners,
+                         int64_t rows_per_owner, int batch, int heads, int64_t nq, int64_t nk, int head_dim,
+                         int64_t q_row_stride, int64_t k_row_stride, int64_t v_row_stride, int64_t o_row_stride,
+                         int64_t q_batch_stride, int64_t k_batch_stride, int64_t v_batch_stride,
+                         int64_t o_batch_stride, float scale, cudaStream_t stream);
+int peer_alloc(int64_t bytes, void** ptr);
+int peer_free(void* ptr);
+int peer_export(const void* ptr, void* handle64);
+int peer_import(const void* handle64, void** ptr);
+int peer_release(void* ptr);
+int peer_barrier(void* const* flag_ptrs, int rank, int world, uint32_t epoch, cudaStream_t stream);
+int qkv_norm_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride, const void* wq, const void* wk,
+                          int heads, int head_dim, float eps, const float* cos, const float* sin,
+                          void* const* dst_ptrs, int world, int rank, int64_t rows_per_rank, int64_t dst_row_stride,
+                          cudaStream_t stream);
 void gemm_set_mode(int mode);
 void attention_set_variant(int v);
 void rows_set_variant(int ln_block, int qk_block);
@@ -179,6 +194,50 @@ int fino_rows_set_variant(int ln_block, int qk_block) {
 
 int fino_swap01(const void* in, void* out, int64_t a, int64_t b, int64_t inner, void* stream) {
   FINO_ENTRY(fino::swap01(in, out, a, b, inner, (cudaStream_t)stream));
+}
+
+int fino_attention_fwd_scatter(const void* q, const void* k, const void* v, void* const* o_owners, int num_owners,
+                               int64_t rows_per_owner, int batch, int heads, int64_t nq, int64_t nk, int head_dim,
+                               int64_t q_row_stride, int64_t k_row_stride, int64_t v_row_stride, int64_t o_row_stride,
+                               int64_t q_batch_stride, int64_t k_batch_stride, int64_t v_batch_stride,
+                               int64_t o_batch_stride, float scale, void* stream) {
+  FINO_ENTRY(fino::attention_fwd_owners(q, k, v, o_owners, num_owners, rows_per_owner, batch, heads, nq, nk, head_dim,
+                                        q_row_stride, k_row_stride, v_row_stride, o_row_stride, q_batch_stride,
+                                        k_batch_stride, v_batch_stride, o_batch_stride, scale, (cudaStream_t)stream));
+}
+
+int fino_qkv_norm_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride, const void* wq, const void* wk,
+                               int heads, int head_dim, float eps, const float* cos, const float* sin,
+                               void* const* dst_ptrs, int world, int rank, int64_t rows_per_rank,
+                               int64_t dst_row_stride, void* stream) {
+  FINO_ENTRY(fino::qkv_norm_rope_scatter(qkv, rows, row_stride, wq, wk, heads, head_dim, eps, cos, sin, dst_ptrs, world,
+                                         rank, rows_per_rank, dst_row_stride, (cudaStream_t)stream));
+}
+
+int fino_peer_barrier(void* const* flag_ptrs, int rank, int world, uint32_t epoch, void* stream) {
+  FINO_ENTRY(fino::peer_barrier(flag_ptrs, rank, world, epoch, (cudaStream_t)stream));
+}
+
+// allocation / IPC: no kernel launch, not counted
+int fino_peer_alloc(int64_t bytes, void** ptr) {
+  int d = ensure_device();
+  return d ? d : fino::peer_alloc(bytes, ptr);
+}
+int fino_peer_free(void* ptr) {
+  int d = ensure_device();
+  return d ? d : fino::peer_free(ptr);
+}
+int fino_peer_export(const void* ptr, void* handle64) {
+  int d = ensure_device();
+  return d ? d : fino::peer_export(ptr, handle64);
+}
+int fino_peer_import(const void* handle64, void** ptr) {
+  int d = ensure_device();
+  return d ? d : fino::peer_import(handle64, ptr);
+}
+int fino_peer_release(void* ptr) {
+  int d = ensure_device();
+  return d ? d : fino::peer_release(ptr);
 }
 
 }  // extern "C"

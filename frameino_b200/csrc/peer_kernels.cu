@@ -1,0 +1,305 @@
+// Ulysses head<->sequence exchange over NVLink / NVSwitch PEER MEMORY, fused into the kernels on either side of it
+// (new capability — the reference is single-GPU). One process per GPU; every rank cudaMalloc's its
+// exchange buffers, exports them with CUDA IPC and maps the buffers of all peers, so a kernel can store straight into
+// another GPU's HBM:
+//
+//   qkv_norm_rope_scatter   RMSNorm-across-heads + 3-D RoPE of the local tokens' q/k (reference transformer_wan.py:64-90)
+//                           whose stores ARE the first all-to-all: head group g of every local token row is written
+//                           into rank g's [N, 3*inner] buffer at the token's global row (v rides along un-normalised).
+//   attention (scatter O)   attention_tcgen05.cu with one output "owner" per rank: the epilogue stores each query
+//                           row's heads into the owning rank's [n_loc, D] buffer — the second all-to-all.
+//   peer_barrier            flag exchange through peer memory between the two (all ranks' stores have landed).
+//
+// Nothing here calls NCCL; torch.distributed is only used once, on the host, to swap the 64-byte IPC handles.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace fino {
+
+constexpr int PEER_MAX_RANKS = 8;
+
+// ------------------------------------------------------------------------------------------------
+// allocation + CUDA IPC
+// ------------------------------------------------------------------------------------------------
+int peer_alloc(int64_t bytes, void** ptr) {
+  FINO_CHECK_ARG(bytes > 0 && ptr != nullptr, "peer_alloc: bad arguments");
+  void* p = nullptr;
+  FINO_CHECK_CUDA(cudaMalloc(&p, (size_t)bytes));
+  cudaError_t e = cudaMemset(p, 0, (size_t)bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    set_last_error("peer_alloc: cudaMemset failed: %s", cudaGetErrorString(e));
+    return FINO_ERR_CUDA;
+  }
+  *ptr = p;
+  return FINO_OK;
+}
+
+int peer_free(void* ptr) {
+  if (ptr != nullptr) FINO_CHECK_CUDA(cudaFree(ptr));
+  return FINO_OK;
+}
+
+int peer_export(const void* ptr, void* handle64) {
+  FINO_CHECK_ARG(ptr != nullptr && handle64 != nullptr, "peer_export: null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+  cudaIpcMemHandle_t h;
+  FINO_CHECK_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(ptr)));
+  memcpy(handle64, &h, 64);
+  return FINO_OK;
+}
+
+int peer_import(const void* handle64, void** ptr) {
+  FINO_CHECK_ARG(handle64 != nullptr && ptr != nullptr, "peer_import: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  FINO_CHECK_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *ptr = p;
+  return FINO_OK;
+}
+
+int peer_release(void* ptr) {
+  if (ptr != nullptr) FINO_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
+  return FINO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// barrier through peer memory
+// ------------------------------------------------------------------------------------------------
+struct BarrierParams {
+  uint32_t* flags[PEER_MAX_RANKS];  // flags[r] = rank r's flag array (PEER_MAX_RANKS words), peer-mapped
+  int rank, world;
+  uint32_t epoch;
+};
+
+// Thread t < world: tell rank t that `rank` reached `epoch`, then wait until rank t told us the same. The kernel is
+// stream-ordered after the producer kernel, whose (peer) stores are complete when it retires; the release/acquire
+// pair at system scope orders them against the consumer kernel that follows the barrier on every rank.
+__global__ void peer_barrier_kernel(const __grid_constant__ BarrierParams p) {
+  const int t = threadIdx.x;
+  if (t < p.world) {
+    __threadfence_system();
+    uint32_t* remote = p.flags[t] + p.rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(p.epoch) : "memory");
+    const uint32_t* mine = p.flags[p.rank] + t;
+    uint32_t v;
+    unsigned long long spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if ((int32_t)(v - p.epoch) >= 0) break;
+      __nanosleep(64);
+      if (++spins > (1ull << 28)) {  // ~20 s: a peer died; trap instead of hanging the GPU forever
+        printf("fino peer_barrier timeout: rank %d waiting for rank %d at epoch %u (saw %u)\n", p.rank, t, p.epoch, v);
+        __trap();
+      }
+    } while (true);
+    __threadfence_system();
+  }
+}
+
+int peer_barrier(void* const* flag_ptrs, int rank, int world, uint32_t epoch, cudaStream_t stream) {
+  FINO_CHECK_ARG(flag_ptrs != nullptr && world >= 1 && world <= PEER_MAX_RANKS && rank >= 0 && rank < world,
+                 "peer_barrier: bad rank/world (%d/%d)", rank, world);
+  BarrierParams p;
+  for (int r = 0; r < PEER_MAX_RANKS; ++r) p.flags[r] = reinterpret_cast<uint32_t*>(flag_ptrs[r < world ? r : 0]);
+  for (int r = 0; r < world; ++r) FINO_CHECK_ARG(flag_ptrs[r] != nullptr, "peer_barrier: null flag pointer %d", r);
+  p.rank = rank;
+  p.world = world;
+  p.epoch = epoch;
+  peer_barrier_kernel<<<1, 32, 0, stream>>>(p);
+  FINO_CHECK_CUDA(cudaGetLastError());
+  return FINO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// q/k RMSNorm-across-heads + RoPE, with the stores scattered to the ranks that own each head group
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float rbf_f(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ void unpack8_f(const uint4& u, float* f) {
+  f[0] = bf16_lo_to_f32(u.x);
+  f[1] = bf16_hi_to_f32(u.x);
+  f[2] = bf16_lo_to_f32(u.y);
+  f[3] = bf16_hi_to_f32(u.y);
+  f[4] = bf16_lo_to_f32(u.z);
+  f[5] = bf16_hi_to_f32(u.z);
+  f[6] = bf16_lo_to_f32(u.w);
+  f[7] = bf16_hi_to_f32(u.w);
+}
+__device__ __forceinline__ uint4 pack8_f(const float* f) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]);
+  u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]);
+  u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+
+struct ScatterParams {
+  const __nv_bfloat16* qkv;  // local [rows, row_stride]: q at column 0, k at dim, v at 2*dim
+  int64_t rows, row_stride;
+  const __nv_bfloat16* wq;
+  const __nv_bfloat16* wk;
+  int heads, head_dim;
+  float eps;
+  const float* cos;  // [rows, head_dim] fp32 rows of the LOCAL tokens (null: no RoPE)
+  const float* sin;
+  __nv_bfloat16* dst[PEER_MAX_RANKS];  // rank g's [world*rows_per_rank, dst_row_stride] buffer (q | k | v, inner each)
+  int world, rank;
+  int64_t rows_per_rank;   // row of local token t in every destination: rank*rows_per_rank + t
+  int64_t dst_row_stride;  // elements (>= 3*inner)
+  int inner;               // dim / world
+};
+
+constexpr int SCATTER_TOKENS_PER_BLOCK = 8;
+
+// Thread c owns 16-byte chunk c (8 columns) of the q, k and v rows of each token the CTA walks over: the RMSNorm
+// weights of its columns stay in registers, cos/sin are fetched once per token and used for q and k, and the two
+// sum-of-squares reductions share one __syncthreads. All 8 columns of a chunk belong to one head, hence one rank.
+__global__ void __launch_bounds__(512) qkv_norm_rope_scatter_kernel(const __grid_constant__ ScatterParams p) {
+  __shared__ float red[2][2][16];
+  const int c = threadIdx.x;
+  const int lane = c & 31, warp = c >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int dim = p.heads * p.head_dim;
+  const bool active = c < (dim >> 3);
+  const float inv_dim = 1.0f / (float)dim;
+  float wq[8], wk[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) wq[e] = wk[e] = 1.f;
+  if (active && p.wq != nullptr) unpack8_f(__ldg(reinterpret_cast<const uint4*>(p.wq) + c), wq);
+  if (active && p.wk != nullptr) unpack8_f(__ldg(reinterpret_cast<const uint4*>(p.wk) + c), wk);
+  const int col = c * 8;
+  const int off = col % p.head_dim;
+  const int g = active ? col / p.inner : 0;  // destination rank of this chunk
+  __nv_bfloat16* dst_base = p.dst[g] + (int64_t)p.rank * p.rows_per_rank * p.dst_row_stride + (col - g * p.inner);
+  const int64_t t0 = (int64_t)blockIdx.x * SCATTER_TOKENS_PER_BLOCK;
+  const int64_t t1 = min(p.rows, t0 + (int64_t)SCATTER_TOKENS_PER_BLOCK);
+  uint4 uq = make_uint4(0, 0, 0, 0), uk = uq, uv = uq;
+  if (active && t0 < t1) {
+    const uint4* src = reinterpret_cast<const uint4*>(p.qkv + t0 * p.row_stride);
+    uq = src[c];
+    uk = src[c + (dim >> 3)];
+    uv = src[c + 2 * (dim >> 3)];
+  }
+  int it = 0;
+  for (int64_t tok = t0; tok < t1; ++tok, ++it) {
+    float q[8], k[8];
+    unpack8_f(uq, q);
+    unpack8_f(uk, k);
+    const uint4 v_now = uv;
+    if (active && tok + 1 < t1) {  // prefetch the next token's rows
+      const uint4* src = reinterpret_cast<const uint4*>(p.qkv + (tok + 1) * p.row_stride);
+      uq = src[c];
+      uk = src[c + (dim >> 3)];
+      uv = src[c + 2 * (dim >> 3)];
+    }
+    float cs[8], sn[8];
+    if (p.cos != nullptr && active) {
+      const float4* cp = reinterpret_cast<const float4*>(p.cos + tok * p.head_dim + off);
+      const float4* sp = reinterpret_cast<const float4*>(p.sin + tok * p.head_dim + off);
+      const float4 a = __ldg(cp), b = __ldg(cp + 1), s0 = __ldg(sp), s1 = __ldg(sp + 1);
+      cs[0] = a.x, cs[1] = a.y, cs[2] = a.z, cs[3] = a.w, cs[4] = b.x, cs[5] = b.y, cs[6] = b.z, cs[7] = b.w;
+      sn[0] = s0.x, sn[1] = s0.y, sn[2] = s0.z, sn[3] = s0.w, sn[4] = s1.x, sn[5] = s1.y, sn[6] = s1.z, sn[7] = s1.w;
+    }
+    float sq = 0.f, sk = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      sq += q[e] * q[e];
+      sk += k[e] * k[e];
+    }
+    sq = warp_sum_f(sq);
+    sk = warp_sum_f(sk);
+    if (lane == 0) {
+      red[it & 1][0][warp] = sq;
+      red[it & 1][1][warp] = sk;
+    }
+    __syncthreads();
+    float tq2 = 0.f, tk2 = 0.f;
+    for (int w = 0; w < nwarps; ++w) {
+      tq2 += red[it & 1][0][w];
+      tk2 += red[it & 1][1][w];
+    }
+    const float rq = rsqrtf(tq2 * inv_dim + p.eps);
+    const float rk = rsqrtf(tk2 * inv_dim + p.eps);
+    if (active) {
+      // RMSNorm (upstream diffusers): fp32 x*rsqrt -> bf16 -> * weight in bf16
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        q[e] = p.wq ? rbf_f(rbf_f(q[e] * rq) * wq[e]) : rbf_f(q[e] * rq);
+        k[e] = p.wk ? rbf_f(rbf_f(k[e] * rk) * wk[e]) : rbf_f(k[e] * rk);
+      }
+      uint4* drow = reinterpret_cast<uint4*>(dst_base + tok * p.dst_row_stride);
+      const int ichunks = p.inner >> 3;
+      if (p.cos != nullptr) {
+        // cos = freqs_cos[..., 0::2], sin = freqs_sin[..., 1::2]   (transformer_wan.py:83-87)
+        float oq[8], ok[8];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          oq[e] = __fsub_rn(__fmul_rn(q[e], cs[e]), __fmul_rn(q[e + 1], sn[e + 1]));
+          oq[e + 1] = __fadd_rn(__fmul_rn(q[e], sn[e + 1]), __fmul_rn(q[e + 1], cs[e]));
+          ok[e] = __fsub_rn(__fmul_rn(k[e], cs[e]), __fmul_rn(k[e + 1], sn[e + 1]));
+          ok[e + 1] = __fadd_rn(__fmul_rn(k[e], sn[e + 1]), __fmul_rn(k[e + 1], cs[e]));
+        }
+        drow[0] = pack8_f(oq);
+        drow[ichunks] = pack8_f(ok);
+      } else {
+        drow[0] = pack8_f(q);
+        drow[ichunks] = pack8_f(k);
+      }
+      drow[2 * ichunks] = v_now;
+    }
+  }
+}
+
+int qkv_norm_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride, const void* wq, const void* wk,
+                          int heads, int head_dim, float eps, const float* cos, const float* sin,
+                          void* const* dst_ptrs, int world, int rank, int64_t rows_per_rank, int64_t dst_row_stride,
+                          cudaStream_t stream) {
+  FINO_CHECK_ARG(qkv != nullptr && rows > 0 && dst_ptrs != nullptr, "qkv_norm_rope_scatter: null / empty input");
+  FINO_CHECK_ARG(world >= 1 && world <= PEER_MAX_RANKS && rank >= 0 && rank < world,
+                 "qkv_norm_rope_scatter: bad rank/world (%d/%d)", rank, world);
+  FINO_CHECK_ARG(heads > 0 && head_dim >= 8 && head_dim % 8 == 0 && heads % world == 0,
+                 "qkv_norm_rope_scatter: heads %d x head_dim %d not divisible over %d ranks", heads, head_dim, world);
+  const int dim = heads * head_dim;
+  FINO_CHECK_ARG(dim / 8 <= 512, "qkv_norm_rope_scatter: heads*head_dim <= 4096");
+  FINO_CHECK_ARG(row_stride % 8 == 0 && row_stride >= 3 * dim, "qkv_norm_rope_scatter: row stride");
+  const int inner = dim / world;
+  FINO_CHECK_ARG(dst_row_stride % 8 == 0 && dst_row_stride >= 3 * inner, "qkv_norm_rope_scatter: dst row stride");
+  FINO_CHECK_ARG(rows <= rows_per_rank, "qkv_norm_rope_scatter: more local rows than rows_per_rank");
+  FINO_CHECK_ARG((cos == nullptr) == (sin == nullptr), "qkv_norm_rope_scatter: cos and sin go together");
+  ScatterParams p;
+  p.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  p.rows = rows;
+  p.row_stride = row_stride;
+  p.wq = reinterpret_cast<const __nv_bfloat16*>(wq);
+  p.wk = reinterpret_cast<const __nv_bfloat16*>(wk);
+  p.heads = heads;
+  p.head_dim = head_dim;
+  p.eps = eps;
+  p.cos = cos;
+  p.sin = sin;
+  for (int r = 0; r < PEER_MAX_RANKS; ++r) {
+    void* d = dst_ptrs[r < world ? r : 0];
+    FINO_CHECK_ARG(d != nullptr && (reinterpret_cast<uintptr_t>(d) & 15) == 0, "qkv_norm_rope_scatter: dst %d", r);
+    p.dst[r] = reinterpret_cast<__nv_bfloat16*>(d);
+  }
+  p.world = world;
+  p.rank = rank;
+  p.rows_per_rank = rows_per_rank;
+  p.dst_row_stride = dst_row_stride;
+  p.inner = inner;
+  const int threads = ((dim / 8 + 31) / 32) * 32;
+  dim3 grid((unsigned)((rows + SCATTER_TOKENS_PER_BLOCK - 1) / SCATTER_TOKENS_PER_BLOCK));
+  qkv_norm_rope_scatter_kernel<<<grid, threads, 0, stream>>>(p);
+  FINO_CHECK_CUDA(cudaGetLastError());
+  return FINO_OK;
+}
+
+}  // namespace fino

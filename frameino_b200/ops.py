@@ -345,3 +345,131 @@ def rows_set_variant(ln_block: bool, qk_block: bool) -> None:
 
 def launch_count() -> int:
     return int(_lib.load().fino_launch_count())
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# peer memory (Ulysses exchange over NVLink / NVSwitch, include/frameino_b200.h "peer" section)
+# ---------------------------------------------------------------------------------------------------------------
+PEER_MAX_RANKS = 8
+
+
+def _bind_current_device():
+    global _bound_device
+    lib = _lib.load()
+    idx = torch.cuda.current_device()
+    if _bound_device != idx:
+        _lib.check(lib.fino_set_device(idx), "fino_set_device")
+        _bound_device = idx
+    return lib
+
+
+def peer_alloc(nbytes: int) -> int:
+    """cudaMalloc'd, zero-filled, IPC-exportable buffer on the current device; returns the device pointer."""
+    import ctypes
+
+    lib = _bind_current_device()
+    p = ctypes.c_void_p()
+    _lib.check(lib.fino_peer_alloc(int(nbytes), ctypes.byref(p)), "fino_peer_alloc")
+    return int(p.value)
+
+
+def peer_free(ptr: int) -> None:
+    _lib.check(_bind_current_device().fino_peer_free(ptr), "fino_peer_free")
+
+
+def peer_export(ptr: int) -> bytes:
+    import ctypes
+
+    buf = ctypes.create_string_buffer(64)
+    _lib.check(_bind_current_device().fino_peer_export(ptr, buf), "fino_peer_export")
+    return bytes(buf.raw)
+
+
+def peer_import(handle: bytes) -> int:
+    import ctypes
+
+    assert len(handle) == 64
+    p = ctypes.c_void_p()
+    _lib.check(_bind_current_device().fino_peer_import(handle, ctypes.byref(p)), "fino_peer_import")
+    return int(p.value)
+
+
+def peer_release(ptr: int) -> None:
+    _lib.check(_bind_current_device().fino_peer_release(ptr), "fino_peer_release")
+
+
+def pointer_table(ptrs) -> "ctypes.Array":
+    """HOST array of up to 8 device pointers, the form every ``*_ptrs`` argument of the peer entry points takes."""
+    import ctypes
+
+    assert 1 <= len(ptrs) <= PEER_MAX_RANKS
+    return (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+
+class _RawCudaBytes:
+    """__cuda_array_interface__ shim: lets torch view memory this library allocated (no copy, no ownership)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+def tensor_from_ptr(ptr: int, shape, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """Tensor view (current device) of raw device memory, e.g. a slice of a ``peer_alloc`` buffer."""
+    numel = 1
+    for s in shape:
+        numel *= int(s)
+    nbytes = numel * torch.empty(0, dtype=dtype).element_size()
+    raw = torch.as_tensor(_RawCudaBytes(ptr, nbytes), device=torch.device("cuda", torch.cuda.current_device()))
+    return raw.view(dtype).view(*shape)
+
+
+def peer_barrier(flag_ptrs, rank: int, world: int, epoch: int) -> None:
+    """Stream-ordered barrier between the ranks through their peer-mapped flag arrays (``pointer_table``)."""
+    lib = _bind_current_device()
+    stream = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.fino_peer_barrier(flag_ptrs, rank, world, epoch & 0xFFFFFFFF, stream), "fino_peer_barrier")
+
+
+def qkv_norm_rope_scatter(qkv: torch.Tensor, wq: Optional[torch.Tensor], wk: Optional[torch.Tensor], heads: int,
+                          eps: float, cos: Optional[torch.Tensor], sin: Optional[torch.Tensor], dst_ptrs, world: int,
+                          rank: int, rows_per_rank: int, dst_row_stride: int) -> None:
+    """RMSNorm-across-heads (+ Wan RoPE) of the local [rows, 3*D] projections, stored into every rank's exchange buffer
+    (``fino_qkv_norm_rope_scatter``). cos/sin: fp32 [rows, head_dim] rows of the local tokens."""
+    assert qkv.dtype == torch.bfloat16
+    lib, stream = _prep(qkv, wq, wk, cos, sin)
+    rows, cols, stride = _rows2d(qkv)
+    dim = cols // 3
+    assert dim * 3 == cols and dim % heads == 0
+    head_dim = dim // heads
+    for t in (wq, wk):
+        if t is not None:
+            assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.numel() == dim
+    if cos is not None:
+        assert cos.dtype == sin.dtype == torch.float32 and cos.is_contiguous() and sin.is_contiguous()
+        assert cos.shape == (rows, head_dim) and sin.shape == (rows, head_dim)
+    status = lib.fino_qkv_norm_rope_scatter(qkv.data_ptr(), rows, stride, _ptr(wq), _ptr(wk), heads, head_dim,
+                                            float(eps), _ptr(cos), _ptr(sin), dst_ptrs, world, rank, rows_per_rank,
+                                            dst_row_stride, stream)
+    _lib.check(status, "fino_qkv_norm_rope_scatter")
+
+
+def attention_scatter(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, o_ptrs, num_owners: int,
+                      rows_per_owner: int, o_row_stride: int, scale: Optional[float] = None) -> None:
+    """``attention`` whose output rows are stored into their owners' buffers (``fino_attention_fwd_scatter``):
+    row g -> o_ptrs[g // rows_per_owner] + (g % rows_per_owner) * o_row_stride. Batch 1."""
+    assert q.dtype == k.dtype == v.dtype == torch.bfloat16
+    lib, stream = _prep(q, k, v)
+    b, nq, inner = q.shape
+    nk = k.shape[1]
+    d = inner // heads
+    assert b == 1 and d in (64, 128), "scatter attention: batch 1, head_dim 64 or 128"
+    for t in (q, k, v):
+        assert t.stride(2) == 1
+    if scale is None:
+        scale = d ** -0.5
+    status = lib.fino_attention_fwd_scatter(
+        q.data_ptr(), k.data_ptr(), v.data_ptr(), o_ptrs, num_owners, rows_per_owner, b, heads, nq, nk, d,
+        q.stride(1), k.stride(1), v.stride(1), o_row_stride, q.stride(0), k.stride(0), v.stride(0), 0, float(scale),
+        stream)
+    _lib.check(status, "fino_attention_fwd_scatter")

@@ -86,6 +86,17 @@ class FinoWanAttnProcessor:
             d_model = w.shape[0] // 2
             k, v = kv[..., :d_model], kv[..., d_model:]
         head_dim = d_model // heads
+        scale = getattr(attn, "scale", head_dim ** -0.5)
+        sp = attn.__dict__.get("_fino_sp") if encoder_hidden_states is None else None
+        if sp is not None and sp.mode == "peer" and b == 1 and norm_q is not None and head_dim in (64, 128):
+            # Ulysses over peer memory: norm + RoPE + 1st exchange in one kernel, attention + 2nd exchange in another
+            cos = sin = None
+            if rotary_emb is not None:
+                cos, sin = _rope_table(rotary_emb[0], head_dim), _rope_table(rotary_emb[1], head_dim)
+                if cos.shape[0] != n:
+                    raise ValueError(f"rotary table has {cos.shape[0]} rows for {n} tokens")
+            o = sp.fused_attention(qkv, norm_q.weight, norm_k.weight, heads, eps, cos, sin, scale)
+            return self._out_proj(attn, o, fino_residual)
         if norm_q is not None or rotary_emb is not None:
             if norm_q is None:
                 raise NotImplementedError("RoPE without qk-norm is not used by the reference Wan path")
@@ -98,12 +109,14 @@ class FinoWanAttnProcessor:
                 mode = ops.ROPE_WAN
             ops.qk_norm_rope(q, norm_q.weight, k, norm_k.weight, heads, norm_mode=ops.QK_RMS_ACROSS_HEADS, eps=eps,
                              rope_mode=mode, cos=cos, sin=sin, seq_len=n)
-        scale = getattr(attn, "scale", head_dim ** -0.5)
-        sp = attn.__dict__.get("_fino_sp")
-        if sp is not None and encoder_hidden_states is None:
-            o = sp.attention(qkv, heads, scale)  # Ulysses all-to-all around the full-sequence attention
+        if sp is not None:
+            o = sp.attention(qkv, heads, scale)  # Ulysses all-to-all (NCCL) around the full-sequence attention
         else:
             o = ops.attention(q, k, v, heads, scale=scale)
+        return self._out_proj(attn, o, fino_residual)
+
+    @staticmethod
+    def _out_proj(attn, o: torch.Tensor, fino_residual):
         wo, bo = attn.to_out[0].weight, attn.to_out[0].bias
         if fino_residual is not None:
             x, gate, row_index, rows_per_group = fino_residual

@@ -8,7 +8,15 @@ sequence. Around self-attention two all-to-alls swap the sharded axis:
 
 RMSNorm-across-heads and RoPE run before the first exchange (they need all heads / are per token). Pad rows (when
 N % P != 0) sit at the END of the global sequence, so the attention kernel's ``nk`` bound masks them as keys.
-The (de)interleave around ``all_to_all_single`` is the ``fino_swap01`` kernel.
+
+Two transports, same partitioning:
+  * ``mode="peer"`` (default on GPUs): both exchanges are FUSED into the neighbouring kernels over NVLink / NVSwitch
+    peer memory (``frameino_b200/csrc/peer_kernels.cu``): the q/k norm+RoPE kernel stores every head group directly
+    into the owning rank's ``[N, 3*D/P]`` buffer, the attention kernel's epilogue stores every query row directly into
+    the owning rank's ``[n_loc, D]`` buffer, and a flag barrier through peer memory separates producer and consumer.
+    No NCCL call, no pack/unpack pass, no staging copy.
+  * ``mode="nccl"``: ``all_to_all_single`` with the ``fino_swap01`` (de)interleave kernel around it — the baseline the
+    fused path is measured against, and the layout the world-size-2 gloo tests exercise on CPU.
 """
 from __future__ import annotations
 
@@ -20,13 +28,88 @@ import torch.distributed as dist
 from . import ops
 
 
+def exchange_layout(world: int, rank: int, n_loc: int, d_model: int, elem_bytes: int = 2) -> dict:
+    """Byte layout of one rank's peer buffer and the offsets the fused kernels are given (pure arithmetic; unit-tested
+    on CPU). Buffer = [flags 256 B | qkv [world*n_loc, 3*inner] | o [n_loc, d_model]], each part 256-byte aligned.
+    ``o_col_offset`` is where THIS rank's heads start inside every owner's O row."""
+    assert d_model % world == 0
+    inner = d_model // world
+
+    def up(x):
+        return (x + 255) // 256 * 256
+
+    qkv_off = 256
+    qkv_bytes = world * n_loc * 3 * inner * elem_bytes
+    o_off = up(qkv_off + qkv_bytes)
+    o_bytes = n_loc * d_model * elem_bytes
+    return {"inner": inner, "n_pad": world * n_loc, "flags_off": 0, "qkv_off": qkv_off, "qkv_row_stride": 3 * inner,
+            "o_off": o_off, "o_row_stride": d_model, "o_col_offset": rank * inner * elem_bytes,
+            "total_bytes": up(o_off + o_bytes)}
+
+
+class PeerExchange:
+    """The peer-mapped exchange buffers of one (n_loc, d_model) problem: own allocation + the mapped buffers of every
+    other rank (CUDA IPC handles swapped once over ``torch.distributed``)."""
+
+    def __init__(self, group, world: int, rank: int, n_loc: int, d_model: int, prims=ops):
+        # `prims`: the device primitives (peer_alloc/export/import/release/free, pointer_table, tensor_from_ptr,
+        # peer_barrier); the world-size-2 gloo test on CPU passes shared-memory stand-ins to exercise this host logic
+        self.group, self.world, self.rank, self.n_loc, self.d_model = group, world, rank, n_loc, d_model
+        self.prims = ops = prims
+        self.layout = lay = exchange_layout(world, rank, n_loc, d_model)
+        self.base = ops.peer_alloc(lay["total_bytes"])
+        handles = [None] * world
+        dist.all_gather_object(handles, ops.peer_export(self.base), group=group)
+        self.imported = {}
+        bases = []
+        for r in range(world):
+            if r == rank:
+                bases.append(self.base)
+            else:
+                self.imported[r] = ops.peer_import(handles[r])
+                bases.append(self.imported[r])
+        self.flag_ptrs = ops.pointer_table([b + lay["flags_off"] for b in bases])
+        self.qkv_ptrs = ops.pointer_table([b + lay["qkv_off"] for b in bases])
+        self.o_ptrs = ops.pointer_table([b + lay["o_off"] + lay["o_col_offset"] for b in bases])
+        self.qkv_local = ops.tensor_from_ptr(self.base + lay["qkv_off"], (1, lay["n_pad"], 3 * lay["inner"]))
+        self.o_local = ops.tensor_from_ptr(self.base + lay["o_off"], (1, n_loc, d_model))
+        self.epoch = 0
+        dist.barrier(group=group)  # every rank has mapped every buffer before anyone stores into one
+
+    def barrier(self) -> None:
+        self.epoch += 1
+        self.prims.peer_barrier(self.flag_ptrs, self.rank, self.world, self.epoch)
+
+    def close(self) -> None:
+        if self.base is None:
+            return
+        ops = self.prims
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        dist.barrier(group=self.group)  # nobody is still storing into a buffer that is about to go away
+        self.qkv_local = self.o_local = None
+        for p in self.imported.values():
+            ops.peer_release(p)
+        self.imported = {}
+        dist.barrier(group=self.group)
+        ops.peer_free(self.base)
+        self.base = None
+
+
 class SequenceParallel:
-    def __init__(self, group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, group: Optional[dist.ProcessGroup] = None, mode: str = "peer"):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised before enabling sequence parallelism")
+        if mode not in ("peer", "nccl"):
+            raise ValueError(f"mode {mode!r}: 'peer' (fused NVLink peer-memory exchange) or 'nccl'")
         self.group = group
+        self.mode = mode
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self._exchanges = {}
+        self._prims = ops
+        self._qkv_scatter = ops.qkv_norm_rope_scatter
+        self._attention_scatter = ops.attention_scatter
         self.n_total = 0
         self.n_pad = 0
         self.n_loc = 0
@@ -93,6 +176,46 @@ class SequenceParallel:
         out = self._swap01(back.view(-1), p, n_loc, inner)  # -> [n_loc, P, inner] == [n_loc, D]
         return out.view(1, n_loc, d_model)
 
+    # ---- the same exchange fused into the neighbouring kernels over peer memory -------------------------------
+    def exchange(self, n_loc: int, d_model: int) -> PeerExchange:
+        key = (n_loc, d_model)
+        ex = self._exchanges.get(key)
+        if ex is None:
+            for old in self._exchanges.values():  # one live problem shape at a time (the sampler's canvas is fixed)
+                old.close()
+            self._exchanges = {}
+            ex = self._exchanges[key] = PeerExchange(self.group, self.world, self.rank, n_loc, d_model, self._prims)
+        return ex
+
+    def fused_attention(self, qkv: torch.Tensor, norm_q_weight, norm_k_weight, heads: int, eps: float, cos, sin,
+                        scale: float) -> torch.Tensor:
+        """qkv: local RAW fused projections [1, n_loc, 3*D] (before q/k norm). Returns the local attention output
+        [1, n_loc, D], a view of this rank's peer buffer (valid until the next call)."""
+        assert qkv.dim() == 3 and qkv.shape[0] == 1, "sequence parallel path handles batch 1 (the Wan sampler's case)"
+        p = self.world
+        n_loc = qkv.shape[1]
+        d_model = qkv.shape[2] // 3
+        assert heads % p == 0, f"{heads} heads cannot be split over {p} ranks"
+        assert n_loc == self.n_loc, "plan() must run before the forward"
+        ex = self.exchange(n_loc, d_model)
+        lay = ex.layout
+        inner = lay["inner"]
+        # 1st all-to-all == the stores of the norm+RoPE kernel
+        self._qkv_scatter(qkv, norm_q_weight, norm_k_weight, heads, eps, cos, sin, ex.qkv_ptrs, p, self.rank, n_loc,
+                          lay["qkv_row_stride"])
+        ex.barrier()
+        full = ex.qkv_local[:, : self.n_total]
+        # 2nd all-to-all == the stores of the attention epilogue
+        self._attention_scatter(full[..., :inner], full[..., inner:2 * inner], full[..., 2 * inner:], heads // p,
+                                ex.o_ptrs, p, n_loc, lay["o_row_stride"], scale)
+        ex.barrier()
+        return ex.o_local
+
+    def close(self) -> None:
+        for ex in self._exchanges.values():
+            ex.close()
+        self._exchanges = {}
+
     def gather_rows(self, y: torch.Tensor) -> torch.Tensor:
         """[1, n_loc, C] local rows -> [1, N, C] on every rank."""
         parts = torch.empty(self.world, y.shape[1], y.shape[2], dtype=y.dtype, device=y.device)
@@ -100,9 +223,9 @@ class SequenceParallel:
         return parts.view(1, self.world * y.shape[1], y.shape[2])[:, : self.n_total]
 
 
-def enable_sequence_parallel(model, group: Optional[dist.ProcessGroup] = None) -> SequenceParallel:
+def enable_sequence_parallel(model, group: Optional[dist.ProcessGroup] = None, mode: str = "peer") -> SequenceParallel:
     """Switches a ``frameino_b200.WanTransformer3DModel`` to Ulysses sequence parallelism over ``group``."""
-    sp = SequenceParallel(group)
+    sp = SequenceParallel(group, mode)
     model.sequence_parallel = sp
     for blk in model.blocks:
         blk.attn1.__dict__["_fino_sp"] = sp
@@ -110,6 +233,8 @@ def enable_sequence_parallel(model, group: Optional[dist.ProcessGroup] = None) -
 
 
 def disable_sequence_parallel(model) -> None:
+    if model.sequence_parallel is not None:
+        model.sequence_parallel.close()
     model.sequence_parallel = None
     for blk in model.blocks:
         blk.attn1.__dict__.pop("_fino_sp", None)

@@ -123,6 +123,40 @@ int fino_build_mod_table(const float* table, const float* proj, float* out, int 
  * around the Ulysses head<->sequence all-to-all (new capability, no reference counterpart: SURVEY.md 8e). */
 int fino_swap01(const void* in, void* out, int64_t a, int64_t b, int64_t inner, void* stream);
 
+/* ---- Ulysses exchange over NVLink/NVSwitch peer memory (new capability, no reference counterpart: SURVEY.md 8e) ----
+ * One process per GPU. Each rank allocates its exchange buffers with fino_peer_alloc, exports a 64-byte CUDA IPC
+ * handle per buffer, swaps the handles with its peers on the host (any transport) and maps theirs with
+ * fino_peer_import. `*_ptrs` arguments below are HOST arrays of `world` device pointers, indexed by rank (the entry
+ * for the calling rank is its own local pointer). world <= 8. */
+int fino_peer_alloc(int64_t bytes, void** ptr);         /* cudaMalloc + zero fill                                  */
+int fino_peer_free(void* ptr);
+int fino_peer_export(const void* ptr, void* handle64);  /* handle64: 64-byte host buffer                           */
+int fino_peer_import(const void* handle64, void** ptr); /* maps a peer's buffer (enables peer access lazily)       */
+int fino_peer_release(void* ptr);                       /* unmaps an imported buffer                               */
+
+/* Barrier between the ranks' streams through peer memory: flag_ptrs[r] = rank r's flag array (>= 8 uint32, zeroed).
+ * `epoch` must increase by one per call (same sequence on every rank). Stream-ordered; no host synchronisation. */
+int fino_peer_barrier(void* const* flag_ptrs, int rank, int world, uint32_t epoch, void* stream);
+
+/* First all-to-all fused into the q/k prologue: RMSNorm across heads (+ Wan RoPE when cos/sin != NULL; transformer_wan.py
+ * :64-90) of the local fused projection rows qkv[rows, row_stride] (q | k | v, heads*head_dim columns each), stored
+ * straight into the owning ranks' buffers: head group g = columns [g*inner, (g+1)*inner), inner = heads*head_dim/world,
+ * of local token t lands in dst_ptrs[g] row rank*rows_per_rank + t as (q | k | v), inner columns each. cos/sin are the
+ * float [rows, head_dim] table rows of the LOCAL tokens. */
+int fino_qkv_norm_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride, const void* wq, const void* wk,
+                               int heads, int head_dim, float eps, const float* cos, const float* sin,
+                               void* const* dst_ptrs, int world, int rank, int64_t rows_per_rank,
+                               int64_t dst_row_stride, void* stream);
+
+/* fino_attention_fwd whose epilogue is the second all-to-all: query row g is stored into
+ * o_owners[g / rows_per_owner] at local row g % rows_per_owner (row stride o_row_stride; pass the column offset of
+ * this rank's heads in each pointer). o_owners: HOST array of num_owners (<= 8) device pointers. */
+int fino_attention_fwd_scatter(const void* q, const void* k, const void* v, void* const* o_owners, int num_owners,
+                               int64_t rows_per_owner, int batch, int heads, int64_t nq, int64_t nk, int head_dim,
+                               int64_t q_row_stride, int64_t k_row_stride, int64_t v_row_stride, int64_t o_row_stride,
+                               int64_t q_batch_stride, int64_t k_batch_stride, int64_t v_batch_stride,
+                               int64_t o_batch_stride, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,7 +25,9 @@ def main():
     cfg = dict(synth.WAN_SMALL)
     if world == 8:
         cfg["num_attention_heads"] = 8
-    for name, shape, per_token in [("even", (3, 32, 32), True), ("ragged", (2, 18, 22), True), ("scalar_t", (3, 16, 16), False)]:
+    cases = [(m, n, sh, pt) for m in ("peer", "nccl")
+             for n, sh, pt in [("even", (3, 32, 32), True), ("ragged", (2, 18, 22), True), ("scalar_t", (3, 16, 16), False)]]
+    for mode, name, shape, per_token in cases:
         sd = synth.make_wan_state_dict(cfg, seed=0, dtype=torch.bfloat16)
         hidden, ts, text = synth.make_wan_inputs(cfg, *shape, n_id=1, text_len=16, text_true_len=11,
                                                  per_token_timestep=per_token, dtype=torch.bfloat16)
@@ -34,14 +36,16 @@ def main():
         model = model.to_inference_dtype(torch.bfloat16).cuda().eval()
         args = dict(hidden_states=hidden.cuda(), timestep=ts.cuda(), encoder_hidden_states=text.cuda(), return_dict=False)
         ref = model(**args)[0]
-        enable_sequence_parallel(model)
+        enable_sequence_parallel(model, mode=mode)
         out = model(**args)[0]
+        out2 = model(**args)[0]  # second forward reuses the exchange buffers
+        assert torch.equal(out, out2), "sequence-parallel forward is not repeatable"
         disable_sequence_parallel(model)
         torch.cuda.synchronize()
         err = float((out.float() - ref.float()).abs().max() / ref.float().abs().max())
         errs = [None] * world
         dist.all_gather_object(errs, err)
-        results[name] = {"tokens": (shape[0] + 1) * (shape[1] // 2) * (shape[2] // 2), "rel_err_per_rank": errs}
+        results[f"{mode}/{name}"] = {"tokens": (shape[0] + 1) * (shape[1] // 2) * (shape[2] // 2), "rel_err_per_rank": errs}
     if rank == 0:
         print("SP_CHECK " + json.dumps(results))
         ok = all(e <= 2e-2 for r in results.values() for e in r["rel_err_per_rank"])
