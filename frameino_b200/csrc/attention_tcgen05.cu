@@ -153,7 +153,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     } else if (warp == 9) {
       // ============================ MMA issuer ============================
-      if (lane == 0) {
+      // The whole warp walks the loop (convergent control flow: descriptors stay in uniform registers); one elected
+      // lane issues each tcgen05.mma / commit inside the *_w wrappers.
+      {
         constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, ATT_BN, 0);  // Q K^T : both K-major
         constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BM, HD, 1);      // P V   : V is MN-major (d contiguous)
         const uint32_t tmem_s[2] = {tmem_base + 0u, tmem_base + 128u};
@@ -165,7 +167,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
           for (int ks = 0; ks < HD / 16; ++ks) {
             const uint32_t off = (ks >> 2) * Cfg::kPanelBytes + (ks & 3) * 32;
-            umma_ss(tmem_s[i], make_sdesc_sw128(qa + off, 16, 1024), make_sdesc_sw128(ka + off, 16, 1024), idesc_s,
+            umma_ss_w(tmem_s[i], make_sdesc_sw128(qa + off, 16, 1024), make_sdesc_sw128(ka + off, 16, 1024), idesc_s,
                     ks != 0 ? 1u : 0u);
           }
         };
@@ -174,7 +176,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
           for (int ks = ks0; ks < ks1; ++ks) {
             // 16 keys per MMA: advance 16 rows (2048 B) in the V panel; LBO = panel stride (d 64..127), SBO = 8 rows
-            umma_ts(tmem_o[i], tmem_s[i] + ks * 8, make_sdesc_sw128(va + ks * 2048, Cfg::kPanelBytes, 1024), idesc_o,
+            umma_ts_w(tmem_o[i], tmem_s[i] + ks * 8, make_sdesc_sw128(va + ks * 2048, Cfg::kPanelBytes, 1024), idesc_o,
                     (accumulate || ks != 0) ? 1u : 0u);
           }
         };
@@ -188,7 +190,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           mbar_wait(k_full(stage), phase, 40 + stage);
           tc_fence_after();
           issue_s(0, stage);
-          tc_commit(s_full(0));
+          tc_commit_w(s_full(0));
           if (j > 0) {
             if (SPLIT) {
               mbar_wait(p_half(1), (uint32_t)((j - 1) & 1), 53);
@@ -202,11 +204,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
               tc_fence_after();
               issue_pv(1, pstage, j - 1 > 0, 0, 8);
             }
-            tc_commit(v_empty(pstage));
+            tc_commit_w(v_empty(pstage));
           }
           issue_s(1, stage);
-          tc_commit(s_full(1));
-          tc_commit(k_empty(stage));
+          tc_commit_w(s_full(1));
+          tc_commit_w(k_empty(stage));
           mbar_wait(v_full(stage), phase, 60 + stage);
           if (SPLIT) {
             mbar_wait(p_half(0), (uint32_t)(j & 1), 54);
@@ -226,7 +228,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             phase ^= 1u;
           }
         }
-        tc_commit(o_done(0));
+        tc_commit_w(o_done(0));
         if (SPLIT) {
           mbar_wait(p_half(1), (uint32_t)((T - 1) & 1), 55);
           tc_fence_after();
@@ -239,8 +241,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           tc_fence_after();
           issue_pv(1, pstage, T - 1 > 0, 0, 8);
         }
-        tc_commit(v_empty(pstage));
-        tc_commit(o_done(1));
+        tc_commit_w(v_empty(pstage));
+        tc_commit_w(o_done(1));
       }
     }
   } else {

@@ -108,7 +108,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // whole warp, convergent: one elected lane issues inside the *_w wrappers (see ptx.cuh)
+    {
       constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -128,15 +129,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             uint64_t adesc = make_sdesc_sw128(a_addr + k * 32, 16, 1024);
             uint64_t bdesc = make_sdesc_sw128(b_addr + k * 32, 16, 1024);
-            umma_ss(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_ss_w(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          tc_commit(empty_bar(stage));  // smem slot is free once these MMAs retire
+          tc_commit_w(empty_bar(stage));  // smem slot is free once these MMAs retire
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        tc_commit(tfull_bar(acc));  // accumulator ready for the epilogue
+        tc_commit_w(tfull_bar(acc));  // accumulator ready for the epilogue
       }
     }
   } else if (warp >= 4) {
@@ -277,7 +278,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
+    // whole warp of the leader CTA, convergent: one elected lane issues inside the *_w wrappers (see ptx.cuh)
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(2 * GEMM_BM, BN, 0);  // M = 256 across the pair
       int stage = 0;
       uint32_t phase = 0;
@@ -300,16 +302,16 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
             for (int mh = 0; mh < MH; ++mh) {
               uint64_t adesc = make_sdesc_sw128(a_addr + mh * (GEMM_BM * GEMM_BK * 2) + k * 32, 16, 1024);
-              umma_ss_2cta(tmem_d + mh * BN, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_ss_2cta_w(tmem_d + mh * BN, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
             }
           }
-          tc_commit_2cta(empty_bar(stage), 0b11);  // frees this stage in BOTH CTAs
+          tc_commit_2cta_w(empty_bar(stage), 0b11);  // frees this stage in BOTH CTAs
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        tc_commit_2cta(tfull_bar(acc), 0b11);  // accumulators ready in both CTAs
+        tc_commit_2cta_w(tfull_bar(acc), 0b11);  // accumulators ready in both CTAs
       }
     }
   } else if (warp >= 4) {

@@ -322,6 +322,74 @@ __device__ __forceinline__ void tc_commit_2cta(uint32_t bar, uint16_t cta_mask) 
       "h"(cta_mask)
       : "memory");
 }
+// ----------------------------------------------------------------------------------------------
+// Warp-uniform issue forms ("_w"): called by ALL 32 lanes of the issuing warp under convergent control flow; one lane,
+// picked by elect.sync inside the asm (deterministic for a full mask, so every call elects the same lane and
+// tcgen05.commit tracks the MMAs that lane issued), executes the instruction. Because the surrounding code is not
+// divergent, ptxas keeps descriptors / addresses in uniform registers and emits the UTC* instruction directly — the
+// `if (lane == 0)` form costs an ELECT + vote + branch loop and four R2UR moves per MMA and made the single issuing
+// thread the bottleneck of the attention kernel (ncu source page, profiles/r01_attn_issue_bound.txt).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void umma_ss_w(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      ".reg .b32 rx;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync rx|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_w(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      ".reg .b32 rx;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync rx|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_w(uint32_t bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      ".reg .b32 rx;\n\t"
+      "elect.sync rx|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ss_2cta_w(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      ".reg .b32 rx;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync rx|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2cta_w(uint32_t bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      ".reg .b32 rx;\n\t"
+      "elect.sync rx|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t"
+      "}\n" ::"r"(bar),
+      "h"(cta_mask)
+      : "memory");
+}
 // arrive on the mbarrier at the same offset in CTA `cta` of the cluster
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
   asm volatile(

@@ -1,0 +1,108 @@
+#!/usr/bin/env python
+"""Isolated kernel timings at the BASELINE config-2 / config-3 shapes (CUDA events on the launching stream, 3 warm-up +
+N timed back-to-back launches per kernel). For A/B-ing a kernel change; the judged numbers come from bench.py.
+Usage: python tools/kbench.py [attn] [attn64] [cross] [gemm] [rows] [--iters 10]"""
+import math
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from frameino_b200 import ops  # noqa: E402
+
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+iters = 10
+if "--iters" in sys.argv:
+    iters = int(sys.argv[sys.argv.index("--iters") + 1])
+which = args or ["attn", "attn64", "cross", "gemm", "rows"]
+if os.environ.get("FINO_GEMM_MODE"):
+    ops.gemm_set_mode(int(os.environ["FINO_GEMM_MODE"]))
+if os.environ.get("FINO_ATTN_VARIANT"):
+    ops.attention_set_variant(int(os.environ["FINO_ATTN_VARIANT"]))
+
+
+def timeit(fn, flops=0.0, bytes_=0.0, name=""):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / iters
+    extra = ""
+    if flops:
+        extra += f"  {flops / ms / 1e9:8.1f} TFLOP/s"
+    if bytes_:
+        extra += f"  {bytes_ / ms / 1e6:8.1f} GB/s"
+    print(f"KBENCH {name:<44} {ms * 1e3:10.1f} us{extra}", flush=True)
+
+
+n, h, hd = 28160, 24, 128
+d = h * hd
+torch.manual_seed(0)
+if "attn" in which:
+    qkv = torch.randn(1, n, 3 * d, device="cuda").bfloat16()
+    o = torch.empty(1, n, d, device="cuda", dtype=torch.bfloat16)
+    timeit(lambda: ops.attention(qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:], h, out=o), 4.0 * n * n * d,
+           name="attention d128 28160x28160 h24")
+    n8 = n
+    q8 = qkv[..., : 3 * 384].contiguous()  # what one rank sees at P = 8: 3 heads, all tokens
+    timeit(lambda: ops.attention(q8[..., :384], q8[..., 384:768], q8[..., 768:], 3), 4.0 * n8 * n8 * 384,
+           name="attention d128 28160x28160 h3 (P=8 shard)")
+    del qkv, o
+if "attn64" in which:
+    n2, h2 = 19126, 48
+    qkv = torch.randn(1, n2, 3 * d, device="cuda").bfloat16()
+    timeit(lambda: ops.attention(qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:], h2), 4.0 * n2 * n2 * d,
+           name="attention d64 19126x19126 h48")
+    del qkv
+if "cross" in which:
+    q = torch.randn(1, n, d, device="cuda").bfloat16()
+    kv = torch.randn(1, 512, 2 * d, device="cuda").bfloat16()
+    timeit(lambda: ops.attention(q, kv[..., :d], kv[..., d:], h), 4.0 * n * 512 * d, name="cross attention 28160x512 h24")
+    del q, kv
+if "gemm" in which:
+    a = torch.randn(n, d, device="cuda").bfloat16()
+    f = 14336
+    x = a.clone()
+    tab = torch.randn(2, 6 * d, device="cuda")
+    ridx = torch.zeros(n, device="cuda", dtype=torch.int32)
+    ridx[880:] = 1
+    for (nn, kk, epi, nm) in [(3 * d, d, ops.EPI_NONE, "qkv"), (d, d, ops.EPI_GATE_RESIDUAL, "out+gate-res"),
+                              (d, d, ops.EPI_NONE, "cross-q"), (f, d, ops.EPI_GELU_TANH, "ffn-up+gelu"),
+                              (d, f, ops.EPI_GATE_RESIDUAL, "ffn-down+gate-res")]:
+        inp = a if kk == d else torch.randn(n, kk, device="cuda").bfloat16()
+        w = (torch.randn(nn, kk, device="cuda") / math.sqrt(kk)).bfloat16()
+        b = torch.randn(nn, device="cuda").bfloat16()
+        if epi == ops.EPI_GATE_RESIDUAL:
+            fn = lambda: ops.linear(inp, w, b, epilogue=epi, residual=x, gate=tab[:, :d], row_index=ridx, out=x)  # noqa: E731
+        else:
+            out = torch.empty(n, nn, device="cuda", dtype=torch.bfloat16)
+            fn = lambda: ops.linear(inp, w, b, epilogue=epi, out=out)  # noqa: E731
+        timeit(fn, 2.0 * n * nn * kk, name=f"gemm {nm} M{n} N{nn} K{kk}")
+        del w, b
+    del a, x
+if "rows" in which:
+    x = torch.randn(n, d, device="cuda").bfloat16()
+    tab = torch.randn(2, 6 * d, device="cuda")
+    ridx = torch.zeros(n, device="cuda", dtype=torch.int32)
+    ridx[880:] = 1
+    o = torch.empty_like(x)
+    timeit(lambda: ops.ln_modulate(x, 1e-6, shift=tab[:, :d], scale=tab[:, d:2 * d], row_index=ridx, out=o),
+           bytes_=2.0 * n * d * 2, name="ln_modulate 28160x3072")
+    g, b = torch.randn(d, device="cuda"), torch.randn(d, device="cuda")
+    timeit(lambda: ops.ln_modulate(x, 1e-6, gamma=g, beta=b, out=o), bytes_=2.0 * n * d * 2,
+           name="ln affine 28160x3072")
+    qkv = torch.randn(1, n, 3 * d, device="cuda").bfloat16()
+    wq = torch.ones(d, device="cuda").bfloat16()
+    cos = torch.rand(n, hd, device="cuda")
+    sin = torch.rand(n, hd, device="cuda")
+    timeit(lambda: ops.qk_norm_rope(qkv[..., :d], wq, qkv[..., d:2 * d], wq, h, rope_mode=ops.ROPE_WAN, cos=cos,
+                                    sin=sin, seq_len=n), bytes_=4.0 * n * d * 2 + 2.0 * n * hd * 4,
+           name="qk_norm_rope 28160x(2x3072)")
+    timeit(lambda: ops.qk_norm_rope(x, wq, None, None, h), bytes_=2.0 * n * d * 2, name="q_norm (cross) 28160x3072")
+print("done", which)
