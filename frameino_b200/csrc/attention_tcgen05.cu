@@ -79,7 +79,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   auto p_half = [&](int i) { return bars + 8u * (7 + 4 * KST + i); };  // first 64 keys of P_i written (SPLIT)
   const uint32_t tmem_ptr_smem = bars + 8u * (9 + 4 * KST);
 
-  const int warp = threadIdx.x >> 5;
+  // shfl makes the warp index provably warp-uniform for ptxas: role branches become uniform branches and the issue
+  // warps keep descriptors / addresses in uniform registers (CUTLASS canonical_warp_idx_sync idiom)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int head = blockIdx.y;
   const int batch = blockIdx.z;
@@ -161,24 +163,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const uint32_t tmem_s[2] = {tmem_base + 0u, tmem_base + 128u};
         const uint32_t tmem_o[2] = {tmem_base + 256u, tmem_base + 384u};
 
+        // Descriptors are built once; per KV tile only the stage offset (in 16-byte descriptor units) is added.
+        const uint64_t qdesc0 = make_sdesc_sw128(q_smem, 16, 1024);
+        const uint64_t kdesc0 = make_sdesc_sw128(k_smem, 16, 1024);
+        const uint64_t vdesc0 = make_sdesc_sw128(v_smem, Cfg::kPanelBytes, 1024);  // LBO = panel stride (d 64..127)
+        constexpr uint32_t kTileUnits = Cfg::kTileBytes >> 4, kPanelUnits = Cfg::kPanelBytes >> 4;
+
         auto issue_s = [&](int i, int kstage) {
-          const uint32_t qa = q_smem + i * Cfg::kTileBytes;
-          const uint32_t ka = k_smem + kstage * Cfg::kTileBytes;
+          const uint64_t qd = qdesc0 + (uint64_t)(i * kTileUnits);
+          const uint64_t kd = kdesc0 + (uint64_t)((uint32_t)kstage * kTileUnits);
 #pragma unroll
-          for (int ks = 0; ks < HD / 16; ++ks) {
-            const uint32_t off = (ks >> 2) * Cfg::kPanelBytes + (ks & 3) * 32;
-            umma_ss_w(tmem_s[i], make_sdesc_sw128(qa + off, 16, 1024), make_sdesc_sw128(ka + off, 16, 1024), idesc_s,
-                    ks != 0 ? 1u : 0u);
-          }
+          for (int hf = 0; hf < Cfg::kHalves; ++hf)  // one 64-column panel of d per call, 4 MMAs each
+            umma_ss_x4_w(tmem_s[i], qd + hf * kPanelUnits, kd + hf * kPanelUnits, idesc_s, hf != 0 ? 1u : 0u);
         };
         auto issue_pv = [&](int i, int vstage, bool accumulate, int ks0, int ks1) {
-          const uint32_t va = v_smem + vstage * Cfg::kTileBytes;
+          const uint64_t vd = vdesc0 + (uint64_t)((uint32_t)vstage * kTileUnits);
 #pragma unroll
-          for (int ks = ks0; ks < ks1; ++ks) {
-            // 16 keys per MMA: advance 16 rows (2048 B) in the V panel; LBO = panel stride (d 64..127), SBO = 8 rows
-            umma_ts_w(tmem_o[i], tmem_s[i] + ks * 8, make_sdesc_sw128(va + ks * 2048, Cfg::kPanelBytes, 1024), idesc_o,
-                    (accumulate || ks != 0) ? 1u : 0u);
-          }
+          for (int g = ks0 / 4; g < ks1 / 4; ++g)  // 64 keys per call; 16 keys = 16 V rows = 2048 B per MMA
+            umma_ts_x4_w(tmem_o[i], tmem_s[i] + g * 32, vd + (uint64_t)(g * 512), idesc_o,
+                         (accumulate || g != ks0 / 4) ? 1u : 0u);
         };
 
         mbar_wait(q_full, 0, 30);

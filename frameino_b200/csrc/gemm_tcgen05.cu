@@ -54,7 +54,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + 2 + s); };
   uint32_t tmem_ptr_smem = bars + 8u * (2 * kStages + 4);
 
-  const int warp = threadIdx.x >> 5;
+  // shfl makes the warp index provably warp-uniform for ptxas: role branches become uniform branches and the issue
+  // warps keep descriptors / addresses in uniform registers (CUTLASS canonical_warp_idx_sync idiom)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
@@ -218,7 +220,9 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + 2 + s); };   // leader only, 8 warp arrivals
   uint32_t tmem_ptr_smem = bars + 8u * (2 * kStages + 4);
 
-  const int warp = threadIdx.x >> 5;
+  // shfl makes the warp index provably warp-uniform for ptxas: role branches become uniform branches and the issue
+  // warps keep descriptors / addresses in uniform registers (CUTLASS canonical_warp_idx_sync idiom)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();
   const bool leader = cta_rank == 0;

@@ -356,6 +356,59 @@ __device__ __forceinline__ void umma_ts_w(uint32_t tmem_d, uint32_t tmem_a, uint
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Four k-steps (64 bf16 of K = one 128-byte swizzle panel) of D (+)= A[smem] * B[smem] in ONE elected issue: the
+// descriptors of steps 1..3 are the step-0 descriptors plus 32 bytes (2 descriptor units) each. `accumulate` applies
+// to the first step; the rest always accumulate.
+__device__ __forceinline__ void umma_ss_x4_w(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e, t;\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 t, %4, %4;\n\t"
+      "add.u64 a1, %1, 2;\n\t"
+      "add.u64 b1, %2, 2;\n\t"
+      "add.u64 a2, %1, 4;\n\t"
+      "add.u64 b2, %2, 4;\n\t"
+      "add.u64 a3, %1, 6;\n\t"
+      "add.u64 b3, %2, 6;\n\t"
+      "elect.sync rx|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, t;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Four k-steps (64 keys) of D (+)= A[tmem] * B[smem, MN-major]: A advances 8 TMEM columns (16 bf16) per step, B
+// advances 16 rows of the 128-byte-swizzled V panel = 2048 bytes = 128 descriptor units.
+__device__ __forceinline__ void umma_ts_x4_w(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e, t;\n\t"
+      ".reg .b32 rx, ta1, ta2, ta3;\n\t"
+      ".reg .b64 b1, b2, b3;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.eq.b32 t, %4, %4;\n\t"
+      "add.u32 ta1, %1, 8;\n\t"
+      "add.u64 b1, %2, 128;\n\t"
+      "add.u32 ta2, %1, 16;\n\t"
+      "add.u64 b2, %2, 256;\n\t"
+      "add.u32 ta3, %1, 24;\n\t"
+      "add.u64 b3, %2, 384;\n\t"
+      "elect.sync rx|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [ta1], b1, %3, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [ta2], b2, %3, t;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [ta3], b3, %3, t;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_commit_w(uint32_t bar) {
   asm volatile(
       "{\n\t"
