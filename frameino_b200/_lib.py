@@ -30,6 +30,7 @@ SIGNATURES = {
     "fino_attention_fwd": (_I, [_P, _P, _P, _P, _I, _I, _L, _L, _I, _L, _L, _L, _L, _L, _L, _L, _L, _F, _P]),
     "fino_attention_set_variant": (_I, [_I]),
     "fino_rows_set_variant": (_I, [_I, _I]),
+    "fino_rows_set_tma": (_I, [_I]),
     "fino_ln_modulate": (_I, [_P, _P, _L, _I, _L, _L, _F, _P, _P, _P, _P, _L, _P, _L, _I, _P]),
     "fino_gate_residual": (_I, [_P, _P, _P, _L, _I, _L, _L, _L, _P, _L, _P, _L, _I, _P]),
     "fino_qk_norm_rope": (_I, [_P, _L, _L, _P, _P, _I, _P, _L, _L, _P, _P, _I, _I, _I, _I, _F, _I, _P, _P, _L, _L, _P]),

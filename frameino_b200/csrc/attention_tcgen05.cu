@@ -135,13 +135,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         int stage = 0;
         uint32_t phase = 0;
         for (int j = 0; j < T; ++j) {
-          mbar_wait(k_empty(stage), phase ^ 1u, 10 + stage);
+          mbar_wait_relaxed(k_empty(stage), phase ^ 1u, 10 + stage);
           mbar_arrive_expect_tx(k_full(stage), Cfg::kTileBytes);
 #pragma unroll
           for (int hf = 0; hf < Cfg::kHalves; ++hf)
             tma_load_3d(k_smem + stage * Cfg::kTileBytes + hf * Cfg::kPanelBytes, &tmap_k, k_full(stage),
                         c_head + hf * 64, j * ATT_BN, batch);
-          mbar_wait(v_empty(stage), phase ^ 1u, 20 + stage);
+          mbar_wait_relaxed(v_empty(stage), phase ^ 1u, 20 + stage);
           mbar_arrive_expect_tx(v_full(stage), Cfg::kTileBytes);
 #pragma unroll
           for (int hf = 0; hf < Cfg::kHalves; ++hf)

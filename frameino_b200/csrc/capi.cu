@@ -51,6 +51,8 @@ int qkv_norm_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride, con
 void gemm_set_mode(int mode);
 void attention_set_variant(int v);
 void rows_set_variant(int ln_block, int qk_block);
+void rows_set_tma(int on);
+void scatter_set_tma(int on);
 }  // namespace fino
 
 static std::atomic<int64_t> g_launches{0};
@@ -189,6 +191,12 @@ int fino_attention_set_variant(int variant) {
 
 int fino_rows_set_variant(int ln_block, int qk_block) {
   fino::rows_set_variant(ln_block, qk_block);
+  return 0;
+}
+
+int fino_rows_set_tma(int on) {
+  fino::rows_set_tma(on);
+  fino::scatter_set_tma(on);
   return 0;
 }
 

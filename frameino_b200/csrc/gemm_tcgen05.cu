@@ -95,7 +95,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         int mt, nt;
         tile_coords(tile, p.num_m_tiles, p.num_n_tiles, mt, nt);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u, 100 + stage);
+          mbar_wait_relaxed(empty_bar(stage), phase ^ 1u, 100 + stage);
           uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
           uint32_t b_dst = a_dst + Cfg::kABytes;
           mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
@@ -267,7 +267,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const int row_a = mt * Cfg::kTileM + (int)cta_rank * (MH * GEMM_BM);
         const int row_b = nt * BN + (int)cta_rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u, 100 + stage);
+          mbar_wait_relaxed(empty_bar(stage), phase ^ 1u, 100 + stage);
           uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
           uint32_t b_dst = a_dst + Cfg::kABytes;
           if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);

@@ -244,6 +244,16 @@ ln_modulate_block_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __r
   }
 }
 
+int ln_modulate_tma(const void* x, void* out, int64_t rows, int dim, int64_t x_stride, int64_t out_stride, float eps,
+                    const float* gamma, const float* beta, const float* shift, const float* scale,
+                    int64_t mod_row_stride, const int32_t* row_index, int64_t rows_per_group, int flags,
+                    cudaStream_t stream);
+// TMA-staged persistent row kernels (rows_tma.cu). Off by default: measured slower than the warp-per-row kernels
+// (in-step LN 260 us vs 120 us, q/k 331 us vs 267 us at 28160 x 3072, r01) - the block-wide reductions put three
+// barrier phases on every ring stage. Kept behind fino_rows_set_tma for the next iteration (per-warp rings).
+static bool g_rows_tma = false;
+void rows_set_tma(int on) { g_rows_tma = on != 0; }
+
 int ln_modulate(const void* x, void* out, int64_t rows, int dim, int64_t x_stride, int64_t out_stride, float eps,
                 const float* gamma, const float* beta, const float* shift, const float* scale, int64_t mod_row_stride,
                 const int32_t* row_index, int64_t rows_per_group, int flags, cudaStream_t stream) {
@@ -255,6 +265,9 @@ int ln_modulate(const void* x, void* out, int64_t rows, int dim, int64_t x_strid
   FINO_CHECK_ARG(shift == nullptr || row_index != nullptr || rows_per_group > 0,
                  "ln_modulate: need row_index or rows_per_group");
   FINO_CHECK_ARG(dim <= 32 * 8 * 32, "ln_modulate: dim %d too large (max 8192)", dim);
+  if (g_rows_tma && dim >= 1024 && dim <= 4096 && rows >= 256 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0)
+    return ln_modulate_tma(x, out, rows, dim, x_stride, out_stride, eps, gamma, beta, shift, scale, mod_row_stride,
+                           row_index, rows_per_group, flags, stream);
   const int cpl = (dim / 8 + 31) / 32;
   dim3 grid((unsigned)((rows + ROW_WARPS - 1) / ROW_WARPS));
   if (rows_per_group <= 0) rows_per_group = (int64_t)1 << 62;
@@ -588,6 +601,11 @@ __global__ void __launch_bounds__(512) qk_rms_rope_block_kernel(const QkParams p
   }
 }
 
+bool qk_tma_eligible(int64_t rows, int heads, int head_dim);
+int qk_rms_rope_tma(void* q, int64_t q_stride, void* k, int64_t k_stride, int64_t rows, const void* wq, const void* wk,
+                    int heads, int head_dim, float eps, const float* cos, const float* sin, int64_t seq_len,
+                    cudaStream_t stream);
+
 int qk_norm_rope(void* x0, int64_t rows0, int64_t stride0, const void* w0, const void* b0, int rope0, void* x1,
                  int64_t rows1, int64_t stride1, const void* w1, const void* b1, int rope1, int heads, int head_dim,
                  int norm_mode, float eps, int rope_mode, const float* cos, const float* sin, int64_t seq_len,
@@ -605,6 +623,24 @@ int qk_norm_rope(void* x0, int64_t rows0, int64_t stride0, const void* w0, const
   FINO_CHECK_ARG(!any_rope || (cos && sin && seq_len > 0), "qk_norm_rope: rope tables / seq_len missing");
   const int dim = heads * head_dim;
   FINO_CHECK_ARG(dim <= 8192, "qk_norm_rope: heads*head_dim too large");
+  // Wan self-attention (q and k, same rows, both rotated or neither) and cross-attention q (alone, no RoPE):
+  // TMA-staged persistent kernel (rows_tma.cu)
+  if (g_rows_tma && norm_mode == QK_RMS_ACROSS_HEADS && qk_tma_eligible(rows0, heads, head_dim) && rope_skip == 0 &&
+      b0 == nullptr && b1 == nullptr && (rope_mode == ROPE_NONE || rope_mode == ROPE_WAN) &&
+      (x1 == nullptr ? !any_rope : (rows1 == rows0 && (!any_rope || (rope0 && rope1)))) &&
+      ((reinterpret_cast<uintptr_t>(x0) | reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(cos) |
+        reinterpret_cast<uintptr_t>(sin)) & 15) == 0 && (!any_rope || head_dim % 4 == 0))
+    return qk_rms_rope_tma(x0, stride0, x1, stride1, rows0, w0, w1, heads, head_dim, eps, any_rope ? cos : nullptr,
+                           any_rope ? sin : nullptr, seq_len, stream);
+  // cross-attention: q has N rows, k the 512 text rows, no RoPE -> the wide q through the TMA kernel, k on its own
+  if (g_rows_tma && norm_mode == QK_RMS_ACROSS_HEADS && x1 != nullptr && rows1 != rows0 && !any_rope &&
+      b0 == nullptr && b1 == nullptr && qk_tma_eligible(rows0, heads, head_dim) &&
+      (reinterpret_cast<uintptr_t>(x0) & 15) == 0) {
+    int r = qk_rms_rope_tma(x0, stride0, nullptr, 0, rows0, w0, nullptr, heads, head_dim, eps, nullptr, nullptr, 0, stream);
+    if (r != FINO_OK) return r;
+    return qk_norm_rope(x1, rows1, stride1, w1, nullptr, 0, nullptr, 0, 0, nullptr, nullptr, 0, heads, head_dim, norm_mode,
+                        eps, ROPE_NONE, nullptr, nullptr, 0, 0, stream);
+  }
   QkParams p;
   p.t[0] = {(__nv_bfloat16*)x0, rows0, stride0, (const __nv_bfloat16*)w0, (const __nv_bfloat16*)b0, rope0};
   p.t[1] = {(__nv_bfloat16*)x1, x1 ? rows1 : 0, stride1, (const __nv_bfloat16*)w1, (const __nv_bfloat16*)b1, rope1};

@@ -258,6 +258,14 @@ __global__ void __launch_bounds__(512) qkv_norm_rope_scatter_kernel(const __grid
   }
 }
 
+bool qk_tma_eligible(int64_t rows, int heads, int head_dim);
+int qkv_rms_rope_scatter_tma(const void* qkv, int64_t rows, int64_t row_stride, const void* wq, const void* wk,
+                             int heads, int head_dim, float eps, const float* cos, const float* sin,
+                             void* const* dst_ptrs, int world, int rank, int64_t rows_per_rank,
+                             int64_t dst_row_stride, cudaStream_t stream);
+static bool g_scatter_tma = false;  // see g_rows_tma in norm_kernels.cu
+void scatter_set_tma(int on) { g_scatter_tma = on != 0; }
+
 int qkv_norm_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride, const void* wq, const void* wk,
                           int heads, int head_dim, float eps, const float* cos, const float* sin,
                           void* const* dst_ptrs, int world, int rank, int64_t rows_per_rank, int64_t dst_row_stride,
@@ -274,6 +282,13 @@ int qkv_norm_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride, con
   FINO_CHECK_ARG(dst_row_stride % 8 == 0 && dst_row_stride >= 3 * inner, "qkv_norm_rope_scatter: dst row stride");
   FINO_CHECK_ARG(rows <= rows_per_rank, "qkv_norm_rope_scatter: more local rows than rows_per_rank");
   FINO_CHECK_ARG((cos == nullptr) == (sin == nullptr), "qkv_norm_rope_scatter: cos and sin go together");
+  for (int r = 0; r < world; ++r)
+    FINO_CHECK_ARG(dst_ptrs[r] != nullptr && (reinterpret_cast<uintptr_t>(dst_ptrs[r]) & 15) == 0,
+                   "qkv_norm_rope_scatter: dst %d null or unaligned", r);
+  if (g_scatter_tma && qk_tma_eligible(rows, heads, head_dim) && head_dim % 4 == 0 &&
+      ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(cos) | reinterpret_cast<uintptr_t>(sin)) & 15) == 0)
+    return qkv_rms_rope_scatter_tma(qkv, rows, row_stride, wq, wk, heads, head_dim, eps, cos, sin, dst_ptrs, world, rank,
+                                    rows_per_rank, dst_row_stride, stream);
   ScatterParams p;
   p.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
   p.rows = rows;

@@ -87,6 +87,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
   }
 }
 
+// Wait with back-off for warps that run AHEAD of the critical path (TMA producers waiting for a free stage): a tight
+// try_wait loop there is pure power draw — the producer warp of the attention kernel executed ~8 % of all the kernel's
+// instructions spinning (ncu, r01) on a part that runs at its power cap.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, int tag = 0) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(96);
+    if (clock64() - t0 > FINO_WAIT_TIMEOUT_CYCLES) {
+      printf("[fino] mbarrier timeout: tag=%d block=(%d,%d,%d) thread=%d parity=%u\n", tag, blockIdx.x,
+             blockIdx.y, blockIdx.z, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+
 // Same, with cluster-scope acquire (the arrivals come from the peer CTA of a pair).
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int tag = 0) {
   long long t0 = clock64();

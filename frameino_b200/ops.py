@@ -343,6 +343,11 @@ def rows_set_variant(ln_block: bool, qk_block: bool) -> None:
     _lib.check(_lib.load().fino_rows_set_variant(int(ln_block), int(qk_block)), "fino_rows_set_variant")
 
 
+def rows_set_tma(on: bool) -> None:
+    """Experimental TMA-staged persistent row kernels for wide rows (default off = register-resident row kernels)."""
+    _lib.check(_lib.load().fino_rows_set_tma(int(on)), "fino_rows_set_tma")
+
+
 def launch_count() -> int:
     return int(_lib.load().fino_launch_count())
 

@@ -64,6 +64,9 @@ int fino_attention_set_variant(int variant);
 
 /* Tuning / test hook: choose the block-per-row variants of the LayerNorm / qk-norm kernels (0 = warp-per-row). */
 int fino_rows_set_variant(int ln_block, int qk_block);
+/* Tuning / test hook: 1 = wide rows (1024 <= dim <= 4096) go through the experimental TMA-staged persistent row
+ * kernels (bulk async copies through a shared-memory ring); 0 (default) = the register-resident row kernels. */
+int fino_rows_set_tma(int on);
 
 #define FINO_LN_FLAG_BF16_STEPS 1 /* emulate the bf16 module flow of CogVideoXLayerNormZero / AdaLayerNorm */
 

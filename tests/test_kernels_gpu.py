@@ -259,3 +259,50 @@ def test_invalid_arguments_raise(ops):
         ops.attention(bf(1, 8, 136).cuda(), bf(1, 8, 136).cuda(), bf(1, 8, 136).cuda(), 1)  # head_dim 136 unsupported
     with pytest.raises(FinoError):
         ops.linear(bf(4, 12).cuda(), bf(8, 12).cuda())  # K not a multiple of 8
+
+
+@pytest.mark.parametrize("rows,dim", [(1003, 3072), (256, 1024), (2049, 4096), (777, 2048)])
+def test_rows_tma_kernels_match_warp_kernels(ops, rows, dim):
+    """The TMA-staged persistent row kernels (rows_tma.cu) against the register-resident warp-per-row kernels on the
+    same inputs: ragged row counts (tail stage), strided views, both modulation-row selectors, q-only and q+k forms."""
+    heads = dim // 128
+    x = bf(rows, dim + 64, scale=2.0)
+    tab = torch.randn(3, 6 * dim, generator=torch.Generator().manual_seed(1)).cuda() * 0.5
+    ridx = torch.randint(0, 3, (rows,), generator=torch.Generator().manual_seed(2)).int().cuda()
+    g, b = torch.randn(dim).cuda(), torch.randn(dim).cuda()
+    xc = x.cuda()[:, 32:32 + dim]  # strided view: per-row bulk copies
+    assert not xc.is_contiguous()
+    qkv = bf(1, rows, 3 * dim, seed=4).cuda()
+    wq, wk = (1 + 0.1 * torch.randn(dim)).bfloat16().cuda(), (1 + 0.1 * torch.randn(dim)).bfloat16().cuda()
+    ang = torch.rand(rows, 64) * 6.28
+    cos = ang.cos().repeat_interleave(2, dim=1).contiguous().cuda()
+    sin = ang.sin().repeat_interleave(2, dim=1).contiguous().cuda()
+    res = {}
+    for tma in (False, True):
+        ops.rows_set_tma(tma)
+        try:
+            r = []
+            r.append(ops.ln_modulate(xc, 1e-6, shift=tab[:, :dim], scale=tab[:, dim:2 * dim], row_index=ridx))
+            r.append(ops.ln_modulate(xc.contiguous(), 1e-6, shift=tab[:, :dim], scale=tab[:, dim:2 * dim],
+                                     rows_per_group=(rows + 2) // 3))
+            r.append(ops.ln_modulate(xc, 1e-6, gamma=g, beta=b))
+            r.append(ops.ln_modulate(xc.contiguous(), 1e-5, gamma=g, beta=b, shift=tab[:, :dim],
+                                     scale=tab[:, dim:2 * dim], row_index=ridx, bf16_steps=True))
+            t = qkv.clone()
+            ops.qk_norm_rope(t[..., :dim], wq, t[..., dim:2 * dim], wk, heads, rope_mode=ops.ROPE_WAN, cos=cos, sin=sin,
+                             seq_len=rows)
+            r.append(t)
+            t2 = qkv.clone()
+            ops.qk_norm_rope(t2[..., :dim], wq, t2[..., dim:2 * dim], wk, heads)  # no rope
+            r.append(t2)
+            q3, k3 = qkv[0, :, :dim].contiguous(), qkv[0, :16, dim:2 * dim].contiguous()
+            ops.qk_norm_rope(q3, wq, k3, wk, heads)  # cross-attention form
+            r += [q3, k3]
+            res[tma] = r
+        finally:
+            ops.rows_set_tma(False)
+    for i, (a, c) in enumerate(zip(res[False], res[True])):
+        if i < 4:  # LayerNorm: the block-wide fp32 sums associate differently -> last-bit differences only
+            assert rel_err(c, a) <= 4e-3, i
+        else:      # RMSNorm + RoPE: one rsqrt per row, everything after it is per element -> bf16-ulp agreement
+            assert rel_err(c, a) <= 8e-3, i  # <= 2 bf16 ulps at the largest magnitude

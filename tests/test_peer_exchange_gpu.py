@@ -29,18 +29,37 @@ def _inputs(n_total, heads, hd, seed=0):
     return qkv, wq, wk, cos, sin
 
 
-@pytest.mark.parametrize("world,n_total,heads,hd", [(1, 300, 2, 128), (2, 1024, 4, 128), (4, 777, 4, 128),
-                                                   (8, 1000, 8, 64), (2, 515, 6, 64)])
-def test_fused_exchange_matches_unsharded(ops, world, n_total, heads, hd):
+@pytest.mark.parametrize("world,n_total,heads,hd,tma", [(1, 300, 2, 128, False), (2, 1024, 4, 128, False),
+                                                       (4, 777, 4, 128, False), (8, 1000, 8, 64, False),
+                                                       (2, 515, 6, 64, False), (2, 1201, 8, 128, True),
+                                                       (4, 2055, 16, 64, True)])
+def test_fused_exchange_matches_unsharded(ops, world, n_total, heads, hd, tma):
+    try:
+        _run_fused_exchange(ops, world, n_total, heads, hd, tma)
+    finally:
+        ops.rows_set_tma(False)
+
+
+def _same(a, b, exact):
+    if exact:
+        return torch.equal(a, b)
+    # TMA-staged scatter kernel: its block-wide sum of squares associates differently -> <= 2 bf16 ulps
+    return float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-9)) <= 1e-2
+
+
+def _run_fused_exchange(ops, world, n_total, heads, hd, tma):
     from frameino_b200.ulysses import SequenceParallel, exchange_layout
 
     d = heads * hd
     qkv, wq, wk, cos, sin = _inputs(n_total, heads, hd)
     # un-sharded reference: in-place norm+rope then attention, same kernels' single-GPU forms
     ref_qkv = qkv.clone()
+    ops.rows_set_tma(False)
     ops.qk_norm_rope(ref_qkv[..., :d], wq, ref_qkv[..., d:2 * d], wk, heads, norm_mode=ops.QK_RMS_ACROSS_HEADS,
                      eps=1e-6, rope_mode=ops.ROPE_WAN, cos=cos, sin=sin, seq_len=n_total)
     ref = ops.attention(ref_qkv[..., :d], ref_qkv[..., d:2 * d], ref_qkv[..., 2 * d:], heads)
+    ops.rows_set_tma(tma)  # True: the TMA-staged scatter kernel (eligible configs only); the reference stays un-staged
+    exact = not tma
 
     n_loc, n_pad = SequenceParallel.partition(n_total, world)
     lays = [exchange_layout(world, r, n_loc, d) for r in range(world)]
@@ -66,7 +85,7 @@ def test_fused_exchange_matches_unsharded(ops, world, n_total, heads, hd):
             got = ops.tensor_from_ptr(bases[r] + lays[r]["qkv_off"], (1, n_pad, 3 * inner))[:, :n_total]
             for part in range(3):
                 want = ref_qkv[..., part * d + r * inner: part * d + (r + 1) * inner]
-                assert torch.equal(got[..., part * inner:(part + 1) * inner], want), (r, part)
+                assert _same(got[..., part * inner:(part + 1) * inner], want, exact or part == 2), (r, part)
         # the barrier kernel with one participant per emulated rank, each on its own stream (all must be resident)
         streams = [torch.cuda.Stream() for _ in range(world)]
         torch.cuda.synchronize()
@@ -86,7 +105,7 @@ def test_fused_exchange_matches_unsharded(ops, world, n_total, heads, hd):
             lo, hi = r * n_loc, min((r + 1) * n_loc, n_total)
             o_loc = ops.tensor_from_ptr(bases[r] + lays[r]["o_off"], (1, n_loc, d))
             if hi > lo:
-                assert torch.equal(o_loc[:, : hi - lo], ref[:, lo:hi]), r
+                assert _same(o_loc[:, : hi - lo], ref[:, lo:hi], exact), r
             if hi - lo < n_loc:  # pad rows are never written: still the zero fill of peer_alloc
                 assert not o_loc[:, max(hi - lo, 0):].any()
     finally:
