@@ -41,6 +41,13 @@ struct AttnParams {
   int heads;
   float scale_log2;  // softmax scale * log2(e)
   int num_kv_tiles;
+  // Work decomposition (1-D grid). A "tile" is 256 query rows of one (batch, head); tile t = (b*heads + h)*q_tiles + qt.
+  // CTAs [0, n_full) each run one whole tile. The remaining tiles (the partial last wave) are split `splits` ways
+  // along the KV axis: CTA n_full + r handles KV tiles [s*T/S, (s+1)*T/S) of tile n_full + r/S (s = r%S) and writes an
+  // un-normalised fp32 partial (O, m, l) to the workspace; attn_combine_kernel merges them. splits == 1: no partials.
+  int q_tiles, n_full, splits;
+  float* ws_o;    // [(tile - n_full)*splits + s][256][HD] fp32
+  float2* ws_ml;  // [(tile - n_full)*splits + s][256] (running max in raw score units, row sum)
 };
 
 template <int HD>
@@ -83,10 +90,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   // warps keep descriptors / addresses in uniform registers (CUTLASS canonical_warp_idx_sync idiom)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
-  const int head = blockIdx.y;
-  const int batch = blockIdx.z;
-  const int q0 = blockIdx.x * (2 * ATT_BM);
-  const int T = p.num_kv_tiles;
+  // tile / KV-range decode (see AttnParams)
+  int tile = blockIdx.x, j0 = 0, T = p.num_kv_tiles;
+  const bool partial = (int)blockIdx.x >= p.n_full;
+  if (partial) {
+    const int r = (int)blockIdx.x - p.n_full;
+    const int sp = r % p.splits;
+    tile = p.n_full + r / p.splits;
+    j0 = (int)(((int64_t)sp * p.num_kv_tiles) / p.splits);
+    T = (int)(((int64_t)(sp + 1) * p.num_kv_tiles) / p.splits) - j0;
+  }
+  const int qt = tile % p.q_tiles;
+  const int head = (tile / p.q_tiles) % p.heads;
+  const int batch = tile / (p.q_tiles * p.heads);
+  const int q0 = qt * (2 * ATT_BM);
 
   if (warp == 8 && lane == 0) {
     prefetch_tmap(&tmap_q);
@@ -140,13 +157,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 #pragma unroll
           for (int hf = 0; hf < Cfg::kHalves; ++hf)
             tma_load_3d(k_smem + stage * Cfg::kTileBytes + hf * Cfg::kPanelBytes, &tmap_k, k_full(stage),
-                        c_head + hf * 64, j * ATT_BN, batch);
+                        c_head + hf * 64, (j0 + j) * ATT_BN, batch);
           mbar_wait_relaxed(v_empty(stage), phase ^ 1u, 20 + stage);
           mbar_arrive_expect_tx(v_full(stage), Cfg::kTileBytes);
 #pragma unroll
           for (int hf = 0; hf < Cfg::kHalves; ++hf)
             tma_load_3d(v_smem + stage * Cfg::kTileBytes + hf * Cfg::kPanelBytes, &tmap_v, v_full(stage),
-                        c_head + hf * 64, j * ATT_BN, batch);
+                        c_head + hf * 64, (j0 + j) * ATT_BN, batch);
           if (++stage == KST) {
             stage = 0;
             phase ^= 1u;
@@ -259,6 +276,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t t_o = tmem_base + lane_base + (wg ? 384u : 256u);
     const float sl2 = p.scale_log2;
 
+    int keys_left = p.nk - j0 * ATT_BN;  // keys from this CTA's first KV tile to the end of the sequence
     float m_used = -INFINITY;  // running max (raw score units) the exponentials are referenced to
     float l_sum = 0.f;
 
@@ -272,7 +290,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tmem_ld_32x32b_x32(t_s + 96, s[3]);
       tmem_wait_ld();
 
-      const int valid = p.nk - j * ATT_BN;  // keys of this tile that exist (>= 1)
+      const int valid = keys_left;  // keys of this tile that exist (>= 1)
+      keys_left -= ATT_BN;
       if (valid < ATT_BN) {
 #pragma unroll
         for (int c = 0; c < 4; ++c)
@@ -368,6 +387,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     // 16-byte ones, which matters doubly when the destination is a peer GPU's buffer behind NVLink.
     mbar_wait(o_done(wg), 0, 80 + wg);
     tc_fence_after();
+    if (partial) {
+      // KV-split CTA: un-normalised fp32 partial (O, m, l) to the workspace; attn_combine_kernel finishes the rows.
+      // (thread == row, so the stores are 16-byte pieces strided by a row; <= 148 CTAs x 128 KB per launch.)
+      const int64_t prow = (int64_t)((int)blockIdx.x - p.n_full) * (2 * ATT_BM) + wg * ATT_BM + row_in_tile;
+      float4* dst = reinterpret_cast<float4*>(p.ws_o + prow * HD);
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(t_o + c * 32, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          dst[c * 8 + e] = make_float4(__uint_as_float(o[4 * e]), __uint_as_float(o[4 * e + 1]),
+                                       __uint_as_float(o[4 * e + 2]), __uint_as_float(o[4 * e + 3]));
+      }
+      p.ws_ml[prow] = make_float2(m_used, l_sum);
+    } else {
     const float inv_l = 1.0f / l_sum;
     constexpr int CH = HD / 8;            // 16-byte chunks per output row
     constexpr int RPI = 32 / CH;          // rows per store instruction
@@ -408,6 +444,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         *reinterpret_cast<uint4*>(dst) = w;
       }
     }
+    }  // !partial
   }
 
   tc_fence_before();
@@ -416,6 +453,81 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+// Merges the KV-split partials of the tiles past n_full: one warp per query row, lane = 4 (d=128) / 2 (d=64) columns.
+//   M = max_s m_s;  w_s = 2^((m_s - M) * scale_log2);  O = sum_s w_s O_s / sum_s w_s l_s
+template <int HD>
+__global__ void __launch_bounds__(256) attn_combine_kernel(const __grid_constant__ AttnParams p, int rows_total) {
+  const int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (gw >= rows_total) return;
+  const int tl = gw / (2 * ATT_BM), r = gw % (2 * ATT_BM);
+  const int tile = p.n_full + tl;
+  const int qt = tile % p.q_tiles;
+  const int head = (tile / p.q_tiles) % p.heads;
+  const int batch = tile / (p.q_tiles * p.heads);
+  const int qrow = qt * (2 * ATT_BM) + r;
+  if (qrow >= p.nq) return;
+  constexpr int CPL = HD / 32;  // columns per lane
+  const int S = p.splits;
+  float mmax = -INFINITY;
+  for (int s = 0; s < S; ++s) mmax = fmaxf(mmax, p.ws_ml[(int64_t)(tl * S + s) * (2 * ATT_BM) + r].x);
+  float acc[CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) acc[i] = 0.f;
+  float l = 0.f;
+  for (int s = 0; s < S; ++s) {
+    const int64_t prow = (int64_t)(tl * S + s) * (2 * ATT_BM) + r;
+    const float2 ml = p.ws_ml[prow];
+    const float w = ex2_approx((ml.x - mmax) * p.scale_log2);
+    l += w * ml.y;
+    const float* src = p.ws_o + prow * HD + lane * CPL;
+    if (CPL == 4) {
+      const float4 v = *reinterpret_cast<const float4*>(src);
+      acc[0] += w * v.x; acc[1] += w * v.y; acc[2] += w * v.z; acc[CPL - 1] += w * v.w;
+    } else {
+      const float2 v = *reinterpret_cast<const float2*>(src);
+      acc[0] += w * v.x; acc[1] += w * v.y;
+    }
+  }
+  const float inv_l = 1.0f / l;
+  const int64_t owner = (int64_t)qrow / p.rows_per_owner;
+  const int64_t lrow = (int64_t)qrow - owner * p.rows_per_owner;
+  __nv_bfloat16* dst =
+      p.o[owner] + (int64_t)batch * p.o_batch_stride + lrow * p.o_row_stride + (int64_t)head * HD + lane * CPL;
+  if (CPL == 4) {
+    uint2 w2;
+    w2.x = pack_bf16x2(acc[0] * inv_l, acc[1] * inv_l);
+    w2.y = pack_bf16x2(acc[2] * inv_l, acc[CPL - 1] * inv_l);
+    *reinterpret_cast<uint2*>(dst) = w2;
+  } else {
+    *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(acc[0] * inv_l, acc[1] * inv_l);
+  }
+}
+
+// Per-device workspace for the KV-split partials (grown on demand; <= 148 CTAs x 256 rows x (HD*4 + 8) B = 19.7 MB in
+// the automatic mode). Calls on one device are assumed stream-ordered with each other (the reference convention: one
+// stream per process), since consecutive launches reuse the same workspace.
+static void* g_attn_ws[16] = {};
+static size_t g_attn_ws_bytes[16] = {};
+static int attn_workspace(size_t bytes, void** out) {
+  int dev = 0;
+  FINO_CHECK_CUDA(cudaGetDevice(&dev));
+  FINO_CHECK_ARG(dev >= 0 && dev < 16, "attention: device index %d out of range", dev);
+  if (g_attn_ws_bytes[dev] < bytes) {
+    if (g_attn_ws[dev]) {
+      FINO_CHECK_CUDA(cudaDeviceSynchronize());
+      FINO_CHECK_CUDA(cudaFree(g_attn_ws[dev]));
+      g_attn_ws[dev] = nullptr;
+      g_attn_ws_bytes[dev] = 0;
+    }
+    size_t want = bytes < ((size_t)20 << 20) ? ((size_t)20 << 20) : bytes;
+    FINO_CHECK_CUDA(cudaMalloc(&g_attn_ws[dev], want));
+    g_attn_ws_bytes[dev] = want;
+  }
+  *out = g_attn_ws[dev];
+  return FINO_OK;
 }
 
 template <int HD, int EMU, bool SPLIT>
@@ -428,9 +540,15 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
                                          Cfg::kSmemBytes));
     configured = true;
   }
-  dim3 grid((p.nq + 2 * ATT_BM - 1) / (2 * ATT_BM), p.heads, batch);
-  attn_fwd_kernel<HD, EMU, SPLIT><<<grid, ATT_THREADS, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
+  const int n_tiles = p.q_tiles * p.heads * batch;
+  const int n_part = (n_tiles - p.n_full) * p.splits;
+  attn_fwd_kernel<HD, EMU, SPLIT><<<p.n_full + n_part, ATT_THREADS, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
   FINO_CHECK_CUDA(cudaGetLastError());
+  if (n_part > 0) {
+    const int rows_total = (n_tiles - p.n_full) * 2 * ATT_BM;
+    attn_combine_kernel<HD><<<(rows_total + 7) / 8, 256, 0, stream>>>(p, rows_total);
+    FINO_CHECK_CUDA(cudaGetLastError());
+  }
   return FINO_OK;
 }
 
@@ -438,6 +556,37 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
 // the exponentials; results agree to bf16 rounding.
 static int g_attn_variant = 0;
 void attention_set_variant(int v) { g_attn_variant = v; }
+
+// KV split of the partial last wave (fino_attention_set_split): -1 = automatic (default), 0 = never, S >= 2 = split
+// EVERY tile S ways (test hook: exercises the partial + combine path at any shape).
+static int g_attn_split = -1;
+void attention_set_split(int s) { g_attn_split = s; }
+
+// Chooses (n_full, splits) for n_tiles tiles of T KV tiles each on `sms` SMs. A grid of n_tiles equal CTAs runs in
+// ceil(n_tiles / sms) waves; when the last wave is only partly full (rem tiles), splitting each of its tiles
+// S = floor(sms / rem) ways turns that wave into 1/S of a wave plus a small merge — at 8-way Ulysses (3 heads,
+// 330 tiles) the kernel goes from 3 waves to 2.25.
+void attention_plan(int n_tiles, int T, int sms, int mode, int* n_full, int* splits) {
+  *n_full = n_tiles;
+  *splits = 1;
+  if (mode == 0) return;
+  if (mode >= 2) {
+    const int s = mode < T ? mode : T;
+    if (s >= 2) {
+      *n_full = 0;
+      *splits = s;
+    }
+    return;
+  }
+  const int rem = n_tiles % sms;
+  if (rem == 0) return;
+  int s = sms / rem;
+  if (s > 8) s = 8;
+  if (s > T / 8) s = T / 8;  // keep at least 8 KV tiles per partial CTA
+  if (s < 2) return;
+  *n_full = n_tiles - rem;
+  *splits = s;
+}
 
 template <int HD>
 static int dispatch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
@@ -466,7 +615,6 @@ int attention_fwd_owners(const void* q, const void* k, const void* v, void* cons
                    "attention: output pointer %d null or not 16-byte aligned", g);
   FINO_CHECK_ARG(head_dim == 128 || head_dim == 64, "attention: head_dim %d unsupported (64 or 128)", head_dim);
   FINO_CHECK_ARG(batch > 0 && heads > 0 && nq > 0 && nk > 0, "attention: non-positive shape");
-  FINO_CHECK_ARG(batch <= 65535 && heads <= 65535, "attention: batch/heads exceed grid limits");
   FINO_CHECK_ARG(q_row_stride % 8 == 0 && k_row_stride % 8 == 0 && v_row_stride % 8 == 0 && o_row_stride % 8 == 0,
                  "attention: row strides must be multiples of 8 elements");
   FINO_CHECK_ARG(q_batch_stride % 8 == 0 && k_batch_stride % 8 == 0 && v_batch_stride % 8 == 0 &&
@@ -498,6 +646,19 @@ int attention_fwd_owners(const void* q, const void* k, const void* v, void* cons
   p.heads = heads;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.num_kv_tiles = (int)((nk + ATT_BN - 1) / ATT_BN);
+  p.q_tiles = (int)((nq + 2 * ATT_BM - 1) / (2 * ATT_BM));
+  FINO_CHECK_ARG((int64_t)p.q_tiles * heads * batch < (int64_t)1 << 30, "attention: too many query tiles");
+  const int n_tiles = p.q_tiles * heads * batch;
+  attention_plan(n_tiles, p.num_kv_tiles, num_sms(), g_attn_split, &p.n_full, &p.splits);
+  p.ws_o = nullptr;
+  p.ws_ml = nullptr;
+  if (p.splits > 1) {
+    const size_t prow = (size_t)(n_tiles - p.n_full) * p.splits * 2 * ATT_BM;
+    void* ws = nullptr;
+    if ((r = attn_workspace(prow * ((size_t)head_dim * 4 + 8), &ws))) return r;
+    p.ws_o = reinterpret_cast<float*>(ws);
+    p.ws_ml = reinterpret_cast<float2*>(p.ws_o + prow * head_dim);
+  }
   if (head_dim == 128) return dispatch_attn<128>(tq, tk, tv, p, batch, stream);
   return dispatch_attn<64>(tq, tk, tv, p, batch, stream);
 }

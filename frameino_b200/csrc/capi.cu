@@ -50,6 +50,8 @@ int qkv_norm_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride, con
                           cudaStream_t stream);
 void gemm_set_mode(int mode);
 void attention_set_variant(int v);
+void attention_set_split(int s);
+void attention_plan(int n_tiles, int T, int sms, int mode, int* n_full, int* splits);
 void rows_set_variant(int ln_block, int qk_block);
 void rows_set_tma(int on);
 void scatter_set_tma(int on);
@@ -186,6 +188,29 @@ int fino_attention_set_variant(int variant) {
     return fino::FINO_ERR_INVALID;
   }
   fino::attention_set_variant(variant);
+  return 0;
+}
+
+int fino_attention_set_split(int mode) {
+  if (mode < -1 || mode == 1 || mode > 64) {
+    fino::set_last_error("fino_attention_set_split: mode %d (want -1 auto, 0 off, or 2..64 forced splits)", mode);
+    return fino::FINO_ERR_INVALID;
+  }
+  fino::attention_set_split(mode);
+  return 0;
+}
+
+int fino_attention_plan(int64_t nq, int64_t nk, int heads, int batch, int sms, int mode, int* n_full, int* splits) {
+  if (nq <= 0 || nk <= 0 || heads <= 0 || batch <= 0 || sms <= 0 || !n_full || !splits) {
+    fino::set_last_error("fino_attention_plan: bad arguments");
+    return fino::FINO_ERR_INVALID;
+  }
+  const int64_t tiles = (nq + 255) / 256 * heads * batch;
+  if (tiles >= ((int64_t)1 << 30)) {
+    fino::set_last_error("fino_attention_plan: too many query tiles");
+    return fino::FINO_ERR_INVALID;
+  }
+  fino::attention_plan((int)tiles, (int)((nk + 127) / 128), sms, mode, n_full, splits);
   return 0;
 }
 

@@ -339,6 +339,22 @@ def attention_set_variant(variant: int) -> None:
     _lib.check(_lib.load().fino_attention_set_variant(variant), "fino_attention_set_variant")
 
 
+def attention_set_split(mode: int) -> None:
+    """KV split of the attention kernel's partial last wave: -1 automatic (default), 0 never, 2..64 split every tile
+    that many ways (test hook). See include/frameino_b200.h."""
+    _lib.check(_lib.load().fino_attention_set_split(int(mode)), "fino_attention_set_split")
+
+
+def attention_plan(nq: int, nk: int, heads: int, batch: int = 1, sms: int = 148, mode: int = -1):
+    """(n_full, splits) the attention launcher would use on a device with ``sms`` SMs (host arithmetic only)."""
+    import ctypes
+
+    n_full, splits = ctypes.c_int(0), ctypes.c_int(0)
+    _lib.check(_lib.load().fino_attention_plan(nq, nk, heads, batch, sms, mode, ctypes.byref(n_full),
+                                               ctypes.byref(splits)), "fino_attention_plan")
+    return n_full.value, splits.value
+
+
 def rows_set_variant(ln_block: bool, qk_block: bool) -> None:
     _lib.check(_lib.load().fino_rows_set_variant(int(ln_block), int(qk_block)), "fino_rows_set_variant")
 

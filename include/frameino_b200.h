@@ -62,6 +62,16 @@ int fino_attention_fwd(const void* q, const void* k, const void* v, void* o, int
 /* Tuning / test hook: scheduling variant of the attention kernel (0 = default; 1..5 see attention_tcgen05.cu). */
 int fino_attention_set_variant(int variant);
 
+/* Work decomposition of fino_attention_fwd. The kernel runs one CTA per 256-query-row tile of one (batch, head); when
+ * the tile count leaves a partly filled last wave on the device's SMs (8-way Ulysses: 3 heads x 110 tiles = 330 CTAs on
+ * 148 SMs), the tiles of that wave are split along the key axis into `splits` partial CTAs each (fp32 partials in a
+ * library-owned per-device workspace, merged by a small second kernel). mode: -1 = automatic (default), 0 = never,
+ * 2..64 = split EVERY tile that many ways (test hook). Calls on one device must be stream-ordered with each other. */
+int fino_attention_set_split(int mode);
+/* The decomposition fino_attention_fwd would use on a device with `sms` SMs (pure host arithmetic; no GPU needed):
+ * CTAs [0, n_full) run whole tiles, the remaining tiles run as `splits` partial CTAs each. */
+int fino_attention_plan(int64_t nq, int64_t nk, int heads, int batch, int sms, int mode, int* n_full, int* splits);
+
 /* Tuning / test hook: choose the block-per-row variants of the LayerNorm / qk-norm kernels (0 = warp-per-row). */
 int fino_rows_set_variant(int ln_block, int qk_block);
 /* Tuning / test hook: 1 = wide rows (1024 <= dim <= 4096) go through the experimental TMA-staged persistent row

@@ -132,3 +132,28 @@ def test_sequence_partition():
     assert SequenceParallel.partition(28160, 8) == (3520, 28160)
     assert SequenceParallel.partition(19126, 8) == (2391, 19128)
     assert SequenceParallel.partition(10, 4) == (3, 12)
+
+
+def test_attention_wave_plan():
+    """fino_attention_plan (host arithmetic of the attention launcher, include/frameino_b200.h): whole tiles first, the
+    partly filled last wave split along KV so that it fits the idle SMs."""
+    from frameino_b200 import ops
+
+    # config 2 on 1 / 2 GPUs: 2640 / 1320 tiles on 148 SMs -> last wave 84 % / 92 % full, no split
+    assert ops.attention_plan(28160, 28160, 24) == (2640, 1)
+    assert ops.attention_plan(28160, 28160, 12) == (1320, 1)
+    # 4-way / 8-way Ulysses: 660 = 4*148 + 68 -> 2 splits; 330 = 2*148 + 34 -> 4 splits
+    assert ops.attention_plan(28160, 28160, 6) == (592, 2)
+    assert ops.attention_plan(28160, 28160, 3) == (296, 4)
+    # cross-attention (4 KV tiles): never split; split off; forced split clamps to the KV tile count
+    assert ops.attention_plan(28160, 512, 24) == (2640, 1)
+    assert ops.attention_plan(28160, 28160, 3, mode=0) == (330, 1)
+    assert ops.attention_plan(1024, 384, 4, mode=7) == (0, 3)
+    for nq, nk, h in [(39936, 39936, 3), (19126, 19126, 48), (19126, 19126, 6), (4096, 4096, 2)]:
+        tiles = (nq + 255) // 256 * h
+        n_full, s = ops.attention_plan(nq, nk, h)
+        assert 0 <= n_full <= tiles and s >= 1
+        if s > 1:
+            assert n_full % 148 == 0 and (tiles - n_full) * s <= 148 and (nk + 127) // 128 // s >= 8
+        else:
+            assert n_full == tiles

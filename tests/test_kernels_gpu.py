@@ -191,6 +191,44 @@ def test_attention_vs_oracle(ops, hd, b, h, nq, nk):
 
 
 @pytest.mark.parametrize("hd", [128, 64])
+@pytest.mark.parametrize("splits", [2, 3, 7])
+def test_attention_kv_split_matches_oracle_and_single_pass(ops, hd, splits):
+    """The KV-split decomposition (partial CTAs + merge kernel, used for the partly filled last wave) forced on every
+    tile: ragged nq/nk, more splits than some shapes have KV tiles, peaky scores (different running maxima per split)."""
+    try:
+        for (b, h, nq, nk, scale) in [(1, 2, 300, 1000, 1.0), (2, 3, 513, 897, 2.5), (1, 1, 64, 129, 1.0)]:
+            dm = h * hd
+            q, k, v = bf(b, nq, dm, scale=scale), bf(b, nk, dm, scale=scale, seed=1), bf(b, nk, dm, seed=2)
+            ops.attention_set_split(0)
+            single = ops.attention(q.cuda(), k.cuda(), v.cuda(), h)
+            ops.attention_set_split(splits)
+            out = ops.attention(q.cuda(), k.cuda(), v.cuda(), h)
+            assert rel_err(out, _sdpa_ref(q, k, v, h)) <= BF16_TOL
+            assert rel_err(out, single.float().cpu()) <= 2.0 ** -7  # same math up to one bf16 rounding of the merge
+    finally:
+        ops.attention_set_split(-1)
+
+
+def test_attention_auto_split_on_a_partial_wave(ops):
+    """Automatic mode on a shape whose tile count leaves a partly filled last wave (the 8-way Ulysses situation)."""
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    h, hd, nk = 1, 128, 2048
+    nq = (sms + 5) * 256  # one full wave + 5 tiles
+    n_full, s = ops.attention_plan(nq, nk, h, 1, sms)
+    assert n_full == sms and s >= 2
+    q, k, v = bf(1, nq, hd), bf(1, nk, hd, seed=1), bf(1, nk, hd, seed=2)
+    out = ops.attention(q.cuda(), k.cuda(), v.cuda(), h)
+    ops.attention_set_split(0)
+    try:
+        single = ops.attention(q.cuda(), k.cuda(), v.cuda(), h)
+    finally:
+        ops.attention_set_split(-1)
+    assert torch.equal(out[:, : sms * 256], single[:, : sms * 256])  # whole tiles take the single-pass path
+    assert rel_err(out[:, sms * 256:], single[:, sms * 256:].float().cpu()) <= 2.0 ** -7
+    assert rel_err(out[:, -1500:], _sdpa_ref(q[:, -1500:].contiguous(), k, v, h)) <= BF16_TOL
+
+
+@pytest.mark.parametrize("hd", [128, 64])
 def test_attention_strided_fused_qkv_and_peaky_scores(ops, hd):
     b, h, n = 2, 3, 700
     dm = h * hd

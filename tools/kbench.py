@@ -53,6 +53,15 @@ if "attn" in which:
     q8 = qkv[..., : 3 * 384].contiguous()  # what one rank sees at P = 8: 3 heads, all tokens
     timeit(lambda: ops.attention(q8[..., :384], q8[..., 384:768], q8[..., 768:], 3), 4.0 * n8 * n8 * 384,
            name="attention d128 28160x28160 h3 (P=8 shard)")
+    q4 = qkv[..., : 3 * 768].contiguous()  # P = 4: 6 heads
+    timeit(lambda: ops.attention(q4[..., :768], q4[..., 768:1536], q4[..., 1536:], 6), 4.0 * n8 * n8 * 768,
+           name="attention d128 28160x28160 h6 (P=4 shard)")
+    ops.attention_set_split(0)
+    timeit(lambda: ops.attention(q8[..., :384], q8[..., 384:768], q8[..., 768:], 3), 4.0 * n8 * n8 * 384,
+           name="  same h3, KV split off")
+    timeit(lambda: ops.attention(q4[..., :768], q4[..., 768:1536], q4[..., 1536:], 6), 4.0 * n8 * n8 * 768,
+           name="  same h6, KV split off")
+    ops.attention_set_split(-1)
     del qkv, o
 if "attn64" in which:
     n2, h2 = 19126, 48
@@ -65,6 +74,27 @@ if "cross" in which:
     kv = torch.randn(1, 512, 2 * d, device="cuda").bfloat16()
     timeit(lambda: ops.attention(q, kv[..., :d], kv[..., d:], h), 4.0 * n * 512 * d, name="cross attention 28160x512 h24")
     del q, kv
+if "gemm8" in which:  # the per-rank GEMM shapes at 8-way sequence parallel (M = 3520)
+    m8 = n // 8
+    f = 14336
+    a = torch.randn(m8, d, device="cuda").bfloat16()
+    x = a.clone()
+    tab = torch.randn(2, 6 * d, device="cuda")
+    ridx = torch.ones(m8, device="cuda", dtype=torch.int32)
+    for (nn, kk, epi, nm) in [(3 * d, d, ops.EPI_NONE, "qkv"), (d, d, ops.EPI_GATE_RESIDUAL, "out+gate-res"),
+                              (d, d, ops.EPI_NONE, "cross-q"), (f, d, ops.EPI_GELU_TANH, "ffn-up+gelu"),
+                              (d, f, ops.EPI_GATE_RESIDUAL, "ffn-down+gate-res")]:
+        inp = a if kk == d else torch.randn(m8, kk, device="cuda").bfloat16()
+        w = (torch.randn(nn, kk, device="cuda") / math.sqrt(kk)).bfloat16()
+        b = torch.randn(nn, device="cuda").bfloat16()
+        if epi == ops.EPI_GATE_RESIDUAL:
+            fn = lambda: ops.linear(inp, w, b, epilogue=epi, residual=x, gate=tab[:, :d], row_index=ridx, out=x)  # noqa: E731
+        else:
+            out = torch.empty(m8, nn, device="cuda", dtype=torch.bfloat16)
+            fn = lambda: ops.linear(inp, w, b, epilogue=epi, out=out)  # noqa: E731
+        timeit(fn, 2.0 * m8 * nn * kk, name=f"gemm {nm} M{m8} N{nn} K{kk}")
+        del w, b
+    del a, x
 if "gemm" in which:
     a = torch.randn(n, d, device="cuda").bfloat16()
     f = 14336

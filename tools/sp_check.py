@@ -15,11 +15,17 @@ from frameino_b200.wan import WanTransformer3DModel  # noqa: E402
 
 
 def main():
-    rank = int(os.environ["RANK"])
     local = int(os.environ["LOCAL_RANK"])
-    world = int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    run_cases()
+    dist.destroy_process_group()
+
+
+def run_cases():
+    """Needs an initialised NCCL process group (also called by tools/step_breakdown.py --sp-check)."""
+    rank = dist.get_rank()
+    world = dist.get_world_size()
     results = {}
     # heads must divide by world: WAN_SMALL has 4 heads (ok for 2, 4); an 8-head variant for world 8
     cfg = dict(synth.WAN_SMALL)
@@ -49,8 +55,7 @@ def main():
     if rank == 0:
         print("SP_CHECK " + json.dumps(results))
         ok = all(e <= 2e-2 for r in results.values() for e in r["rel_err_per_rank"])
-        print("SP_CHECK_OK" if ok else "SP_CHECK_FAILED")
-    dist.destroy_process_group()
+        print("SP_CHECK_OK" if ok else "SP_CHECK_FAILED", flush=True)
 
 
 if __name__ == "__main__":
