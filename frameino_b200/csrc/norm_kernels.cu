@@ -6,6 +6,7 @@
 //   gate_residual    x + y*gate                                  reference transformer_wan.py:336,341,348
 //   qk_norm_rope     RMSNorm across heads + 3-D RoPE (Wan)       reference transformer_wan.py:64-90
 //                    per-head LayerNorm + RoPE on video tokens   reference attention_processor.py:2848-2860
+#include <algorithm>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -144,16 +145,126 @@ ln_modulate_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
   }
 }
 
+// Warp-per-row kernel, second layout (variant 3). ncu on the kernel above (profiles/r01_rows_ncu.txt): L1 63 % busy,
+// 16 warps per SM. Two causes, both addressed here:
+//   * a lane owning 8 consecutive columns reads its fp32 shift / scale values as two float4 32 bytes apart, so every
+//     warp-wide LDG.128 of the modulation tables spans 1 KB and costs 8 L1 wavefronts for 512 useful bytes. Here a
+//     lane owns 4 consecutive columns per group of 128: the bf16 row moves as 8-byte pieces (256 contiguous bytes per
+//     instruction) and the fp32 tables as 16-byte pieces (512 contiguous bytes) — every wavefront is full;
+//   * the row was held as 96 fp32 registers (128 registers per thread, 2 CTAs per SM). Here it stays packed (bf16x2,
+//     2 registers per group) and is unpacked where it is used, which fits 3 CTAs = 24 warps per SM.
+template <int GPL, bool AFFINE, bool MOD, bool STEPS>  // GPL 4-column groups per lane: dim == GPL * 128 exactly
+__global__ void __launch_bounds__(ROW_WARPS * 32, (GPL <= 24 ? 2 : 1))
+ln_modulate_kernel2(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t rows,
+                    int64_t x_stride, int64_t out_stride, float eps, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, const float* __restrict__ shift, const float* __restrict__ scale,
+                    int64_t mod_row_stride, const int32_t* __restrict__ row_index, int64_t rows_per_group) {
+  constexpr int dim = GPL * 128;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const uint2* xr = reinterpret_cast<const uint2*>(x + row * x_stride) + lane;
+  uint2 v[GPL];
+#pragma unroll
+  for (int i = 0; i < GPL; ++i)
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v[i].x), "=r"(v[i].y) : "l"(xr + i * 32));
+  int64_t grp = 0;
+  if (MOD) grp = row_index ? (int64_t)__ldg(row_index + row) : row / rows_per_group;
+  // all fp32 arithmetic below is issued as packed f32x2 operations (add/fma.rn.f32x2): half the instruction count of
+  // the scalar form — the scalar kernel was issue/latency bound (its time scales with the SM clock, not with HBM)
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < GPL; ++i) {
+    fadd2(s0, s1, s0, s1, bf16_lo_to_f32(v[i].x), bf16_hi_to_f32(v[i].x));
+    fadd2(s2, s3, s2, s3, bf16_lo_to_f32(v[i].y), bf16_hi_to_f32(v[i].y));
+  }
+  const float mean = warp_sum((s0 + s1) + (s2 + s3)) * (1.0f / (float)dim);
+  const float nmean = -mean;
+  float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < GPL; ++i) {
+    float d0, d1, d2, d3;
+    fadd2(d0, d1, bf16_lo_to_f32(v[i].x), bf16_hi_to_f32(v[i].x), nmean, nmean);
+    fadd2(d2, d3, bf16_lo_to_f32(v[i].y), bf16_hi_to_f32(v[i].y), nmean, nmean);
+    ffma2(q0, q1, d0, d1, d0, d1, q0, q1);
+    ffma2(q2, q3, d2, d3, d2, d3, q2, q3);
+  }
+  const float rstd = rsqrtf(warp_sum((q0 + q1) + (q2 + q3)) * (1.0f / (float)dim) + eps);
+  const float c0 = nmean * rstd;  // (x - mean) * rstd == fma(x, rstd, -mean * rstd) up to one fp32 rounding
+
+  const float4* sh4 = MOD ? reinterpret_cast<const float4*>(shift + grp * mod_row_stride) + lane : nullptr;
+  const float4* sc4 = MOD ? reinterpret_cast<const float4*>(scale + grp * mod_row_stride) + lane : nullptr;
+  const float4* ga4 = reinterpret_cast<const float4*>(gamma) + lane;
+  const float4* be4 = reinterpret_cast<const float4*>(beta) + lane;
+  uint2* orow = reinterpret_cast<uint2*>(out + row * out_stride) + lane;
+#pragma unroll
+  for (int i = 0; i < GPL; ++i) {
+    float y0, y1, y2, y3;
+    ffma2(y0, y1, bf16_lo_to_f32(v[i].x), bf16_hi_to_f32(v[i].x), rstd, rstd, c0, c0);
+    ffma2(y2, y3, bf16_lo_to_f32(v[i].y), bf16_hi_to_f32(v[i].y), rstd, rstd, c0, c0);
+    if (AFFINE) {
+      const float4 a = __ldg(ga4 + i * 32);
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (beta != nullptr) b = __ldg(be4 + i * 32);
+      ffma2(y0, y1, y0, y1, a.x, a.y, b.x, b.y);
+      ffma2(y2, y3, y2, y3, a.z, a.w, b.z, b.w);
+    }
+    if (MOD) {
+      const float4 s4 = __ldg(sc4 + i * 32);
+      const float4 h4 = __ldg(sh4 + i * 32);
+      float t0, t1, t2, t3;
+      fadd2(t0, t1, s4.x, s4.y, 1.0f, 1.0f);
+      fadd2(t2, t3, s4.z, s4.w, 1.0f, 1.0f);
+      if (STEPS) {
+        y0 = rbf(rbf(y0) * rbf(t0)) + h4.x;
+        y1 = rbf(rbf(y1) * rbf(t1)) + h4.y;
+        y2 = rbf(rbf(y2) * rbf(t2)) + h4.z;
+        y3 = rbf(rbf(y3) * rbf(t3)) + h4.w;
+      } else {
+        ffma2(y0, y1, y0, y1, t0, t1, h4.x, h4.y);
+        ffma2(y2, y3, y2, y3, t2, t3, h4.z, h4.w);
+      }
+    }
+    orow[i * 32] = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+  }
+}
+
+template <int GPL>
+static void launch_ln2(dim3 grid, cudaStream_t stream, bool aff, bool mod, bool steps, const void* x, void* out,
+                       int64_t rows, int64_t x_stride, int64_t out_stride, float eps, const float* gamma,
+                       const float* beta, const float* shift, const float* scale, int64_t mod_row_stride,
+                       const int32_t* row_index, int64_t rows_per_group) {
+#define LN2(A, M, S)                                                                                             \
+  ln_modulate_kernel2<GPL, A, M, S><<<grid, ROW_WARPS * 32, 0, stream>>>(                                        \
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)out, rows, x_stride, out_stride, eps, gamma, beta, shift, scale,  \
+      mod_row_stride, row_index, rows_per_group)
+  if (!mod) {
+    if (aff) LN2(true, false, false);
+    else LN2(false, false, false);
+  } else if (steps) {
+    if (aff) LN2(true, true, true);
+    else LN2(false, true, true);
+  } else {
+    if (aff) LN2(true, true, false);
+    else LN2(false, true, false);
+  }
+#undef LN2
+}
+
 // Block-per-row variant for wide rows: thread c owns 16-byte chunk c of every row the CTA processes, so the LayerNorm
 // affine and the AdaLN shift / scale values for its 8 columns stay in REGISTERS across rows and are re-read only when
 // the modulation row changes (with the warp-per-row kernel every row pulled 24 KB of fp32 modulation through L1 for
 // 12 KB of activation traffic, and L1 bandwidth, not HBM, set the pace: profiles/r01_rows_ncu.txt).
 constexpr int LN_ROWS_PER_BLOCK = 16;
-static bool g_ln_block_kernel = false;  // measured 2.4 TB/s vs 3.6 TB/s for the warp-per-row kernel (r01)
-static bool g_qk_block_kernel = true;
+// LayerNorm variant: 0 = warp per row, 1 = block per row one row at a time (2.4 TB/s vs 3.6 TB/s for the warp kernel,
+// r01), 2 = batched block-per-row kernel (ln_rows_kernel; 1.3-1.6 TB/s, kept as a measured dead end), 3 = packed
+// warp-per-row kernel (ln_modulate_kernel2; 5.3-5.9 TB/s, the default for dim 1024/2048/3072/4096/5120)
+static int g_ln_block_kernel = 3;
+// q/k norm variant: 0 = warp per row, 1 = block per token, 2 = packed warp per row (qk_rms_rope_kernel2)
+static int g_qk_block_kernel = 2;
 void rows_set_variant(int ln_block, int qk_block) {
-  g_ln_block_kernel = ln_block != 0;
-  g_qk_block_kernel = qk_block != 0;
+  g_ln_block_kernel = ln_block;
+  g_qk_block_kernel = qk_block;
 }
 
 __global__ void __launch_bounds__(1024)
@@ -244,6 +355,183 @@ ln_modulate_block_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __r
   }
 }
 
+// Batched block-per-row kernel (the default for wide rows). Same ownership as above — thread c owns 16-byte chunk c of
+// every row, so the affine / modulation values of its 8 columns live in registers — but built around the two things
+// that held the one-row-at-a-time version at 2.4 TB/s:
+//   * bytes in flight: R rows are processed per iteration and the NEXT R rows are already being fetched (64 B per
+//     thread outstanding; 2 CTAs x 384 threads per SM = 48 KB per SM, enough to cover HBM latency at the read rate a
+//     read+write stream needs);
+//   * barriers: one __syncthreads per R rows. Each warp reduces its own 256 elements to (sum, M2 about the warp mean)
+//     with shuffles and the CTA combines the per-warp pairs with Chan's parallel-variance formula
+//     (M2 = sum M2_w + sum n_w (mean_w - mean)^2) — as accurate as the two-pass form, one block-wide exchange.
+// The reduction scratch is double buffered, so iteration i+1 may write while a slow warp still reads iteration i.
+constexpr int LN3_R = 4;
+constexpr int LN3_MAX_THREADS = 384;  // dim <= 3072
+
+template <bool AFFINE, bool MOD>
+__global__ void __launch_bounds__(LN3_MAX_THREADS, 2)
+ln_rows_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t rows, int dim,
+               int64_t x_stride, int64_t out_stride, float eps, const float* __restrict__ gamma,
+               const float* __restrict__ beta, const float* __restrict__ shift, const float* __restrict__ scale,
+               int64_t mod_row_stride, const int32_t* __restrict__ row_index, int64_t rows_per_group, int flags,
+               int rows_per_cta) {
+  constexpr int R = LN3_R;
+  __shared__ __align__(16) float2 red[2][R][LN3_MAX_THREADS / 32];
+  const int c = threadIdx.x;
+  const int lane = c & 31, warp = c >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int nchunks = dim >> 3;
+  const bool active = c < nchunks;
+  const bool steps = (flags & LN_FLAG_BF16_STEPS) != 0;
+  const float inv_dim = 1.0f / (float)dim;
+  // elements held by this warp (the last warp of a row may be partial)
+  const int n_mine = 8 * max(0, min(32, nchunks - 32 * warp));
+  const float inv_n_mine = n_mine > 0 ? 1.0f / (float)n_mine : 0.f;
+  const float n_last = (float)(8 * (nchunks - 32 * (nwarps - 1)));  // elements of the row's last warp
+  const float inv_n_last = 1.0f / n_last;
+
+  float g8[8], b8[8], sc8[8], sh8[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    g8[e] = 1.f;
+    b8[e] = 0.f;
+    sc8[e] = 1.f;  // holds 1 + scale
+    sh8[e] = 0.f;
+  }
+  if (AFFINE && active) {
+    ld8f(gamma + c * 8, g8);
+    if (beta != nullptr) ld8f(beta + c * 8, b8);
+  }
+  int64_t cached_g = -1;
+
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = min(rows, r0 + (int64_t)rows_per_cta);
+  uint4 nxt[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    nxt[r] = make_uint4(0, 0, 0, 0);
+    if (active && r0 + r < r1) nxt[r] = ld_stream(reinterpret_cast<const uint4*>(x + (r0 + r) * x_stride) + c);
+  }
+  int it = 0;
+  for (int64_t base = r0; base < r1; base += R, ++it) {
+    uint4 cur[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) cur[r] = nxt[r];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {  // prefetch the next batch
+      nxt[r] = make_uint4(0, 0, 0, 0);
+      const int64_t row = base + R + r;
+      if (active && row < r1) nxt[r] = ld_stream(reinterpret_cast<const uint4*>(x + row * x_stride) + c);
+    }
+    int gi[R];
+    if (MOD) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int64_t row = min(base + r, r1 - 1);
+        gi[r] = row_index ? __ldg(row_index + row) : (int)(row / rows_per_group);
+      }
+    }
+    // per-warp (sum, M2)
+    float s[R], m2[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float v[8];
+      unpack8(cur[r], v);
+      float a = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a += v[e];
+      s[r] = a;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) s[r] = warp_sum(s[r]);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      float v[8];
+      unpack8(cur[r], v);
+      const float mw = s[r] * inv_n_mine;
+      float a = 0.f;
+      if (active) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float d = v[e] - mw;
+          a += d * d;
+        }
+      }
+      m2[r] = a;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) m2[r] = warp_sum(m2[r]);
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) red[it & 1][r][warp] = make_float2(s[r], m2[r]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int64_t row = base + r;
+      if (row >= r1) break;  // block-uniform
+      // every thread combines the per-warp pairs itself (broadcast shared-memory reads, no second barrier)
+      constexpr int MAXW = LN3_MAX_THREADS / 32;
+      const float4* rp = reinterpret_cast<const float4*>(&red[it & 1][r][0]);
+      float tot = 0.f;
+#pragma unroll
+      for (int w = 0; w < MAXW; w += 2) {
+        const float4 t = rp[w >> 1];
+        if (w < nwarps) tot += t.x;
+        if (w + 1 < nwarps) tot += t.z;
+      }
+      const float mean = tot * inv_dim;
+      float m2t = 0.f;
+#pragma unroll
+      for (int w = 0; w < MAXW; w += 2) {  // second read of the pairs instead of 24 live registers
+        const float4 t = rp[w >> 1];
+        if (w < nwarps) {
+          const bool last = w == nwarps - 1;
+          const float dm = t.x * (last ? inv_n_last : (1.0f / 256.0f)) - mean;
+          m2t += t.y + (last ? n_last : 256.0f) * dm * dm;
+        }
+        if (w + 1 < nwarps) {
+          const bool last = w + 1 == nwarps - 1;
+          const float dm = t.z * (last ? inv_n_last : (1.0f / 256.0f)) - mean;
+          m2t += t.w + (last ? n_last : 256.0f) * dm * dm;
+        }
+      }
+      const float rstd = rsqrtf(m2t * inv_dim + eps);
+      if (MOD) {
+        if ((int64_t)gi[r] != cached_g) {  // block-uniform
+          cached_g = gi[r];
+          if (active) {
+            ld8f(scale + cached_g * mod_row_stride + c * 8, sc8);
+            ld8f(shift + cached_g * mod_row_stride + c * 8, sh8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sc8[e] = 1.0f + sc8[e];
+          }
+        }
+      }
+      if (active) {
+        float v[8], y[8];
+        unpack8(cur[r], v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) y[e] = (v[e] - mean) * rstd;
+        if (AFFINE) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) y[e] = y[e] * g8[e] + b8[e];
+        }
+        if (MOD) {
+          if (steps) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) y[e] = rbf(rbf(y[e]) * rbf(sc8[e])) + sh8[e];
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) y[e] = y[e] * sc8[e] + sh8[e];
+          }
+        }
+        reinterpret_cast<uint4*>(out + row * out_stride)[c] = pack8(y);
+      }
+    }
+  }
+}
+
 int ln_modulate_tma(const void* x, void* out, int64_t rows, int dim, int64_t x_stride, int64_t out_stride, float eps,
                     const float* gamma, const float* beta, const float* shift, const float* scale,
                     int64_t mod_row_stride, const int32_t* row_index, int64_t rows_per_group, int flags,
@@ -271,12 +559,47 @@ int ln_modulate(const void* x, void* out, int64_t rows, int dim, int64_t x_strid
   const int cpl = (dim / 8 + 31) / 32;
   dim3 grid((unsigned)((rows + ROW_WARPS - 1) / ROW_WARPS));
   if (rows_per_group <= 0) rows_per_group = (int64_t)1 << 62;
-  if (g_ln_block_kernel && dim >= 1024 && rows >= 64) {  // experimental block-per-row kernel (slower today)
+  if (g_ln_block_kernel == 2 && dim >= 1024 && dim <= 8 * LN3_MAX_THREADS && rows >= 64) {
+    // ~2 CTAs per SM, each walking a contiguous run of rows (a multiple of the batch size R)
+    const int threads = ((dim / 8 + 31) / 32) * 32;
+    const int64_t want_ctas = (int64_t)num_sms() * 2;
+    int64_t per = (rows + want_ctas - 1) / want_ctas;
+    per = (per + LN3_R - 1) / LN3_R * LN3_R;
+    const unsigned ctas = (unsigned)((rows + per - 1) / per);
+#define LAUNCH_LN3(A, M)                                                                                          \
+  ln_rows_kernel<A, M><<<ctas, threads, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, rows, dim,     \
+                                                     x_stride, out_stride, eps, gamma, beta, shift, scale,        \
+                                                     mod_row_stride, row_index, rows_per_group, flags, (int)per)
+    const bool aff = gamma != nullptr, mod = shift != nullptr;
+    if (aff && mod) LAUNCH_LN3(true, true);
+    else if (aff) LAUNCH_LN3(true, false);
+    else if (mod) LAUNCH_LN3(false, true);
+    else LAUNCH_LN3(false, false);
+#undef LAUNCH_LN3
+    FINO_CHECK_CUDA(cudaGetLastError());
+    return FINO_OK;
+  }
+  if (g_ln_block_kernel == 1 && dim >= 1024 && rows >= 64) {  // experimental block-per-row kernel (slower today)
     const int threads = ((dim / 8 + 31) / 32) * 32;
     dim3 bgrid((unsigned)((rows + LN_ROWS_PER_BLOCK - 1) / LN_ROWS_PER_BLOCK));
     ln_modulate_block_kernel<<<bgrid, threads, 0, stream>>>(
         (const __nv_bfloat16*)x, (__nv_bfloat16*)out, rows, dim, x_stride, out_stride, eps, gamma, beta, shift, scale,
         mod_row_stride, row_index, rows_per_group, flags);
+    FINO_CHECK_CUDA(cudaGetLastError());
+    return FINO_OK;
+  }
+  if (g_ln_block_kernel == 3 && (dim == 1024 || dim == 2048 || dim == 3072 || dim == 4096 || dim == 5120)) {
+    const bool aff = gamma != nullptr, mod = shift != nullptr, steps = (flags & LN_FLAG_BF16_STEPS) != 0;
+#define LN2_ARGS grid, stream, aff, mod, steps, x, out, rows, x_stride, out_stride, eps, gamma, beta, shift, scale, \
+                 mod_row_stride, row_index, rows_per_group
+    switch (dim / 128) {
+      case 8: launch_ln2<8>(LN2_ARGS); break;
+      case 16: launch_ln2<16>(LN2_ARGS); break;
+      case 24: launch_ln2<24>(LN2_ARGS); break;
+      case 32: launch_ln2<32>(LN2_ARGS); break;
+      default: launch_ln2<40>(LN2_ARGS); break;
+    }
+#undef LN2_ARGS
     FINO_CHECK_CUDA(cudaGetLastError());
     return FINO_OK;
   }
@@ -498,6 +821,76 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) qk_norm_rope_kernel(const QkPa
   }
 }
 
+// Warp-per-row RMSNorm-across-heads (+ Wan RoPE) in the 4-column-group layout with packed f32x2 arithmetic (see
+// ln_modulate_kernel2): dim == GPL * 128. With head_dim == 128 a lane's 4 columns sit at the same position of every
+// head, so ONE float4 of cos and one of sin per token serve all heads of the row. Even CTAs take tensor 0 (q), odd
+// CTAs tensor 1 (k), so the q and k rows of a token run side by side and share the cos/sin lines in L2.
+// Cast points as in qk_norm_rope_kernel: fp32 rsqrt -> bf16 -> x weight (bf16 product) -> fp32 rotate (separate,
+// unfused multiplies and adds, like the reference's elementwise ops) -> bf16.
+template <int GPL, bool ROPE>
+__global__ void __launch_bounds__(ROW_WARPS * 32, (GPL <= 24 ? 2 : 1)) qk_rms_rope_kernel2(const QkParams p) {
+  constexpr int dim = GPL * 128;
+  const int lane = threadIdx.x & 31;
+  const int which = blockIdx.x & 1;
+  const QkTensor& t = p.t[which];
+  const int64_t row = (int64_t)(blockIdx.x >> 1) * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= t.rows) return;
+  uint2* xr = reinterpret_cast<uint2*>(t.ptr + row * t.row_stride) + lane;
+  uint2 v[GPL];
+#pragma unroll
+  for (int i = 0; i < GPL; ++i) v[i] = xr[i * 32];
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), sn = cs;
+  bool do_rope = false;
+  if (ROPE) {
+    const int64_t s_in_seq = row % p.seq_len;
+    do_rope = t.rope && s_in_seq >= p.rope_skip;
+    if (do_rope) {
+      cs = __ldg(reinterpret_cast<const float4*>(p.cos + (s_in_seq - p.rope_skip) * 128) + lane);
+      sn = __ldg(reinterpret_cast<const float4*>(p.sin + (s_in_seq - p.rope_skip) * 128) + lane);
+    }
+  }
+  float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < GPL; ++i) {
+    const float a0 = bf16_lo_to_f32(v[i].x), a1 = bf16_hi_to_f32(v[i].x);
+    const float a2 = bf16_lo_to_f32(v[i].y), a3 = bf16_hi_to_f32(v[i].y);
+    ffma2(q0, q1, a0, a1, a0, a1, q0, q1);
+    ffma2(q2, q3, a2, a3, a2, a3, q2, q3);
+  }
+  const float rstd = rsqrtf(warp_sum((q0 + q1) + (q2 + q3)) * (1.0f / (float)dim) + p.eps);
+  const uint2* wr = reinterpret_cast<const uint2*>(t.weight) + lane;
+  // rotation coefficients of this lane's two pairs: (x1, x2) -> (x1 c - x2 s, x2 c + x1 s), c = cos[even], s = sin[odd]
+  const float c01 = cs.x, s01 = sn.y, c23 = cs.z, s23 = sn.w;
+#pragma unroll
+  for (int i = 0; i < GPL; ++i) {
+    float a0, a1, a2, a3;
+    fmul2(a0, a1, bf16_lo_to_f32(v[i].x), bf16_hi_to_f32(v[i].x), rstd, rstd);
+    fmul2(a2, a3, bf16_lo_to_f32(v[i].y), bf16_hi_to_f32(v[i].y), rstd, rstd);
+    uint32_t n01 = pack_bf16x2(a0, a1), n23 = pack_bf16x2(a2, a3);  // .to(bf16)
+    if (t.weight != nullptr) {
+      const uint2 w = __ldg(wr + i * 32);
+      fmul2(a0, a1, bf16_lo_to_f32(n01), bf16_hi_to_f32(n01), bf16_lo_to_f32(w.x), bf16_hi_to_f32(w.x));
+      fmul2(a2, a3, bf16_lo_to_f32(n23), bf16_hi_to_f32(n23), bf16_lo_to_f32(w.y), bf16_hi_to_f32(w.y));
+      n01 = pack_bf16x2(a0, a1);  // bf16 * bf16 product rounded to bf16
+      n23 = pack_bf16x2(a2, a3);
+    }
+    if (ROPE && do_rope) {
+      const float x0 = bf16_lo_to_f32(n01), x1 = bf16_hi_to_f32(n01);
+      const float x2 = bf16_lo_to_f32(n23), x3 = bf16_hi_to_f32(n23);
+      float pa, pb, ra, rb, o0, o1, o2, o3;
+      fmul2(pa, pb, x0, x1, c01, c01);    // (x1 c, x2 c)
+      fmul2(ra, rb, x1, x0, -s01, s01);   // (-(x2 s), x1 s): the sign folds into the exact product
+      fadd2(o0, o1, pa, pb, ra, rb);
+      fmul2(pa, pb, x2, x3, c23, c23);
+      fmul2(ra, rb, x3, x2, -s23, s23);
+      fadd2(o2, o3, pa, pb, ra, rb);
+      n01 = pack_bf16x2(o0, o1);
+      n23 = pack_bf16x2(o2, o3);
+    }
+    xr[i * 32] = make_uint2(n01, n23);
+  }
+}
+
 // Block-per-token variant of the RMS-across-heads path (Wan self-attention): thread c owns 16-byte chunk c of the q
 // row AND of the k row of each token the CTA processes. The RMSNorm weights of its 8 columns live in registers for
 // the whole CTA, the cos/sin values of the token are fetched once and used for both q and k, and the two
@@ -655,7 +1048,25 @@ int qk_norm_rope(void* x0, int64_t rows0, int64_t stride0, const void* w0, const
   p.rope_skip = rope_skip;
   p.blocks0 = (rows0 + ROW_WARPS - 1) / ROW_WARPS;
   const int64_t blocks1 = x1 ? (rows1 + ROW_WARPS - 1) / ROW_WARPS : 0;
-  if (g_qk_block_kernel && norm_mode == QK_RMS_ACROSS_HEADS && x1 != nullptr && rows0 == rows1 && rows0 >= 64 && dim >= 1024 && dim <= 4096 &&
+  // packed warp-per-row kernel: RMS across heads, dim 3072 / 5120, head_dim 128 when rotating, no bias, row strides
+  // that keep the 8-byte pieces aligned (always true: strides are multiples of 8 elements)
+  if (g_qk_block_kernel == 2 && norm_mode == QK_RMS_ACROSS_HEADS && (dim == 3072 || dim == 5120) && b0 == nullptr &&
+      b1 == nullptr && rope_skip == 0 && (p.rope_mode == ROPE_NONE || (p.rope_mode == ROPE_WAN && head_dim == 128))) {
+    const int64_t nb = std::max(p.blocks0, blocks1);
+    dim3 g2((unsigned)(2 * nb));
+    if (x1 == nullptr) p.t[1].rows = 0;
+    const bool rope = p.rope_mode == ROPE_WAN;
+    if (dim == 3072) {
+      if (rope) qk_rms_rope_kernel2<24, true><<<g2, ROW_WARPS * 32, 0, stream>>>(p);
+      else qk_rms_rope_kernel2<24, false><<<g2, ROW_WARPS * 32, 0, stream>>>(p);
+    } else {
+      if (rope) qk_rms_rope_kernel2<40, true><<<g2, ROW_WARPS * 32, 0, stream>>>(p);
+      else qk_rms_rope_kernel2<40, false><<<g2, ROW_WARPS * 32, 0, stream>>>(p);
+    }
+    FINO_CHECK_CUDA(cudaGetLastError());
+    return FINO_OK;
+  }
+  if (g_qk_block_kernel == 1 && norm_mode == QK_RMS_ACROSS_HEADS && x1 != nullptr && rows0 == rows1 && rows0 >= 64 && dim >= 1024 && dim <= 4096 &&
       (p.rope_mode == ROPE_NONE || (rope0 && rope1))) {
     const int threads = ((dim / 8 + 31) / 32) * 32;
     dim3 bgrid((unsigned)((rows0 + QK_TOKENS_PER_BLOCK - 1) / QK_TOKENS_PER_BLOCK));

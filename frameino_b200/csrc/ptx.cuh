@@ -519,6 +519,17 @@ __device__ __forceinline__ void fadd2(float& d0, float& d1, float a0, float a1, 
       : "=f"(d0), "=f"(d1)
       : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
+__device__ __forceinline__ void fmul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t"
+      ".reg .b64 ra, rb, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %5};\n\t"
+      "mul.rn.f32x2 rd, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t"
+      "}\n"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
 // 2^x for two values on the FMA/ALU pipes (no MUFU): Cody-Waite split x = n + f with the round-to-minus-infinity
 // magic-add trick, cubic minimax polynomial for 2^f on [0,1) (max rel. error ~9e-5, far below bf16's 3.9e-3), and the
 // integer n added straight into the exponent field. x is clamped to >= -126 (so -inf gives ~1e-38, not NaN).

@@ -355,7 +355,9 @@ def attention_plan(nq: int, nk: int, heads: int, batch: int = 1, sms: int = 148,
     return n_full.value, splits.value
 
 
-def rows_set_variant(ln_block: bool, qk_block: bool) -> None:
+def rows_set_variant(ln_block: int, qk_block: int) -> None:
+    """LayerNorm kernel: 0 warp per row, 1 block per row (one row at a time), 2 batched block per row (default for
+    1024 <= dim <= 3072). q/k kernel: 0 warp per row, 1 block per token (default)."""
     _lib.check(_lib.load().fino_rows_set_variant(int(ln_block), int(qk_block)), "fino_rows_set_variant")
 
 

@@ -72,7 +72,8 @@ int fino_attention_set_split(int mode);
  * CTAs [0, n_full) run whole tiles, the remaining tiles run as `splits` partial CTAs each. */
 int fino_attention_plan(int64_t nq, int64_t nk, int heads, int batch, int sms, int mode, int* n_full, int* splits);
 
-/* Tuning / test hook: choose the block-per-row variants of the LayerNorm / qk-norm kernels (0 = warp-per-row). */
+/* Tuning / test hook: LayerNorm kernel 0 = warp per row, 1 = block per row, 2 = batched block per row (default for
+ * 1024 <= dim <= 3072); q/k-norm kernel 0 = warp per row, 1 = block per token (default). */
 int fino_rows_set_variant(int ln_block, int qk_block);
 /* Tuning / test hook: 1 = wide rows (1024 <= dim <= 4096) go through the experimental TMA-staged persistent row
  * kernels (bulk async copies through a shared-memory ring); 0 (default) = the register-resident row kernels. */

@@ -53,6 +53,43 @@ def test_ln_modulate_vs_oracle(ops, rows, dim):
     assert rel_err(out3, ref3) <= BF16_TOL
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("rows,dim", [(64, 1024), (1003, 3072), (4099, 3072), (777, 1160), (130, 5120), (70, 2048)])
+def test_ln_kernel_variants_vs_oracle(ops, variant, rows, dim):
+    """Each LayerNorm kernel (warp per row / block per row / batched block per row with the per-warp (sum, M2)
+    combine) against the fp32 oracle: ragged row counts, a partial last warp (dim 1160), strided input, row groups
+    that change inside a batch of rows."""
+    from oracle.wan_oracle import fp32_layer_norm
+
+    x = bf(rows, dim + 64, scale=2.0)
+    x[:, 32:] += 3.0  # non-zero mean: the variance must not be computed as E[x^2] - mean^2
+    xs = x.cuda()[:, 32:32 + dim]
+    xf = x[:, 32:32 + dim].float()
+    tab = torch.randn(3, 6 * dim, generator=torch.Generator().manual_seed(1)) * 0.5
+    ridx = torch.randint(0, 3, (rows,), generator=torch.Generator().manual_seed(2)).int()
+    shift, scale = tab[:, :dim], tab[:, dim:2 * dim]
+    g, b = torch.randn(dim), torch.randn(dim)
+    tc = tab.cuda()
+    ops.rows_set_variant(variant, 2)
+    try:
+        out = ops.ln_modulate(xs, 1e-6, shift=tc[:, :dim], scale=tc[:, dim:2 * dim], row_index=ridx.cuda())
+        ref = (fp32_layer_norm(xf, None, None, 1e-6) * (1 + scale[ridx.long()]) + shift[ridx.long()]).bfloat16()
+        assert rel_err(out, ref) <= BF16_TOL
+        out = ops.ln_modulate(xs, 1e-6, gamma=g.cuda(), beta=b.cuda())
+        assert rel_err(out, fp32_layer_norm(xf, g, b, 1e-6).bfloat16()) <= BF16_TOL
+        out = ops.ln_modulate(xs, 1e-6)
+        assert rel_err(out, fp32_layer_norm(xf, None, None, 1e-6).bfloat16()) <= BF16_TOL
+        per = 333
+        gi = (torch.arange(rows) // per).long() % 3
+        if rows <= 3 * per:
+            out = ops.ln_modulate(xs, 1e-6, gamma=g.cuda(), beta=b.cuda(), shift=tc[:, :dim], scale=tc[:, dim:2 * dim],
+                                  rows_per_group=per)
+            ref = (fp32_layer_norm(xf, g, b, 1e-6) * (1 + scale[gi]) + shift[gi]).bfloat16()
+            assert rel_err(out, ref) <= BF16_TOL
+    finally:
+        ops.rows_set_variant(3, 2)
+
+
 def test_ln_bf16_module_flow_vs_torch(ops):
     """CogVideoXLayerNormZero body: bf16 LayerNorm, then bf16 (1+scale) multiply and shift add."""
     rows, dim = 300, 3072
@@ -76,10 +113,14 @@ def test_gate_residual(ops):
     assert rel_err(ops.gate_residual(x.cuda(), y.cuda()), x + y) <= BF16_TOL
 
 
-@pytest.mark.parametrize("b,n,h,d", [(1, 384, 8, 32), (2, 300, 24, 128), (1, 77, 4, 128)])
-def test_qk_rmsnorm_rope_vs_oracle(ops, b, n, h, d):
+@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("b,n,h,d", [(1, 384, 8, 32), (2, 300, 24, 128), (1, 77, 4, 128), (1, 45, 40, 128)])
+def test_qk_rmsnorm_rope_vs_oracle(ops, variant, b, n, h, d, request):
     from oracle.wan_oracle import apply_wan_rope, rms_norm
 
+    # q/k kernel variants: warp per row, block per token, packed warp per row (the default at dim 3072 / 5120)
+    ops.rows_set_variant(3, variant)
+    request.addfinalizer(lambda: ops.rows_set_variant(3, 2))
     dm = h * d
     qkv = bf(b, n, 3 * dm)
     wq, wk = (1 + 0.1 * torch.randn(dm)).bfloat16(), (1 + 0.1 * torch.randn(dm)).bfloat16()

@@ -122,17 +122,26 @@ if "rows" in which:
     ridx = torch.zeros(n, device="cuda", dtype=torch.int32)
     ridx[880:] = 1
     o = torch.empty_like(x)
-    timeit(lambda: ops.ln_modulate(x, 1e-6, shift=tab[:, :d], scale=tab[:, d:2 * d], row_index=ridx, out=o),
-           bytes_=2.0 * n * d * 2, name="ln_modulate 28160x3072")
     g, b = torch.randn(d, device="cuda"), torch.randn(d, device="cuda")
-    timeit(lambda: ops.ln_modulate(x, 1e-6, gamma=g, beta=b, out=o), bytes_=2.0 * n * d * 2,
-           name="ln affine 28160x3072")
+    for variant in (0, 3):
+        ops.rows_set_variant(variant, 2)
+        timeit(lambda: ops.ln_modulate(x, 1e-6, shift=tab[:, :d], scale=tab[:, d:2 * d], row_index=ridx, out=o),
+               bytes_=2.0 * n * d * 2, name=f"ln_modulate 28160x3072 (variant {variant})")
+        timeit(lambda: ops.ln_modulate(x, 1e-6, gamma=g, beta=b, out=o), bytes_=2.0 * n * d * 2,
+               name=f"ln affine 28160x3072 (variant {variant})")
+        x8 = x[:3520]
+        timeit(lambda: ops.ln_modulate(x8, 1e-6, shift=tab[:, :d], scale=tab[:, d:2 * d], row_index=ridx[:3520],
+                                       out=o[:3520]), bytes_=2.0 * 3520 * d * 2,
+               name=f"ln_modulate 3520x3072 (variant {variant})")
     qkv = torch.randn(1, n, 3 * d, device="cuda").bfloat16()
     wq = torch.ones(d, device="cuda").bfloat16()
     cos = torch.rand(n, hd, device="cuda")
     sin = torch.rand(n, hd, device="cuda")
-    timeit(lambda: ops.qk_norm_rope(qkv[..., :d], wq, qkv[..., d:2 * d], wq, h, rope_mode=ops.ROPE_WAN, cos=cos,
-                                    sin=sin, seq_len=n), bytes_=4.0 * n * d * 2 + 2.0 * n * hd * 4,
-           name="qk_norm_rope 28160x(2x3072)")
-    timeit(lambda: ops.qk_norm_rope(x, wq, None, None, h), bytes_=2.0 * n * d * 2, name="q_norm (cross) 28160x3072")
+    for variant in (1, 2):
+        ops.rows_set_variant(3, variant)
+        timeit(lambda: ops.qk_norm_rope(qkv[..., :d], wq, qkv[..., d:2 * d], wq, h, rope_mode=ops.ROPE_WAN, cos=cos,
+                                        sin=sin, seq_len=n), bytes_=4.0 * n * d * 2 + 2.0 * n * hd * 4,
+               name=f"qk_norm_rope 28160x(2x3072) (variant {variant})")
+        timeit(lambda: ops.qk_norm_rope(x, wq, None, None, h), bytes_=2.0 * n * d * 2,
+               name=f"q_norm (cross) 28160x3072 (variant {variant})")
 print("done", which)
