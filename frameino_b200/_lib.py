@@ -70,6 +70,12 @@ def load() -> ctypes.CDLL:
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    # tuning hooks for A/B runs of a whole step (tools/step_breakdown.py, bench.py): same effect as the setters in ops
+    for env, fn in (("FINO_ATTN_VARIANT", lib.fino_attention_set_variant), ("FINO_ATTN_SPLIT", lib.fino_attention_set_split),
+                    ("FINO_GEMM_MODE", lib.fino_gemm_set_mode)):
+        if os.environ.get(env):
+            if fn(int(os.environ[env])) != 0:
+                raise RuntimeError(f"{env}={os.environ[env]}: {lib.fino_last_error().decode()}")
     return lib
 
 

@@ -55,6 +55,7 @@ void attention_plan(int n_tiles, int T, int sms, int mode, int* n_full, int* spl
 void rows_set_variant(int ln_block, int qk_block);
 void rows_set_tma(int on);
 void scatter_set_tma(int on);
+void scatter_set_packed(int on);
 }  // namespace fino
 
 static std::atomic<int64_t> g_launches{0};
@@ -216,6 +217,7 @@ int fino_attention_plan(int64_t nq, int64_t nk, int heads, int batch, int sms, i
 
 int fino_rows_set_variant(int ln_block, int qk_block) {
   fino::rows_set_variant(ln_block, qk_block);
+  fino::scatter_set_packed(qk_block == 2);
   return 0;
 }
 

@@ -258,13 +258,95 @@ __global__ void __launch_bounds__(512) qkv_norm_rope_scatter_kernel(const __grid
   }
 }
 
+// Packed warp-per-row form of the kernel above (see ln_modulate_kernel2 / qk_rms_rope_kernel2 in norm_kernels.cu for
+// the layout): head_dim == 128, GPL == heads, HPR == heads per rank. A lane owns 4 columns of every head, so group i
+// of a row IS head i: its destination rank (i / HPR) and column inside that rank's buffer are compile-time constants
+// after unrolling, one float4 of cos / sin per token serves all heads, and each warp-wide store writes one head's 256
+// contiguous bytes into the owner's buffer. CTA x handles q (x % 3 == 0), k (1) or v (2, a plain copy) rows.
+template <int GPL, int HPR>
+__global__ void __launch_bounds__(256, (GPL <= 24 ? 2 : 1))
+qkv_norm_rope_scatter_kernel2(const __grid_constant__ ScatterParams p) {
+  constexpr int dim = GPL * 128;
+  constexpr int inner = HPR * 128;
+  const int lane = threadIdx.x & 31;
+  const int which = blockIdx.x % 3;
+  const int64_t row = (int64_t)(blockIdx.x / 3) * 8 + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const uint2* src = reinterpret_cast<const uint2*>(p.qkv + row * p.row_stride + which * dim) + lane;
+  uint2 v[GPL];
+#pragma unroll
+  for (int i = 0; i < GPL; ++i)
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v[i].x), "=r"(v[i].y) : "l"(src + i * 32));
+  const int64_t drow_off = ((int64_t)p.rank * p.rows_per_rank + row) * p.dst_row_stride + which * inner + lane * 4;
+  if (which == 2) {
+#pragma unroll
+    for (int i = 0; i < GPL; ++i)
+      *reinterpret_cast<uint2*>(p.dst[i / HPR] + drow_off + (i % HPR) * 128) = v[i];
+    return;
+  }
+  const bool rope = p.cos != nullptr;
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), sn = cs;
+  if (rope) {
+    cs = __ldg(reinterpret_cast<const float4*>(p.cos + row * 128) + lane);
+    sn = __ldg(reinterpret_cast<const float4*>(p.sin + row * 128) + lane);
+  }
+  float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+  for (int i = 0; i < GPL; ++i) {
+    const float a0 = bf16_lo_to_f32(v[i].x), a1 = bf16_hi_to_f32(v[i].x);
+    const float a2 = bf16_lo_to_f32(v[i].y), a3 = bf16_hi_to_f32(v[i].y);
+    ffma2(q0, q1, a0, a1, a0, a1, q0, q1);
+    ffma2(q2, q3, a2, a3, a2, a3, q2, q3);
+  }
+  const float rstd = rsqrtf(warp_sum_f((q0 + q1) + (q2 + q3)) * (1.0f / (float)dim) + p.eps);
+  const __nv_bfloat16* wt = which ? p.wk : p.wq;
+  const uint2* wr = reinterpret_cast<const uint2*>(wt) + lane;
+  const float c01 = cs.x, s01 = sn.y, c23 = cs.z, s23 = sn.w;
+#pragma unroll
+  for (int i = 0; i < GPL; ++i) {
+    float a0, a1, a2, a3;
+    fmul2(a0, a1, bf16_lo_to_f32(v[i].x), bf16_hi_to_f32(v[i].x), rstd, rstd);
+    fmul2(a2, a3, bf16_lo_to_f32(v[i].y), bf16_hi_to_f32(v[i].y), rstd, rstd);
+    uint32_t n01 = pack_bf16x2(a0, a1), n23 = pack_bf16x2(a2, a3);
+    if (wt != nullptr) {
+      const uint2 w = __ldg(wr + i * 32);
+      fmul2(a0, a1, bf16_lo_to_f32(n01), bf16_hi_to_f32(n01), bf16_lo_to_f32(w.x), bf16_hi_to_f32(w.x));
+      fmul2(a2, a3, bf16_lo_to_f32(n23), bf16_hi_to_f32(n23), bf16_lo_to_f32(w.y), bf16_hi_to_f32(w.y));
+      n01 = pack_bf16x2(a0, a1);
+      n23 = pack_bf16x2(a2, a3);
+    }
+    if (rope) {
+      const float x0 = bf16_lo_to_f32(n01), x1 = bf16_hi_to_f32(n01);
+      const float x2 = bf16_lo_to_f32(n23), x3 = bf16_hi_to_f32(n23);
+      float pa, pb, ra, rb, o0, o1, o2, o3;
+      fmul2(pa, pb, x0, x1, c01, c01);
+      fmul2(ra, rb, x1, x0, -s01, s01);
+      fadd2(o0, o1, pa, pb, ra, rb);
+      fmul2(pa, pb, x2, x3, c23, c23);
+      fmul2(ra, rb, x3, x2, -s23, s23);
+      fadd2(o2, o3, pa, pb, ra, rb);
+      n01 = pack_bf16x2(o0, o1);
+      n23 = pack_bf16x2(o2, o3);
+    }
+    *reinterpret_cast<uint2*>(p.dst[i / HPR] + drow_off + (i % HPR) * 128) = make_uint2(n01, n23);
+  }
+}
+
+template <int GPL, int HPR>
+static void launch_scatter2(const ScatterParams& p, cudaStream_t stream) {
+  dim3 grid((unsigned)(3 * ((p.rows + 7) / 8)));
+  qkv_norm_rope_scatter_kernel2<GPL, HPR><<<grid, 256, 0, stream>>>(p);
+}
+
 bool qk_tma_eligible(int64_t rows, int heads, int head_dim);
 int qkv_rms_rope_scatter_tma(const void* qkv, int64_t rows, int64_t row_stride, const void* wq, const void* wk,
                              int heads, int head_dim, float eps, const float* cos, const float* sin,
                              void* const* dst_ptrs, int world, int rank, int64_t rows_per_rank,
                              int64_t dst_row_stride, cudaStream_t stream);
 static bool g_scatter_tma = false;  // see g_rows_tma in norm_kernels.cu
+static bool g_scatter_packed = true;  // packed warp-per-row kernel for the Wan shapes (24 / 40 heads x 128)
 void scatter_set_tma(int on) { g_scatter_tma = on != 0; }
+void scatter_set_packed(int on) { g_scatter_packed = on != 0; }  // follows the q/k variant of fino_rows_set_variant
 
 int qkv_norm_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride, const void* wq, const void* wk,
                           int heads, int head_dim, float eps, const float* cos, const float* sin,
@@ -276,7 +358,6 @@ int qkv_norm_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride, con
   FINO_CHECK_ARG(heads > 0 && head_dim >= 8 && head_dim % 8 == 0 && heads % world == 0,
                  "qkv_norm_rope_scatter: heads %d x head_dim %d not divisible over %d ranks", heads, head_dim, world);
   const int dim = heads * head_dim;
-  FINO_CHECK_ARG(dim / 8 <= 512, "qkv_norm_rope_scatter: heads*head_dim <= 4096");
   FINO_CHECK_ARG(row_stride % 8 == 0 && row_stride >= 3 * dim, "qkv_norm_rope_scatter: row stride");
   const int inner = dim / world;
   FINO_CHECK_ARG(dst_row_stride % 8 == 0 && dst_row_stride >= 3 * inner, "qkv_norm_rope_scatter: dst row stride");
@@ -310,6 +391,21 @@ int qkv_norm_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride, con
   p.rows_per_rank = rows_per_rank;
   p.dst_row_stride = dst_row_stride;
   p.inner = inner;
+  if (g_scatter_packed && head_dim == 128 && (heads == 24 || heads == 40) && (world == 2 || world == 4 || world == 8)) {
+    const int hpr = heads / world;
+    if (heads == 24) {
+      if (hpr == 12) launch_scatter2<24, 12>(p, stream);
+      else if (hpr == 6) launch_scatter2<24, 6>(p, stream);
+      else launch_scatter2<24, 3>(p, stream);
+    } else {
+      if (hpr == 20) launch_scatter2<40, 20>(p, stream);
+      else if (hpr == 10) launch_scatter2<40, 10>(p, stream);
+      else launch_scatter2<40, 5>(p, stream);
+    }
+    FINO_CHECK_CUDA(cudaGetLastError());
+    return FINO_OK;
+  }
+  FINO_CHECK_ARG(dim / 8 <= 512, "qkv_norm_rope_scatter: heads*head_dim <= 4096 (or 24 / 40 heads x 128)");
   const int threads = ((dim / 8 + 31) / 32) * 32;
   dim3 grid((unsigned)((rows + SCATTER_TOKENS_PER_BLOCK - 1) / SCATTER_TOKENS_PER_BLOCK));
   qkv_norm_rope_scatter_kernel<<<grid, threads, 0, stream>>>(p);

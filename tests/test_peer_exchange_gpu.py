@@ -32,12 +32,16 @@ def _inputs(n_total, heads, hd, seed=0):
 @pytest.mark.parametrize("world,n_total,heads,hd,tma", [(1, 300, 2, 128, False), (2, 1024, 4, 128, False),
                                                        (4, 777, 4, 128, False), (8, 1000, 8, 64, False),
                                                        (2, 515, 6, 64, False), (2, 1201, 8, 128, True),
+                                                       (8, 1003, 24, 128, False), (4, 520, 24, 128, False),
+                                                       (2, 300, 24, 128, False), (8, 261, 40, 128, False),
                                                        (4, 2055, 16, 64, True)])
 def test_fused_exchange_matches_unsharded(ops, world, n_total, heads, hd, tma):
     try:
+        ops.attention_set_split(0)  # bit-exact comparison: keep the KV-split merge out of both sides
         _run_fused_exchange(ops, world, n_total, heads, hd, tma)
     finally:
         ops.rows_set_tma(False)
+        ops.attention_set_split(-1)
 
 
 def _same(a, b, exact):
