@@ -72,19 +72,32 @@ __device__ __forceinline__ const float* gate_row_ptr(const GemmParams& p, int64_
   return nullptr;
 }
 
-// Residual values of one 32-column chunk of one row, fetched one chunk ahead of their use (EPI_GATE_RESIDUAL only).
+// Residual and gate values of one 32-column chunk of one row, fetched one chunk ahead of their use
+// (EPI_GATE_RESIDUAL only). The gate loads used to sit inside epilogue_chunk, right in front of the multiply that
+// consumes them: ncu showed the epilogue warps parked on that long-scoreboard stall eight times per tile
+// (profiles/r01_gemm_gate_res_ncu.txt), which made the gate-residual epilogue longer than a K = 3072 main loop.
 struct ResidualChunk {
   uint4 v[4];
+  float4 g[8];
 };
 template <int EPI>
 __device__ __forceinline__ void load_residual_chunk(const GemmParams& p, int64_t row, int col0, bool row_ok,
-                                                    ResidualChunk& rc) {
+                                                    const float* gate_row, ResidualChunk& rc) {
   if (EPI != EPI_GATE_RESIDUAL) return;
   const int ngrp = row_ok ? min(4, (p.N - col0) >> 3) : 0;
   const uint4* rp4 = reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col0);
 #pragma unroll
   for (int g = 0; g < 4; ++g)
     if (g < ngrp) rc.v[g] = __ldg(rp4 + g);
+  if (gate_row != nullptr) {
+    const float4* gp4 = reinterpret_cast<const float4*>(gate_row + col0);
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < ngrp) {
+        rc.g[2 * g] = __ldg(gp4 + 2 * g);
+        rc.g[2 * g + 1] = __ldg(gp4 + 2 * g + 1);
+      }
+  }
 }
 
 // One 32-column chunk of one accumulator row: bias, activation / gated residual, convert, 16-byte stores. N is a
@@ -121,8 +134,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int64_t row,
       } else if (EPI == EPI_GATE_RESIDUAL) {
         float gt[8];
         if (gate_row != nullptr) {
-          const float4 g0 = __ldg(reinterpret_cast<const float4*>(gate_row + col0) + 2 * g);
-          const float4 g1 = __ldg(reinterpret_cast<const float4*>(gate_row + col0) + 2 * g + 1);
+          const float4 g0 = rc.g[2 * g];
+          const float4 g1 = rc.g[2 * g + 1];
           gt[0] = g0.x, gt[1] = g0.y, gt[2] = g0.z, gt[3] = g0.w;
           gt[4] = g1.x, gt[5] = g1.y, gt[6] = g1.z, gt[7] = g1.w;
         } else {

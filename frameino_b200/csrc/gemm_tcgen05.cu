@@ -164,7 +164,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint32_t r[32];
         ResidualChunk rc;
         tmem_ld_32x32b_x32(taddr_row + c * 32, r);
-        load_residual_chunk<EPI>(p, row, col0, row_ok, rc);
+        load_residual_chunk<EPI>(p, row, col0, row_ok, gate_row, rc);
         tmem_wait_ld();
         if (row_ok) epilogue_chunk<EPI>(p, row, col0, gate_row, r, p.bias ? p.bias + col0 : nullptr, rc);
       }
@@ -353,18 +353,21 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const uint32_t taddr_row =
           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ((kAcc == 2) ? acc * BN : mh * BN);
       const int nchunk = min(BN / 32, (p.N - nt * BN + 31) / 32);  // warp-uniform
-      mbar_wait(tfull_bar(acc), acc_phase, 400 + acc);
-      tc_fence_after();
       uint32_t buf0[32], buf1[32];
       ResidualChunk rc0, rc1;
       const int colt = nt * BN;
+      // the first chunk's residual / gate values do not depend on the accumulator: fetch them while the main loop of
+      // this tile is still running (each output element is read and written by its owner thread only, so the
+      // in-place form residual == C is safe)
+      load_residual_chunk<EPI>(p, row, colt, row_ok, gate_row, rc0);
+      mbar_wait(tfull_bar(acc), acc_phase, 400 + acc);
+      tc_fence_after();
       auto release_acc = [&]() {  // every TMEM read of this warp is done: hand the accumulator back early
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
       };
       tmem_ld_32x32b_x32(taddr_row, buf0);
-      load_residual_chunk<EPI>(p, row, colt, row_ok, rc0);
       // Two chunks per iteration (static register buffers), not unrolled further: the epilogue body exists twice in
       // the instruction stream instead of eight times (the 8x unrolled version thrashed the instruction cache).
 #pragma unroll 1
@@ -372,7 +375,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         tmem_wait_ld();  // chunk c has landed in buf0
         if (c + 1 < nchunk) {
           tmem_ld_32x32b_x32(taddr_row + (c + 1) * 32, buf1);
-          load_residual_chunk<EPI>(p, row, colt + (c + 1) * 32, row_ok, rc1);
+          load_residual_chunk<EPI>(p, row, colt + (c + 1) * 32, row_ok, gate_row, rc1);
         } else {
           release_acc();
         }
@@ -381,7 +384,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           tmem_wait_ld();  // chunk c+1 has landed in buf1
           if (c + 2 < nchunk) {
             tmem_ld_32x32b_x32(taddr_row + (c + 2) * 32, buf0);
-            load_residual_chunk<EPI>(p, row, colt + (c + 2) * 32, row_ok, rc0);
+            load_residual_chunk<EPI>(p, row, colt + (c + 2) * 32, row_ok, gate_row, rc0);
           } else {
             release_acc();
           }

@@ -1066,7 +1066,7 @@ int qk_norm_rope(void* x0, int64_t rows0, int64_t stride0, const void* w0, const
     FINO_CHECK_CUDA(cudaGetLastError());
     return FINO_OK;
   }
-  if (g_qk_block_kernel == 1 && norm_mode == QK_RMS_ACROSS_HEADS && x1 != nullptr && rows0 == rows1 && rows0 >= 64 && dim >= 1024 && dim <= 4096 &&
+  if (g_qk_block_kernel >= 1 && norm_mode == QK_RMS_ACROSS_HEADS && x1 != nullptr && rows0 == rows1 && rows0 >= 64 && dim >= 1024 && dim <= 4096 &&
       (p.rope_mode == ROPE_NONE || (rope0 && rope1))) {
     const int threads = ((dim / 8 + 31) / 32) * 32;
     dim3 bgrid((unsigned)((rows0 + QK_TOKENS_PER_BLOCK - 1) / QK_TOKENS_PER_BLOCK));

@@ -35,6 +35,16 @@ if "gemm" in which:
     o = torch.empty(n, 3 * d, device="cuda", dtype=torch.bfloat16)
     for _ in range(3):
         ops.linear(a, w, b, out=o)
+if "gemm_gate" in which:  # out-projection with the gate*y + residual epilogue, in place
+    a = torch.randn(n, d, device="cuda").bfloat16()
+    x = torch.randn(n, d, device="cuda").bfloat16()
+    w = (torch.randn(d, d, device="cuda") / math.sqrt(d)).bfloat16()
+    b = torch.randn(d, device="cuda").bfloat16()
+    tab = torch.randn(2, 6 * d, device="cuda")
+    ridx = torch.zeros(n, device="cuda", dtype=torch.int32)
+    ridx[880:] = 1
+    for _ in range(3):
+        ops.linear(a, w, b, epilogue=ops.EPI_GATE_RESIDUAL, residual=x, gate=tab[:, :d], row_index=ridx, out=x)
 if "ffn" in which:
     f = 14336
     a = torch.randn(n, d, device="cuda").bfloat16()
