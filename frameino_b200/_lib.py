@@ -27,6 +27,8 @@ SIGNATURES = {
     "fino_launch_count": (_L, []),
     "fino_gemm_bf16": (_I, [_P, _L, _P, _L, _P, _P, _L, _L, _I, _I, _I, _I, _I, _P, _L, _P, _L, _P, _L, _P]),
     "fino_gemm_set_mode": (_I, [_I]),
+    "fino_gemm_set_split": (_I, [_I]),
+    "fino_gemm_plan": (_I, [_L, _I, _I, _I, _I, _P, _P]),
     "fino_attention_fwd": (_I, [_P, _P, _P, _P, _I, _I, _L, _L, _I, _L, _L, _L, _L, _L, _L, _L, _L, _F, _P]),
     "fino_attention_set_variant": (_I, [_I]),
     "fino_attention_set_split": (_I, [_I]),
@@ -72,7 +74,7 @@ def load() -> ctypes.CDLL:
     _lib = lib
     # tuning hooks for A/B runs of a whole step (tools/step_breakdown.py, bench.py): same effect as the setters in ops
     for env, fn in (("FINO_ATTN_VARIANT", lib.fino_attention_set_variant), ("FINO_ATTN_SPLIT", lib.fino_attention_set_split),
-                    ("FINO_GEMM_MODE", lib.fino_gemm_set_mode)):
+                    ("FINO_GEMM_MODE", lib.fino_gemm_set_mode), ("FINO_GEMM_SPLIT", lib.fino_gemm_set_split)):
         if os.environ.get(env):
             if fn(int(os.environ[env])) != 0:
                 raise RuntimeError(f"{env}={os.environ[env]}: {lib.fino_last_error().decode()}")

@@ -49,6 +49,8 @@ int qkv_norm_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride, con
                           void* const* dst_ptrs, int world, int rank, int64_t rows_per_rank, int64_t dst_row_stride,
                           cudaStream_t stream);
 void gemm_set_mode(int mode);
+void gemm_set_split(int mode);
+void gemm_plan(int tiles, int num_kb, int clusters, int mode, int* num_full, int* splits);
 void attention_set_variant(int v);
 void attention_set_split(int s);
 void attention_plan(int n_tiles, int T, int sms, int mode, int* n_full, int* splits);
@@ -180,6 +182,29 @@ int fino_gemm_set_mode(int mode) {
     return fino::FINO_ERR_INVALID;
   }
   fino::gemm_set_mode(mode);
+  return 0;
+}
+
+int fino_gemm_set_split(int mode) {
+  if (mode < -1 || mode == 1 || mode > 16) {
+    fino::set_last_error("fino_gemm_set_split: mode %d (want -1 auto, 0 off, or 2..16 forced K slices)", mode);
+    return fino::FINO_ERR_INVALID;
+  }
+  fino::gemm_set_split(mode);
+  return 0;
+}
+
+int fino_gemm_plan(int64_t m, int n, int k, int sms, int mode, int* num_full, int* splits) {
+  if (m <= 0 || n <= 0 || k <= 0 || sms < 2 || !num_full || !splits) {
+    fino::set_last_error("fino_gemm_plan: bad arguments");
+    return fino::FINO_ERR_INVALID;
+  }
+  const int64_t tiles = ((m + 255) / 256) * ((n + 255) / 256);
+  if (tiles >= ((int64_t)1 << 30)) {
+    fino::set_last_error("fino_gemm_plan: too many tiles");
+    return fino::FINO_ERR_INVALID;
+  }
+  fino::gemm_plan((int)tiles, (k + 63) / 64, sms / 2, mode, num_full, splits);
   return 0;
 }
 

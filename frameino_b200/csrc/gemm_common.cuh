@@ -35,6 +35,11 @@ struct GemmParams {
   const int32_t* row_index;  // [M] or null => row / rows_per_group
   int64_t rows_per_group;
   int num_m_tiles, num_n_tiles;
+  // Split-K of the partly filled last round of the persistent CTA-pair kernel (gemm2). Work units [0, num_full) are
+  // whole tiles; unit num_full + r is K-slice r % splits of tile num_full + r / splits, whose raw fp32 accumulators
+  // go to ws[r][256][256]; gemm_fixup_kernel adds the slices and applies the epilogue. splits == 1: no partial units.
+  int num_full, splits;
+  float* ws;
 };
 
 // groups of GM M-tiles; inside a group N is the slow axis so that the CTAs sharing a W tile run together
@@ -100,9 +105,65 @@ __device__ __forceinline__ void load_residual_chunk(const GemmParams& p, int64_t
   }
 }
 
-// One 32-column chunk of one accumulator row: bias, activation / gated residual, convert, 16-byte stores. N is a
-// multiple of 8 (checked by the launcher), so a ragged chunk is handled as whole 8-column groups: everything stays in
-// registers with static indices. `bias32`: the 32 bias values of this chunk (global or shared memory), or null.
+// Eight consecutive columns of one output row: bias, activation / gated residual, convert, one 16-byte store (two for
+// fp32 output). v = accumulators; bias8 = the 8 bias values (global or shared memory) or null; g0/g1 = gate values
+// (used when has_gate); x = the 8 residual values (EPI_GATE_RESIDUAL).
+template <int EPI>
+__device__ __forceinline__ void epilogue_group8(const GemmParams& p, int64_t row, int col, float (&v)[8],
+                                                const __nv_bfloat16* bias8, bool has_gate, const float4& g0,
+                                                const float4& g1, const uint4& x) {
+  if (bias8 != nullptr) {
+    const uint4 b = *reinterpret_cast<const uint4*>(bias8);
+    v[0] += bf16_lo_to_f32(b.x);
+    v[1] += bf16_hi_to_f32(b.x);
+    v[2] += bf16_lo_to_f32(b.y);
+    v[3] += bf16_hi_to_f32(b.y);
+    v[4] += bf16_lo_to_f32(b.z);
+    v[5] += bf16_hi_to_f32(b.z);
+    v[6] += bf16_lo_to_f32(b.w);
+    v[7] += bf16_hi_to_f32(b.w);
+  }
+  if (EPI == EPI_GELU_TANH) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = gelu_tanh_f(round_bf16(v[e]));
+  } else if (EPI == EPI_SILU) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = silu_f(round_bf16(v[e]));
+  } else if (EPI == EPI_GATE_RESIDUAL) {
+    float gt[8];
+    if (has_gate) {
+      gt[0] = g0.x, gt[1] = g0.y, gt[2] = g0.z, gt[3] = g0.w;
+      gt[4] = g1.x, gt[5] = g1.y, gt[6] = g1.z, gt[7] = g1.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) gt[e] = 1.0f;
+    }
+    const float xr[8] = {bf16_lo_to_f32(x.x), bf16_hi_to_f32(x.x), bf16_lo_to_f32(x.y), bf16_hi_to_f32(x.y),
+                         bf16_lo_to_f32(x.z), bf16_hi_to_f32(x.z), bf16_lo_to_f32(x.w), bf16_hi_to_f32(x.w)};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float y = round_bf16(v[e]) * gt[e];
+      if (p.flags & GEMM_FLAG_ROUND_PRODUCT) y = round_bf16(y);
+      v[e] = xr[e] + y;
+    }
+  }
+  if (p.out_fp32) {
+    float4* cp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + row * p.ldc + col);
+    cp[0] = make_float4(v[0], v[1], v[2], v[3]);
+    cp[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]);
+    o.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col) = o;
+  }
+}
+
+// One 32-column chunk of one accumulator row. N is a multiple of 8 (checked by the launcher), so a ragged chunk is
+// handled as whole 8-column groups: everything stays in registers with static indices. `bias32`: the 32 bias values
+// of this chunk (global or shared memory), or null.
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int64_t row, int col0, const float* gate_row,
                                                const uint32_t (&r)[32], const __nv_bfloat16* bias32,
@@ -114,56 +175,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, int64_t row,
       float v[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] = __uint_as_float(r[8 * g + e]);
-      if (bias32 != nullptr) {
-        const uint4 b = reinterpret_cast<const uint4*>(bias32)[g];
-        v[0] += bf16_lo_to_f32(b.x);
-        v[1] += bf16_hi_to_f32(b.x);
-        v[2] += bf16_lo_to_f32(b.y);
-        v[3] += bf16_hi_to_f32(b.y);
-        v[4] += bf16_lo_to_f32(b.z);
-        v[5] += bf16_hi_to_f32(b.z);
-        v[6] += bf16_lo_to_f32(b.w);
-        v[7] += bf16_hi_to_f32(b.w);
-      }
-      if (EPI == EPI_GELU_TANH) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = gelu_tanh_f(round_bf16(v[e]));
-      } else if (EPI == EPI_SILU) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = silu_f(round_bf16(v[e]));
-      } else if (EPI == EPI_GATE_RESIDUAL) {
-        float gt[8];
-        if (gate_row != nullptr) {
-          const float4 g0 = rc.g[2 * g];
-          const float4 g1 = rc.g[2 * g + 1];
-          gt[0] = g0.x, gt[1] = g0.y, gt[2] = g0.z, gt[3] = g0.w;
-          gt[4] = g1.x, gt[5] = g1.y, gt[6] = g1.z, gt[7] = g1.w;
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) gt[e] = 1.0f;
-        }
-        const uint4 x = rc.v[g];
-        const float xr[8] = {bf16_lo_to_f32(x.x), bf16_hi_to_f32(x.x), bf16_lo_to_f32(x.y), bf16_hi_to_f32(x.y),
-                             bf16_lo_to_f32(x.z), bf16_hi_to_f32(x.z), bf16_lo_to_f32(x.w), bf16_hi_to_f32(x.w)};
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float y = round_bf16(v[e]) * gt[e];
-          if (p.flags & GEMM_FLAG_ROUND_PRODUCT) y = round_bf16(y);
-          v[e] = xr[e] + y;
-        }
-      }
-      if (p.out_fp32) {
-        float4* cp = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + row * p.ldc + col0) + 2 * g;
-        cp[0] = make_float4(v[0], v[1], v[2], v[3]);
-        cp[1] = make_float4(v[4], v[5], v[6], v[7]);
-      } else {
-        uint4 o;
-        o.x = pack_bf16x2(v[0], v[1]);
-        o.y = pack_bf16x2(v[2], v[3]);
-        o.z = pack_bf16x2(v[4], v[5]);
-        o.w = pack_bf16x2(v[6], v[7]);
-        reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + row * p.ldc + col0)[g] = o;
-      }
+      epilogue_group8<EPI>(p, row, col0 + 8 * g, v, bias32 ? bias32 + 8 * g : nullptr, gate_row != nullptr,
+                           rc.g[2 * g], rc.g[2 * g + 1], rc.v[g]);
     }
   }
 }

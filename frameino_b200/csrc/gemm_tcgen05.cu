@@ -203,6 +203,25 @@ struct Gemm2Cfg {
   static constexpr int kThreads = 128 + 32 * kEpiWarps;        // 256 / 384
 };
 
+// Work unit -> (cluster tile, K-block range, partial slot). See GemmParams::num_full / splits.
+struct GemmUnit {
+  int tile, kb0, kb1, part;  // part < 0: whole tile with the fused epilogue
+};
+__device__ __forceinline__ GemmUnit gemm_unit(const GemmParams& p, int u, int num_kb) {
+  GemmUnit w;
+  if (u < p.num_full) {
+    w.tile = u, w.kb0 = 0, w.kb1 = num_kb, w.part = -1;
+  } else {
+    const int r = u - p.num_full;
+    const int ks = r % p.splits;
+    w.tile = p.num_full + r / p.splits;
+    w.kb0 = (ks * num_kb) / p.splits;
+    w.kb1 = ((ks + 1) * num_kb) / p.splits;
+    w.part = r;
+  }
+  return w;
+}
+
 template <int MH, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Gemm2Cfg<MH>::kThreads, 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -230,6 +249,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int num_clusters = gridDim.x >> 1;
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;  // cluster tiles
+  const int num_units = p.num_full + (num_tiles - p.num_full) * p.splits;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -261,12 +281,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      for (int u = cluster_id; u < num_units; u += num_clusters) {
+        const GemmUnit wu = gemm_unit(p, u, num_kb);
         int mt, nt;
-        tile_coords(tile, p.num_m_tiles, p.num_n_tiles, mt, nt);
+        tile_coords(wu.tile, p.num_m_tiles, p.num_n_tiles, mt, nt);
         const int row_a = mt * Cfg::kTileM + (int)cta_rank * (MH * GEMM_BM);
         const int row_b = nt * BN + (int)cta_rank * (BN / 2);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = wu.kb0; kb < wu.kb1; ++kb) {
           mbar_wait_relaxed(empty_bar(stage), phase ^ 1u, 100 + stage);
           uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
           uint32_t b_dst = a_dst + Cfg::kABytes;
@@ -288,14 +309,15 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      for (int u = cluster_id; u < num_units; u += num_clusters, ++it) {
+        const GemmUnit wu = gemm_unit(p, u, num_kb);
         const int acc = (kAcc == 2) ? (it & 1) : 0;
         const uint32_t acc_phase = (kAcc == 2) ? ((it >> 1) & 1) : (it & 1);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 200 + acc);
         fence_acq_rel_cluster();  // the arrivals are remote (peer epilogue warps, release.cluster)
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + ((kAcc == 2) ? acc * BN : 0);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = wu.kb0; kb < wu.kb1; ++kb) {
           mbar_wait(full_bar(stage), phase, 300 + stage);
           tc_fence_after();
           uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
@@ -306,7 +328,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
             for (int mh = 0; mh < MH; ++mh) {
               uint64_t adesc = make_sdesc_sw128(a_addr + mh * (GEMM_BM * GEMM_BK * 2) + k * 32, 16, 1024);
-              umma_ss_2cta_w(tmem_d + mh * BN, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              umma_ss_2cta_w(tmem_d + mh * BN, adesc, bdesc, idesc, ((kb - wu.kb0) | k) != 0 ? 1u : 0u);
             }
           }
           tc_commit_2cta_w(empty_bar(stage), 0b11);  // frees this stage in BOTH CTAs
@@ -330,11 +352,35 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const __nv_bfloat16* bias_s = reinterpret_cast<const __nv_bfloat16*>(
         smem_raw + (bias_s_u32 - smem_u32(smem_raw)));
     int it = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+    for (int u = cluster_id; u < num_units; u += num_clusters, ++it) {
+      const GemmUnit wu = gemm_unit(p, u, num_kb);
       int mt, nt;
-      tile_coords(tile, p.num_m_tiles, p.num_n_tiles, mt, nt);
+      tile_coords(wu.tile, p.num_m_tiles, p.num_n_tiles, mt, nt);
       const int acc = (kAcc == 2) ? (it & 1) : 0;
       const uint32_t acc_phase = (kAcc == 2) ? ((it >> 1) & 1) : (it & 1);
+      if (wu.part >= 0) {
+        // K-slice of a tail tile: raw fp32 accumulators to the workspace, [part][256 rows][256 columns]
+        // (MH == 1 only; gemm_fixup_kernel adds the slices and runs the fused epilogue)
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ((kAcc == 2) ? acc * BN : 0);
+        float4* dst = reinterpret_cast<float4*>(p.ws + ((int64_t)wu.part * Cfg::kTileM +
+                                                        (int64_t)cta_rank * GEMM_BM + q * 32 + lane) * BN);
+        mbar_wait(tfull_bar(acc), acc_phase, 400 + acc);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            dst[c * 8 + e] = make_float4(__uint_as_float(r[4 * e]), __uint_as_float(r[4 * e + 1]),
+                                         __uint_as_float(r[4 * e + 2]), __uint_as_float(r[4 * e + 3]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_bar(acc), 0);
+        continue;
+      }
       if (p.bias != nullptr) {  // stage bias[nt*256 .. +256) while the main loop is still running
         const int colb = nt * BN + lane * 8;
         uint4 b = make_uint4(0, 0, 0, 0);
@@ -405,6 +451,90 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
 }
 
+// Adds the K-slices of the tail tiles and applies the fused epilogue. One thread per (row, 8 columns): a warp covers
+// one 256-column row segment, so the partial reads (32 B per lane per slice) and the output stores are contiguous.
+template <int EPI>
+__global__ void __launch_bounds__(256) gemm_fixup_kernel(const GemmParams p) {
+  constexpr int TM = 2 * GEMM_BM, BN = 256;
+  const int tl = blockIdx.x / (TM / 8);           // tail tile
+  const int r = (blockIdx.x % (TM / 8)) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  int mt, nt;
+  tile_coords(p.num_full + tl, p.num_m_tiles, p.num_n_tiles, mt, nt);
+  const int64_t row = (int64_t)mt * TM + r;
+  const int col = nt * BN + lane * 8;
+  if (row >= p.M || col >= p.N) return;
+  float v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) v[e] = 0.f;
+  for (int s = 0; s < p.splits; ++s) {
+    const float4* src = reinterpret_cast<const float4*>(p.ws + ((int64_t)(tl * p.splits + s) * TM + r) * BN + lane * 8);
+    const float4 a = src[0], b = src[1];
+    v[0] += a.x, v[1] += a.y, v[2] += a.z, v[3] += a.w;
+    v[4] += b.x, v[5] += b.y, v[6] += b.z, v[7] += b.w;
+  }
+  const float* gate_row = gate_row_ptr(p, row, true);
+  float4 g0 = make_float4(1.f, 1.f, 1.f, 1.f), g1 = g0;
+  uint4 x = make_uint4(0, 0, 0, 0);
+  if (EPI == EPI_GATE_RESIDUAL) {
+    x = __ldg(reinterpret_cast<const uint4*>(p.residual + row * p.ldr + col));
+    if (gate_row != nullptr) {
+      g0 = __ldg(reinterpret_cast<const float4*>(gate_row + col));
+      g1 = __ldg(reinterpret_cast<const float4*>(gate_row + col) + 1);
+    }
+  }
+  epilogue_group8<EPI>(p, row, col, v, p.bias ? p.bias + col : nullptr, gate_row != nullptr, g0, g1, x);
+}
+
+// Per-device workspace for the K-slices (<= 74 clusters x 256 x 256 fp32 = 19.4 MB; grown on demand). Calls on one
+// device are assumed stream-ordered with each other, like the attention workspace.
+static void* g_gemm_ws[16] = {};
+static size_t g_gemm_ws_bytes[16] = {};
+static int gemm_workspace(size_t bytes, float** out) {
+  int dev = 0;
+  FINO_CHECK_CUDA(cudaGetDevice(&dev));
+  FINO_CHECK_ARG(dev >= 0 && dev < 16, "gemm: device index %d out of range", dev);
+  if (g_gemm_ws_bytes[dev] < bytes) {
+    if (g_gemm_ws[dev]) {
+      FINO_CHECK_CUDA(cudaDeviceSynchronize());
+      FINO_CHECK_CUDA(cudaFree(g_gemm_ws[dev]));
+      g_gemm_ws[dev] = nullptr;
+      g_gemm_ws_bytes[dev] = 0;
+    }
+    const size_t want = bytes < ((size_t)20 << 20) ? ((size_t)20 << 20) : bytes;
+    FINO_CHECK_CUDA(cudaMalloc(&g_gemm_ws[dev], want));
+    g_gemm_ws_bytes[dev] = want;
+  }
+  *out = reinterpret_cast<float*>(g_gemm_ws[dev]);
+  return FINO_OK;
+}
+
+// Split-K plan of the pair kernel (see GemmParams): tiles of 256 x 256 on `clusters` CTA pairs, num_kb K-blocks.
+// mode: -1 automatic, 0 never, S >= 2: split every tile of the last (or only) round S ways (test hook).
+static int g_gemm_split = -1;
+void gemm_set_split(int mode) { g_gemm_split = mode; }
+void gemm_plan(int tiles, int num_kb, int clusters, int mode, int* num_full, int* splits) {
+  *num_full = tiles;
+  *splits = 1;
+  if (mode == 0) return;
+  const int rem = tiles % clusters;
+  if (rem == 0 && mode < 2) return;
+  int s;
+  if (mode >= 2) {
+    s = mode;
+  } else {
+    s = clusters / rem;
+    if (s > 4) s = 4;
+  }
+  // a slice must be long enough to pay for its exposed partial epilogue and the fix-up launch: measured at M = 3520,
+  // N = 3072 (168 tiles, 74 pairs): K = 14336 254 -> 233 us with 3 slices, K = 3072 64 -> 66 us (no gain)
+  const int min_kb = mode >= 2 ? 8 : 32;
+  if (s > num_kb / min_kb) s = num_kb / min_kb;
+  if (s < 2) return;
+  *num_full = tiles - (rem == 0 ? clusters < tiles ? clusters : tiles : rem);
+  *splits = s;
+}
+
 // ================================================================================================
 // host side
 // ================================================================================================
@@ -434,10 +564,15 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
     configured = true;
   }
   int tiles = p.num_m_tiles * p.num_n_tiles;
+  int units = p.num_full + (tiles - p.num_full) * p.splits;
   int clusters = num_sms() / 2;
-  if (tiles < clusters) clusters = tiles;
+  if (units < clusters) clusters = units;
   gemm2_bf16_kernel<MH, EPI><<<2 * clusters, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   FINO_CHECK_CUDA(cudaGetLastError());
+  if (p.splits > 1) {
+    gemm_fixup_kernel<EPI><<<(tiles - p.num_full) * (Cfg::kTileM / 8), 256, 0, stream>>>(p);
+    FINO_CHECK_CUDA(cudaGetLastError());
+  }
   return FINO_OK;
 }
 
@@ -502,6 +637,18 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
   p.rows_per_group = rows_per_group > 0 ? rows_per_group : (int64_t)1 << 62;
   p.num_m_tiles = (int)((m + BM - 1) / BM);
   p.num_n_tiles = (n + BN - 1) / BN;
+  p.num_full = p.num_m_tiles * p.num_n_tiles;
+  p.splits = 1;
+  p.ws = nullptr;
+  if (mh == 1) {  // 256 x 256 pair kernel: split-K of the partly filled last round
+    const int tiles = p.num_m_tiles * p.num_n_tiles;
+    gemm_plan(tiles, (k + GEMM_BK - 1) / GEMM_BK, num_sms() / 2, g_gemm_split, &p.num_full, &p.splits);
+    if (p.splits > 1) {
+      const size_t bytes = (size_t)(tiles - p.num_full) * p.splits * 256 * 256 * sizeof(float);
+      int r = gemm_workspace(bytes, &p.ws);
+      if (r) return r;
+    }
+  }
 
   CUtensorMap ta, tb;
   {

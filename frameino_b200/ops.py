@@ -335,6 +335,21 @@ def gemm_set_mode(mode: int) -> None:
     _lib.check(_lib.load().fino_gemm_set_mode(mode), "fino_gemm_set_mode")
 
 
+def gemm_set_split(mode: int) -> None:
+    """Split-K of the pair GEMM's partly filled last round: -1 automatic (default), 0 never, 2..16 forced (test hook)."""
+    _lib.check(_lib.load().fino_gemm_set_split(int(mode)), "fino_gemm_set_split")
+
+
+def gemm_plan(m: int, n: int, k: int, sms: int = 148, mode: int = -1):
+    """(num_full, splits) of the pair GEMM on a device with ``sms`` SMs (host arithmetic only)."""
+    import ctypes
+
+    num_full, splits = ctypes.c_int(0), ctypes.c_int(0)
+    _lib.check(_lib.load().fino_gemm_plan(m, n, k, sms, mode, ctypes.byref(num_full), ctypes.byref(splits)),
+               "fino_gemm_plan")
+    return num_full.value, splits.value
+
+
 def attention_set_variant(variant: int) -> None:
     _lib.check(_lib.load().fino_attention_set_variant(variant), "fino_attention_set_variant")
 

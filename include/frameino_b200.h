@@ -51,6 +51,16 @@ int fino_gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const
  * 256x256 cluster tiles, 3 = CTA pair with 512x256 cluster tiles. */
 int fino_gemm_set_mode(int mode);
 
+/* Work decomposition of the CTA-pair GEMM kernel (256 x 256 tiles on sms/2 CTA pairs, persistent). When the tile count
+ * leaves a partly filled last round (8-way Ulysses: M = 3520, N = 3072 -> 168 tiles on 74 pairs = 2.27 rounds), the
+ * tiles of that round are split along K into `splits` slices each (raw fp32 partials in a library-owned per-device
+ * workspace; a small second kernel adds the slices and applies the fused epilogue). mode: -1 = automatic (default),
+ * 0 = never, 2..16 = split the whole last round that many ways (test hook). Calls on one device must be
+ * stream-ordered with each other. */
+int fino_gemm_set_split(int mode);
+/* The decomposition fino_gemm_bf16 would use for an m x n x k problem on a device with `sms` SMs (host arithmetic). */
+int fino_gemm_plan(int64_t m, int n, int k, int sms, int mode, int* num_full, int* splits);
+
 /* O = softmax(Q K^T * scale) V, non-causal, no mask; tcgen05 flash attention, head_dim 64 or 128.
  * Replaces F.scaled_dot_product_attention: transformer_wan.py:108-110, attention_processor.py:2863.
  * Q/K/V/O are [batch, n, heads*head_dim] views (heads contiguous inside a row). */

@@ -157,3 +157,21 @@ def test_attention_wave_plan():
             assert n_full % 148 == 0 and (tiles - n_full) * s <= 148 and (nk + 127) // 128 // s >= 8
         else:
             assert n_full == tiles
+
+
+def test_gemm_round_plan():
+    """fino_gemm_plan: split-K only where the persistent pair kernel's last round is partly filled."""
+    from frameino_b200 import ops
+
+    # 8-way Ulysses shard, N = 3072: 14 x 12 = 168 tiles on 74 pairs -> 148 whole tiles + 20 tiles in 3 K-slices
+    assert ops.gemm_plan(3520, 3072, 14336) == (148, 3)
+    # ... but not when the K-slices would be too short to pay for the fix-up (measured: no gain at K = 3072)
+    assert ops.gemm_plan(3520, 3072, 3072) == (168, 1)
+    # last round more than half full: left alone (QKV / FFN-up at P = 8, everything at P = 1)
+    assert ops.gemm_plan(3520, 9216, 3072) == (504, 1)
+    assert ops.gemm_plan(3520, 14336, 3072) == (784, 1)
+    assert ops.gemm_plan(28160, 3072, 3072) == (1320, 1)
+    # K too short to slice; split off; forced mode on a small problem slices every tile
+    assert ops.gemm_plan(3520, 3072, 512) == (168, 1)
+    assert ops.gemm_plan(3520, 3072, 3072, mode=0) == (168, 1)
+    assert ops.gemm_plan(512, 512, 2048, mode=4) == (0, 4)

@@ -211,6 +211,42 @@ def test_gemm_epilogues_vs_oracle(ops):
     assert rel_err(out, ref_cog) <= BF16_TOL
 
 
+@pytest.mark.parametrize("splits", [2, 3])
+def test_gemm_split_k_tail_matches_fused_epilogues(ops, splits):
+    """The split-K work units of the pair kernel (raw fp32 slices + fix-up kernel with the fused epilogue) forced on
+    the last round: every epilogue, ragged M and N, in-place gated residual, against the unsplit kernel and torch."""
+    m, n, k = 700, 520, 1536
+    a, w, b = bf(m, k), bf(n, k, scale=1.0 / math.sqrt(k), seed=1), bf(n, seed=2)
+    x = bf(m, n, seed=3)
+    gate = torch.randn(3, n, generator=torch.Generator().manual_seed(4))
+    ridx = torch.randint(0, 3, (m,), generator=torch.Generator().manual_seed(5)).int()
+    ac, wc, bc = a.cuda(), w.cuda(), b.cuda()
+    y = F.linear(a.float(), w.float(), b.float())
+    refs = {
+        ops.EPI_NONE: y,
+        ops.EPI_GELU_TANH: F.gelu(y.bfloat16().float(), approximate="tanh"),
+        ops.EPI_SILU: F.silu(y.bfloat16().float()),
+        ops.EPI_GATE_RESIDUAL: x.float() + y.bfloat16().float() * gate[ridx.long()],
+    }
+    try:
+        for epi, ref in refs.items():
+            kw = {}
+            if epi == ops.EPI_GATE_RESIDUAL:
+                kw = dict(residual=x.cuda(), gate=gate.cuda(), row_index=ridx.cuda())
+            ops.gemm_set_split(0)
+            whole = ops.linear(ac, wc, bc, epilogue=epi, **kw)
+            ops.gemm_set_split(splits)
+            if epi == ops.EPI_GATE_RESIDUAL:  # in place, as the blocks use it
+                xs = x.cuda()
+                out = ops.linear(ac, wc, bc, epilogue=epi, residual=xs, gate=gate.cuda(), row_index=ridx.cuda(), out=xs)
+            else:
+                out = ops.linear(ac, wc, bc, epilogue=epi, **kw)
+            assert rel_err(out, ref) <= BF16_TOL, epi
+            assert rel_err(out, whole.float().cpu()) <= 2.0 ** -7, epi  # same sums, different association
+    finally:
+        ops.gemm_set_split(-1)
+
+
 def _sdpa_ref(q, k, v, heads):
     from oracle.wan_oracle import sdpa
 
