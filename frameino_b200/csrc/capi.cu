@@ -48,6 +48,12 @@ int qkv_norm_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride, con
                           int heads, int head_dim, float eps, const float* cos, const float* sin,
                           void* const* dst_ptrs, int world, int rank, int64_t rows_per_rank, int64_t dst_row_stride,
                           cudaStream_t stream);
+int wan_pack_model_input(const float* latents, const float* condition, const float* mask, const float* id_latents,
+                         const float* traj, void* rows, int B, int C, int F, int NID, int H, int W, int pt, int ph,
+                         int pw, int64_t ld, cudaStream_t stream);
+int wan_cfg_euler_step(const void* y_cond, const void* y_uncond, int64_t ld, float* latents, int B, int C, int F,
+                       int NID, int H, int W, int pt, int ph, int pw, float guidance, float dsigma,
+                       cudaStream_t stream);
 void gemm_set_mode(int mode);
 void gemm_set_split(int mode);
 void gemm_plan(int tiles, int num_kb, int clusters, int mode, int* num_full, int* splits);
@@ -276,6 +282,20 @@ int fino_qkv_norm_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride
 
 int fino_peer_barrier(void* const* flag_ptrs, int rank, int world, uint32_t epoch, void* stream) {
   FINO_ENTRY(fino::peer_barrier(flag_ptrs, rank, world, epoch, (cudaStream_t)stream));
+}
+
+int fino_wan_pack_model_input(const float* latents, const float* condition, const float* mask,
+                              const float* id_latents, const float* traj_latents, void* rows, int b, int c, int f,
+                              int n_id, int h, int w, int pt, int ph, int pw, int64_t ld, void* stream) {
+  FINO_ENTRY(fino::wan_pack_model_input(latents, condition, mask, id_latents, traj_latents, rows, b, c, f, n_id, h, w,
+                                        pt, ph, pw, ld, (cudaStream_t)stream));
+}
+
+int fino_wan_cfg_euler_step(const void* y_cond, const void* y_uncond, int64_t ld, float* latents, int b, int c, int f,
+                            int n_id, int h, int w, int pt, int ph, int pw, float guidance, float dsigma,
+                            void* stream) {
+  FINO_ENTRY(fino::wan_cfg_euler_step(y_cond, y_uncond, ld, latents, b, c, f, n_id, h, w, pt, ph, pw, guidance, dsigma,
+                                      (cudaStream_t)stream));
 }
 
 // allocation / IPC: no kernel launch, not counted

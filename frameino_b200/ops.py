@@ -319,6 +319,62 @@ def build_mod_table(table: torch.Tensor, proj: torch.Tensor, layers: int, table_
     return out
 
 
+def _f32c(t: Optional[torch.Tensor], shape, what: str) -> None:
+    if t is None:
+        return
+    if t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{what}: want contiguous float32 {tuple(shape)}, got {t.dtype} {tuple(t.shape)}")
+
+
+def wan_pack_model_input(latents: torch.Tensor, condition: torch.Tensor, mask: torch.Tensor,
+                         id_latents: Optional[torch.Tensor], traj_latents: torch.Tensor,
+                         patch: Tuple[int, int, int], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Blend + ID concat + trajectory concat + bf16 cast + patchify of one sampler step (``fino_wan_pack_model_input``).
+    latents/condition: fp32 [B, C, F, H, W]; mask: fp32 [F, H, W]; id_latents: fp32 [B, C, n_id, H, W] or None;
+    traj_latents: fp32 [B, C, F + n_id, H, W]. Returns bf16 rows [B * tokens, 2*C*pt*ph*pw]."""
+    b, c, f, h, w = latents.shape
+    n_id = 0 if id_latents is None else id_latents.shape[2]
+    _f32c(latents, (b, c, f, h, w), "latents")
+    _f32c(condition, (b, c, f, h, w), "condition")
+    _f32c(mask, (f, h, w), "mask")
+    _f32c(id_latents, (b, c, n_id, h, w), "id_latents")
+    _f32c(traj_latents, (b, c, f + n_id, h, w), "traj_latents")
+    lib, stream = _prep(latents, condition, mask, id_latents, traj_latents, out)
+    pt, ph, pw = patch
+    rows = b * ((f + n_id) // pt) * (h // ph) * (w // pw)
+    kdim = 2 * c * pt * ph * pw
+    if out is None:
+        out = torch.empty(rows, kdim, dtype=torch.bfloat16, device=latents.device)
+    assert out.dtype == torch.bfloat16 and out.shape == (rows, kdim) and out.stride(1) == 1
+    status = lib.fino_wan_pack_model_input(latents.data_ptr(), condition.data_ptr(), mask.data_ptr(), _ptr(id_latents),
+                                           traj_latents.data_ptr(), out.data_ptr(), b, c, f, n_id, h, w, pt, ph, pw,
+                                           out.stride(0), stream)
+    _lib.check(status, "fino_wan_pack_model_input")
+    return out
+
+
+def wan_cfg_euler_step(latents: torch.Tensor, y_cond: torch.Tensor, y_uncond: Optional[torch.Tensor], n_id: int,
+                       patch: Tuple[int, int, int], guidance: float, dsigma: float) -> torch.Tensor:
+    """In place: latents += dsigma * (y_uncond + guidance * (y_cond - y_uncond)) from the forwards' proj_out rows
+    (``fino_wan_cfg_euler_step``; CFG + ID-frame drop + Euler step + un-patchify). latents: fp32 [B, C, F, H, W];
+    y_*: bf16 [B * tokens(F + n_id), pt*ph*pw*C]."""
+    b, c, f, h, w = latents.shape
+    _f32c(latents, (b, c, f, h, w), "latents")
+    lib, stream = _prep(latents, y_cond, y_uncond)
+    pt, ph, pw = patch
+    rows = b * ((f + n_id) // pt) * (h // ph) * (w // pw)
+    for y in (y_cond, y_uncond):
+        if y is not None:
+            assert y.dtype == torch.bfloat16 and y.dim() == 2 and y.stride(1) == 1
+            assert y.shape == (rows, c * pt * ph * pw), f"rows {tuple(y.shape)} != {(rows, c * pt * ph * pw)}"
+    if y_uncond is not None:
+        assert y_uncond.stride(0) == y_cond.stride(0)
+    status = lib.fino_wan_cfg_euler_step(y_cond.data_ptr(), _ptr(y_uncond), y_cond.stride(0), latents.data_ptr(), b, c,
+                                         f, n_id, h, w, pt, ph, pw, float(guidance), float(dsigma), stream)
+    _lib.check(status, "fino_wan_cfg_euler_step")
+    return latents
+
+
 def swap01(x: torch.Tensor, a: int, b: int, inner: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Contiguous [a, b, inner] -> [b, a, inner] (bf16, inner % 8 == 0)."""
     assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() == a * b * inner

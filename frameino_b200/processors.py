@@ -51,9 +51,25 @@ def _rope_table(t: torch.Tensor, head_dim: int) -> torch.Tensor:
 class FinoWanAttnProcessor:
     """``processor(attn, hidden_states, encoder_hidden_states=None, attention_mask=None, rotary_emb=None)`` -> Tensor.
 
-    Extra keyword (only passed by frameino_b200's own block): ``fino_residual=(x, gate, row_index, rows_per_group)``
-    fuses ``x + out * gate`` (transformer_wan.py:336 / :341) into the out-projection epilogue and returns ``x``.
+    Extra keywords (only passed by frameino_b200's own block): ``fino_residual=(x, gate, row_index, rows_per_group)``
+    fuses ``x + out * gate`` (transformer_wan.py:336 / :341) into the out-projection epilogue and returns ``x``;
+    ``fino_text_kv=(k, v)`` supplies the cross-attention key (already normalised) and value projections of
+    ``encoder_hidden_states`` computed once per prompt by ``project_text`` (they do not change over the sampler steps).
     """
+
+    @staticmethod
+    def project_text(attn, encoder_hidden_states: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """``(norm_k(to_k(text)), to_v(text))`` of a cross-attention module (transformer_wan.py:61-67), each
+        [B, T, D] (views of one fused [B, T, 2D] GEMM output)."""
+        _check_dtype(encoder_hidden_states, "encoder_hidden_states")
+        w, bias = _fused_weights(attn, ("to_k", "to_v"), "kv")
+        kv = ops.linear(encoder_hidden_states, w, bias)  # [B, T, 2D]
+        d_model = w.shape[0] // 2
+        k, v = kv[..., :d_model], kv[..., d_model:]
+        if attn.norm_k is not None:
+            ops.qk_norm_rope(k, attn.norm_k.weight, None, None, attn.heads, norm_mode=ops.QK_RMS_ACROSS_HEADS,
+                             eps=getattr(attn.norm_k, "eps", 1e-6), rope_mode=ops.ROPE_NONE, seq_len=k.shape[1])
+        return k, v
 
     def __call__(
         self,
@@ -63,6 +79,7 @@ class FinoWanAttnProcessor:
         attention_mask: Optional[torch.Tensor] = None,
         rotary_emb: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
         fino_residual=None,
+        fino_text_kv=None,
     ) -> torch.Tensor:
         if attention_mask is not None:
             raise NotImplementedError("attention_mask is not supported (the reference never passes one)")
@@ -73,6 +90,17 @@ class FinoWanAttnProcessor:
         b, n, _ = hidden_states.shape
         norm_q, norm_k = attn.norm_q, attn.norm_k
         eps = getattr(norm_q, "eps", 1e-6) if norm_q is not None else 1e-6
+        if fino_text_kv is not None:  # cross-attention against pre-projected text K/V: only the query side is left
+            if encoder_hidden_states is None or rotary_emb is not None:
+                raise ValueError("fino_text_kv belongs to a cross-attention call (encoder_hidden_states, no rotary_emb)")
+            k, v = fino_text_kv
+            q = ops.linear(hidden_states, attn.to_q.weight, attn.to_q.bias)
+            if norm_q is not None:
+                ops.qk_norm_rope(q, norm_q.weight, None, None, heads, norm_mode=ops.QK_RMS_ACROSS_HEADS, eps=eps,
+                                 rope_mode=ops.ROPE_NONE, seq_len=n)
+            head_dim = q.shape[-1] // heads
+            o = ops.attention(q, k, v, heads, scale=getattr(attn, "scale", head_dim ** -0.5))
+            return self._out_proj(attn, o, fino_residual)
         if encoder_hidden_states is None:
             w, bias = _fused_weights(attn, ("to_q", "to_k", "to_v"), "qkv")
             qkv = ops.linear(hidden_states, w, bias)  # [B, N, 3D]

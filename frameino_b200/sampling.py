@@ -2,10 +2,20 @@
 (pipelines/pipeline_wan_i2v_motion_FrameINO.py:809-908): first-frame mask blend, per-token timesteps, frame-wise ID
 concat, channel-wise trajectory concat, two CFG forwards, ID-frame drop, flow-match Euler step.
 
-This is the CALLER of the hot path (SURVEY.md §8f "next" #1), kept in plain torch so that the same function can drive
-either the native model or any other ``transformer(hidden_states=, timestep=, encoder_hidden_states=, return_dict=False)``
-callable; parity tests run it on both sides. The scheduler is flow-match Euler with shift 5.0
-(config/train_wan_motion_FrameINO.yaml:43-50) — the stepper is not the thing under test.
+This is the CALLER of the hot path (SURVEY.md §8f "next" #1), in two forms:
+
+* ``wan_frameino_denoise`` — plain torch, drives the native model or any other
+  ``transformer(hidden_states=, timestep=, encoder_hidden_states=, return_dict=False)`` callable exactly as the reference
+  pipeline does (about 15 small tensor ops per step around the two forwards); parity tests run it on both sides.
+* ``wan_frameino_denoise_fused`` — the same loop for the native ``WanTransformer3DModel`` with the glue on the device in
+  two kernels per scheduler step (``fino_wan_pack_model_input`` before, ``fino_wan_cfg_euler_step`` after the two
+  forwards) and everything step-invariant hoisted out of the loop: the text-embedder MLP and the 30 cross-attention
+  K/V projections of both prompts (``WanTextState``), the RoPE tables, the per-token timestep selector. The 5-D model
+  input and the 5-D model outputs are never materialised (the forwards run rows -> rows through ``forward_rows``), and
+  there is no host synchronisation inside the loop. Same arithmetic, bit for bit, as the plain form.
+
+The scheduler is flow-match Euler with shift 5.0 (config/train_wan_motion_FrameINO.yaml:43-50) — the stepper is not
+the thing under test.
 """
 from __future__ import annotations
 
@@ -58,3 +68,75 @@ def wan_frameino_denoise(
         v = v[:, :, :n_gen].float()  # :886 drop the ID frames
         latents = latents + (sigmas[i + 1] - sigmas[i]) * v  # :891 Euler
     return latents
+
+
+@torch.no_grad()
+def wan_frameino_denoise_fused(
+    transformer,                    # frameino_b200.wan.WanTransformer3DModel on a CUDA device
+    latents: torch.Tensor,          # [B, C, F, H, W] initial noise
+    condition: torch.Tensor,        # [B, C, F, H, W]
+    first_frame_mask: torch.Tensor, # [1, 1|C, F, H, W], 0/1 valued (pipeline :529-532)
+    traj_latents: torch.Tensor,     # [B, C, F + n_id, H, W]
+    id_latents: Optional[torch.Tensor],  # [B, C, n_id, H, W] or None
+    prompt_embeds: torch.Tensor,
+    negative_prompt_embeds: Optional[torch.Tensor],
+    num_steps: int = 50,
+    guidance_scale: float = 5.0,
+    shift: float = 5.0,
+) -> torch.Tensor:
+    """Same contract and result as ``wan_frameino_denoise`` (see the module docstring for what is fused)."""
+    from . import ops
+
+    dev = latents.device
+    if dev.type != "cuda":
+        raise RuntimeError("frameino_b200 has no CPU path: move the model and inputs to a CUDA device")
+    cfg = transformer.config
+    patch = tuple(cfg.patch_size)
+    p_t, p_h, p_w = patch
+    b, c, f, h, w = latents.shape
+    n_id = 0 if id_latents is None else id_latents.shape[2]
+    if 2 * c != cfg.in_channels or c != cfg.out_channels:
+        raise ValueError(f"latent channels {c} do not match the model (in {cfg.in_channels}, out {cfg.out_channels})")
+    if p_t != 1:
+        raise NotImplementedError("fused sampler loop: temporal patch size 1 (Wan) only")
+
+    f32 = dict(device=dev, dtype=torch.float32)
+    lat = latents.to(**f32).clone(memory_format=torch.contiguous_format)
+    cond = condition.to(**f32).expand(b, c, f, h, w).contiguous()
+    traj = traj_latents.to(**f32).expand(b, c, f + n_id, h, w).contiguous()
+    idl = None if n_id == 0 else id_latents.to(**f32).expand(b, c, n_id, h, w).contiguous()
+    mask5 = first_frame_mask.to(**f32)
+    if mask5.dim() != 5 or mask5.shape[0] != 1 or tuple(mask5.shape[2:]) != (f, h, w):
+        raise ValueError(f"first_frame_mask shape {tuple(first_frame_mask.shape)}: want [1, 1|C, {f}, {h}, {w}]")
+    mask = mask5[0, 0].contiguous()
+    if mask5.shape[1] != 1 and not bool((mask5 == mask5[:, :1]).all()):
+        raise NotImplementedError("fused sampler loop: first_frame_mask must be the same for every channel")
+    if not bool(((mask == 0) | (mask == 1)).all()):  # one host sync, before the loop
+        raise NotImplementedError("fused sampler loop: first_frame_mask must be 0/1 valued (it selects timestep rows)")
+
+    # per-token timestep selector, constant over the loop (pipeline :842-843): mask sampled at the patch corners,
+    # ID tokens carry t; time row 0 = timestep 0 (clean first frame), row 1 = t
+    sel = mask[:, ::p_h, ::p_w].reshape(-1)
+    sel = torch.cat([sel, sel.new_ones(n_id * (h // p_h) * (w // p_w))])
+    row_index = sel.to(torch.int32).repeat(b).contiguous()
+    mixed = bool((sel == 0).any())  # False: every token carries t (a single time row)
+
+    sigmas = flow_match_sigmas(num_steps, shift, dev)
+    sig_host = sigmas.cpu()
+    do_cfg = guidance_scale > 1.0 and negative_prompt_embeds is not None
+    text_c = transformer.prepare_text(prompt_embeds)
+    text_u = transformer.prepare_text(negative_prompt_embeds) if do_cfg else None
+    grid = (f + n_id, h, w)
+    tokens = ((f + n_id) // p_t) * (h // p_h) * (w // p_w)
+    rows = None
+    for i in range(num_steps):
+        t = sigmas[i] * 1000.0
+        uniq = torch.stack([torch.zeros_like(t), t]) if mixed else t.reshape(1)
+        temb, proj = transformer.time_rows(uniq)
+        conditioning = (temb, proj, row_index, 0) if mixed else (temb, proj, None, b * tokens)
+        rows = ops.wan_pack_model_input(lat, cond, mask, idl, traj, patch, out=rows)
+        y_c = transformer.forward_rows(rows, b, grid, conditioning, text_c)
+        y_u = transformer.forward_rows(rows, b, grid, conditioning, text_u) if do_cfg else None
+        dsigma = float(sig_host[i + 1] - sig_host[i])  # fp32 difference, as the tensor form computes it
+        ops.wan_cfg_euler_step(lat, y_c, y_u, n_id, patch, guidance_scale, dsigma)
+    return lat

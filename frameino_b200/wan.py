@@ -12,8 +12,9 @@ What changes relative to the reference arithmetic (and why it is still the same 
 from __future__ import annotations
 
 import math
+from contextlib import contextmanager
 from dataclasses import dataclass
-from typing import Any, Dict, Optional, Tuple, Union
+from typing import Any, Dict, List, Optional, Tuple, Union
 
 import torch
 from torch import nn
@@ -31,6 +32,19 @@ class Transformer2DModelOutput:
 
     def __getitem__(self, i):
         return (self.sample,)[i]
+
+
+@dataclass
+class WanTextState:
+    """The text-side work of one forward that does not depend on the latents or the timestep — constant over the 50
+    sampler steps of a prompt: the text-embedder MLP (transformer_wan.py:185) and every block's
+    cross-attention ``norm_k(to_k(text))`` / ``to_v(text)`` (transformer_wan.py:61-67 with encoder_hidden_states = text).
+    Built by ``WanTransformer3DModel.prepare_text``; reused across forwards inside ``model.cache_context(name)``."""
+
+    text: torch.Tensor                                         # [B, T, D] bf16
+    kv: List[Optional[Tuple[torch.Tensor, torch.Tensor]]]      # per block; None where a foreign processor is plugged in
+    key: Any = None                                            # validity key (input + weight identities/versions)
+    source: Optional[torch.Tensor] = None                      # strong reference: keeps the keyed memory from being reused
 
 
 def _rope_1d(dim: int, max_len: int, theta: float = 10000.0) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -59,6 +73,10 @@ class WanRotaryPosEmbed(nn.Module):
 
     def forward(self, hidden_states: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         _, _, f, h, w = hidden_states.shape
+        return self.tables(f, h, w)
+
+    def tables(self, f: int, h: int, w: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(cos, sin) for a latent of f x h x w (before patching)."""
         key = (f, h, w, self.freqs_cos.device)
         hit = self._cache.get(key)
         if hit is not None:
@@ -115,9 +133,10 @@ class WanTransformerBlock(nn.Module):
         self.scale_shift_table = nn.Parameter(torch.randn(1, 6, dim) / dim ** 0.5)
 
     def forward(self, hidden_states: torch.Tensor, encoder_hidden_states: torch.Tensor, mod: torch.Tensor,
-                row_index: Optional[torch.Tensor], rows_per_group: int, rotary_emb) -> torch.Tensor:
+                row_index: Optional[torch.Tensor], rows_per_group: int, rotary_emb, text_kv=None) -> torch.Tensor:
         """``mod``: fp32 [R, 6*dim] = scale_shift_table + timestep_proj rows (shift, scale, gate, c_shift, c_scale,
-        c_gate). ``hidden_states`` [B, N, dim] is updated in place and returned."""
+        c_gate). ``hidden_states`` [B, N, dim] is updated in place and returned. ``text_kv``: this block's
+        pre-projected cross-attention (k, v) from a ``WanTextState`` (native processor only)."""
         x = hidden_states
         dim = x.shape[-1]
         shift, scale, gate = mod[:, 0:dim], mod[:, dim:2 * dim], mod[:, 2 * dim:3 * dim]
@@ -139,7 +158,7 @@ class WanTransformerBlock(nn.Module):
             h = x
         if isinstance(self.attn2.processor, FinoWanAttnProcessor):
             x = self.attn2(hidden_states=h, encoder_hidden_states=encoder_hidden_states,
-                           fino_residual=(x, None, None, 0))
+                           fino_residual=(x, None, None, 0), fino_text_kv=text_kv)
         else:
             a = self.attn2(hidden_states=h, encoder_hidden_states=encoder_hidden_states)
             x = ops.gate_residual(x, a.contiguous(), out=x)
@@ -225,7 +244,6 @@ class WanTransformer3DModel(ModelBase):
     def _conditioning(self, timestep: torch.Tensor, batch: int, tokens: int):
         """De-duplicated time MLP. Returns (temb_rows fp32-of-bf16 [R, D], proj_rows fp32-of-bf16 [R, 6D],
         row_index int32 [B*N] or None, rows_per_group)."""
-        ce = self.condition_embedder
         if timestep.ndim == 2:  # [B, N] per-token timesteps (wan 2.2 ti2v, transformer_wan.py:490-492)
             if timestep.shape != (batch, tokens):
                 raise ValueError(f"timestep shape {tuple(timestep.shape)} != (batch, tokens) = ({batch}, {tokens})")
@@ -240,6 +258,14 @@ class WanTransformer3DModel(ModelBase):
                 raise ValueError(f"timestep has {uniq.numel()} entries for batch {batch}")
             row_index = None
             rows_per_group = tokens
+        temb, proj = self.time_rows(uniq)
+        return temb, proj, row_index, rows_per_group
+
+    def time_rows(self, uniq: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Time MLP on distinct timestep values (fp32 [R]): (temb [R, D], timestep_proj [R, 6D]), fp32 holding the
+        bf16-rounded module outputs (transformer_wan.py:175-183). Row r is what the reference computes for every token
+        whose timestep is uniq[r]."""
+        ce = self.condition_embedder
         r = uniq.numel()
         te = ce.time_embedder
         emb = ops.timestep_embedding(uniq.contiguous(), ce.time_freq_dim, True, 0.0)  # :175
@@ -260,39 +286,84 @@ class WanTransformer3DModel(ModelBase):
             temb = temb_b.float()
             s = torch.nn.functional.silu(temb_b)
             proj = ops.linear(s, ce.time_proj.weight, ce.time_proj.bias).float()
-        return temb, proj, row_index, rows_per_group
+        return temb, proj
 
     # ------------------------------------------------------------------------------------------------------------
-    @torch.no_grad()
-    def forward(
-        self,
-        hidden_states: torch.Tensor,
-        timestep: torch.Tensor,
-        encoder_hidden_states: torch.Tensor,
-        encoder_hidden_states_image: Optional[torch.Tensor] = None,
-        return_dict: bool = True,
-        attention_kwargs: Optional[Dict[str, Any]] = None,
-    ) -> Union[Transformer2DModelOutput, Tuple[torch.Tensor]]:
-        if attention_kwargs is not None and attention_kwargs.get("scale", None) is not None:
-            logger.warning("Passing `scale` via `attention_kwargs` when not using the PEFT backend is ineffective.")
-        if encoder_hidden_states_image is not None:
-            raise NotImplementedError("encoder_hidden_states_image (Wan2.1 I2V) is not part of the FrameINO path")
-        if not hidden_states.is_cuda:
+    # step-invariant text work
+    @contextmanager
+    def cache_context(self, name: str):
+        """The reference pipeline wraps its two CFG forwards in ``cache_context("cond")`` / ``("uncond")``
+        (pipeline_wan_i2v_motion_FrameINO.py:862, :873). Here the name keys a ``WanTextState``: the text-embedder MLP
+        and every block's cross-attention K/V are computed on the first forward of a prompt and reused by the later
+        steps, as long as the same ``encoder_hidden_states`` memory (unchanged) and the same weights are passed."""
+        prev = self.__dict__.get("_fino_cache_name")
+        self.__dict__["_fino_cache_name"] = name
+        try:
+            yield
+        finally:
+            self.__dict__["_fino_cache_name"] = prev
+
+    def clear_text_cache(self) -> None:
+        self.__dict__["_fino_text_cache"] = {}
+
+    def _text_key(self, ehs: torch.Tensor):
+        def ident(t):
+            return None if t is None else (t.data_ptr(), t._version)
+
+        te = self.condition_embedder.text_embedder
+        parts = [ident(ehs), tuple(ehs.shape), tuple(ehs.stride()), ehs.dtype, ehs.device,
+                 ident(te.linear_1.weight), ident(te.linear_1.bias), ident(te.linear_2.weight), ident(te.linear_2.bias)]
+        for b in self.blocks:
+            a = b.attn2
+            parts.append((id(a.processor), ident(a.to_k.weight), ident(a.to_k.bias), ident(a.to_v.weight),
+                          ident(a.to_v.bias), ident(getattr(a.norm_k, "weight", None))))
+        return tuple(parts)
+
+    def prepare_text(self, encoder_hidden_states: torch.Tensor) -> WanTextState:
+        """Runs the text embedder (:185) and every block's cross-attention key/value projection + key norm once."""
+        if not encoder_hidden_states.is_cuda:
             raise RuntimeError("frameino_b200 has no CPU path: move the model and inputs to a CUDA device")
         dt = self.proj_out.weight.dtype
-        if dt != torch.bfloat16:
-            raise NotImplementedError(f"model dtype {dt}: call .to_inference_dtype(torch.bfloat16) first")
-        cfg = self.config
-        batch, channels, frames, height, width = hidden_states.shape
-        p_t, p_h, p_w = cfg.patch_size
-        ppf, pph, ppw = frames // p_t, height // p_h, width // p_w
-        tokens = ppf * pph * ppw
-        dim = cfg.num_attention_heads * cfg.attention_head_dim
+        ce = self.condition_embedder
+        text_in = encoder_hidden_states.to(dt)
+        t1, t2 = ce.text_embedder.linear_1, ce.text_embedder.linear_2
+        text = ops.linear(ops.linear(text_in, t1.weight, t1.bias, epilogue=ops.EPI_GELU_TANH), t2.weight, t2.bias)  # :185
+        kv: List[Optional[Tuple[torch.Tensor, torch.Tensor]]] = []
+        for b in self.blocks:
+            proc = b.attn2.processor
+            kv.append(proc.project_text(b.attn2, text) if isinstance(proc, FinoWanAttnProcessor) else None)
+        return WanTextState(text=text, kv=kv, key=self._text_key(encoder_hidden_states), source=encoder_hidden_states)
 
-        rotary_emb = self.rope(hidden_states)  # :484
-        hs = hidden_states.to(dt)
-        rows = ops.patchify(hs, (batch, channels, frames, height, width), hs.stride(), (p_t, p_h, p_w))
-        temb, proj, row_index, rows_per_group = self._conditioning(timestep, batch, tokens)
+    def _text_state(self, encoder_hidden_states: torch.Tensor) -> WanTextState:
+        name = self.__dict__.get("_fino_cache_name")
+        if name is None:
+            return self.prepare_text(encoder_hidden_states)
+        cache = self.__dict__.setdefault("_fino_text_cache", {})
+        hit = cache.get(name)
+        if hit is not None and hit.key == self._text_key(encoder_hidden_states):
+            return hit
+        state = self.prepare_text(encoder_hidden_states)
+        cache[name] = state
+        return state
+
+    # ------------------------------------------------------------------------------------------------------------
+    def forward_rows(self, rows: torch.Tensor, batch: int, grid: Tuple[int, int, int], conditioning,
+                     text_state: WanTextState) -> torch.Tensor:
+        """The transformer body on already patchified input: ``rows`` bf16 [batch * tokens, C_in*pt*ph*pw] (token order
+        (frame, height, width) of the ``grid`` = latent (frames, height, width)), ``conditioning`` =
+        (temb [R, D], timestep_proj [R, 6D], row_index int32 [batch*tokens] | None, rows_per_group) as ``time_rows``
+        produces them. Returns the proj_out rows bf16 [batch * tokens, pt*ph*pw*C_out] (:537), i.e. the model output
+        before the final un-patchify. ``forward`` = patchify + this + unpatchify; the fused sampler loop
+        (frameino_b200/sampling.py) calls it directly."""
+        cfg = self.config
+        p_t, p_h, p_w = cfg.patch_size
+        frames, height, width = grid
+        tokens = (frames // p_t) * (height // p_h) * (width // p_w)
+        dim = cfg.num_attention_heads * cfg.attention_head_dim
+        if rows.shape[0] != batch * tokens:
+            raise ValueError(f"rows has {rows.shape[0]} rows for batch {batch} x {tokens} tokens")
+        temb, proj, row_index, rows_per_group = conditioning
+        rotary_emb = self.rope.tables(frames, height, width)  # :484
 
         sp = self.sequence_parallel
         if sp is not None:  # Ulysses: every rank keeps a contiguous token slice (frameino_b200/ulysses.py)
@@ -308,11 +379,7 @@ class WanTransformer3DModel(ModelBase):
 
         pe = self.patch_embedding
         x = ops.linear(rows, pe.weight.view(dim, -1), pe.bias).view(batch, n_loc, dim)  # :486-487
-
-        ce = self.condition_embedder
-        text_in = encoder_hidden_states.to(dt)
-        t1, t2 = ce.text_embedder.linear_1, ce.text_embedder.linear_2
-        text = ops.linear(ops.linear(text_in, t1.weight, t1.bias, epilogue=ops.EPI_GELU_TANH), t2.weight, t2.bias)  # :185
+        text = text_state.text
 
         # per-layer modulation rows: scale_shift_table + timestep_proj.float()  (:317-331)
         mod_all = ops.build_mod_table(self._stacked_tables(), proj.contiguous(), len(self.blocks), 6 * dim)
@@ -322,7 +389,7 @@ class WanTransformer3DModel(ModelBase):
             taps["patch_embed"] = x.clone()
             taps["text"] = text.clone()
         for i, block in enumerate(self.blocks):  # :516-517
-            x = block(x, text, mod_all[i], row_index, rows_per_group, rotary_emb)
+            x = block(x, text, mod_all[i], row_index, rows_per_group, rotary_emb, text_state.kv[i])
             if taps is not None:
                 taps[f"blocks.{i}.out"] = x.clone()
 
@@ -334,10 +401,46 @@ class WanTransformer3DModel(ModelBase):
         y = ops.linear(h, self.proj_out.weight, self.proj_out.bias)  # :537
         if sp is not None:
             y = sp.gather_rows(y)
+        return y.view(batch * tokens, -1)
+
+    def _check_ready(self, t: torch.Tensor) -> torch.dtype:
+        if not t.is_cuda:
+            raise RuntimeError("frameino_b200 has no CPU path: move the model and inputs to a CUDA device")
+        dt = self.proj_out.weight.dtype
+        if dt != torch.bfloat16:
+            raise NotImplementedError(f"model dtype {dt}: call .to_inference_dtype(torch.bfloat16) first")
+        return dt
+
+    @torch.no_grad()
+    def forward(
+        self,
+        hidden_states: torch.Tensor,
+        timestep: torch.Tensor,
+        encoder_hidden_states: torch.Tensor,
+        encoder_hidden_states_image: Optional[torch.Tensor] = None,
+        return_dict: bool = True,
+        attention_kwargs: Optional[Dict[str, Any]] = None,
+    ) -> Union[Transformer2DModelOutput, Tuple[torch.Tensor]]:
+        if attention_kwargs is not None and attention_kwargs.get("scale", None) is not None:
+            logger.warning("Passing `scale` via `attention_kwargs` when not using the PEFT backend is ineffective.")
+        if encoder_hidden_states_image is not None:
+            raise NotImplementedError("encoder_hidden_states_image (Wan2.1 I2V) is not part of the FrameINO path")
+        dt = self._check_ready(hidden_states)
+        cfg = self.config
+        batch, channels, frames, height, width = hidden_states.shape
+        p_t, p_h, p_w = cfg.patch_size
+        tokens = (frames // p_t) * (height // p_h) * (width // p_w)
+
+        hs = hidden_states.to(dt)
+        rows = ops.patchify(hs, (batch, channels, frames, height, width), hs.stride(), (p_t, p_h, p_w))
+        conditioning = self._conditioning(timestep, batch, tokens)
+        text_state = self._text_state(encoder_hidden_states)
+        y = self.forward_rows(rows, batch, (frames, height, width), conditioning, text_state)
+
         c_out = y.shape[-1] // (p_t * p_h * p_w)
-        out = torch.empty(batch, c_out, frames, height, width, dtype=dt, device=x.device)
-        ops.unpatchify(y.view(batch * tokens, -1), out, (batch, c_out, frames, height, width), out.stride(),
-                       (p_t, p_h, p_w), channel_last=True)  # :539-543
+        out = torch.empty(batch, c_out, frames, height, width, dtype=dt, device=y.device)
+        ops.unpatchify(y, out, (batch, c_out, frames, height, width), out.stride(), (p_t, p_h, p_w),
+                       channel_last=True)  # :539-543
         if not return_dict:
             return (out,)
         return Transformer2DModelOutput(sample=out)

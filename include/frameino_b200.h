@@ -143,6 +143,27 @@ int fino_linear_small_m(const float* x, const void* w, const void* b, float* y, 
 int fino_build_mod_table(const float* table, const float* proj, float* out, int layers, int r, int cols,
                          int64_t table_layer_stride, void* stream);
 
+/* ---- denoise-loop glue of the Wan2.2 FrameINO sampler, one kernel before and one after the
+ * transformer forwards of a scheduler step. All 5-D tensors are contiguous float [b, c, frames, h, w]. ----
+ *
+ * rows[(b, f/pt, h/ph, w/pw), (c2, pt, ph, pw)] (bf16, row stride ld, c2 in [0, 2c)) = the patchified transformer input
+ *   c2 <  c, frame <  f : (1 - mask) * condition + mask * latents     pipeline_wan_i2v_motion_FrameINO.py:829-830
+ *   c2 <  c, frame >= f : id_latents[b, c2, frame - f]                 :854 (frame-wise ID concat)
+ *   c2 >= c             : traj_latents[b, c2 - c, frame]               :858 (channel-wise trajectory concat)
+ * mask is float [f, h, w] (the reference's [1,1,f,h,w] first_frame_mask); traj_latents has f + n_id frames;
+ * id_latents may be NULL when n_id == 0. Fuses the concat/cast chain with the patchify of transformer_wan.py:486. */
+int fino_wan_pack_model_input(const float* latents, const float* condition, const float* mask,
+                              const float* id_latents, const float* traj_latents, void* rows, int b, int c, int f,
+                              int n_id, int h, int w, int pt, int ph, int pw, int64_t ld, void* stream);
+
+/* latents += dsigma * (y_uncond + guidance * (y_cond - y_uncond)) over the f generated frames, reading the bf16
+ * proj_out rows [(b, (f+n_id)/pt, h/ph, w/pw), (pt, ph, pw, c)] of the two forwards (row stride ld): classifier-free
+ * guidance :882, ID-frame drop :886, flow-match Euler scheduler step :891, fused with the un-patchify of
+ * transformer_wan.py:539-543. y_uncond may be NULL (no guidance). fp32, no FMA contraction. */
+int fino_wan_cfg_euler_step(const void* y_cond, const void* y_uncond, int64_t ld, float* latents, int b, int c, int f,
+                            int n_id, int h, int w, int pt, int ph, int pw, float guidance, float dsigma,
+                            void* stream);
+
 /* out[b][a][:] = in[a][b][:] with `inner` contiguous bf16 elements (multiple of 8) per (a,b): the pack / unpack step
  * around the Ulysses head<->sequence all-to-all (new capability, no reference counterpart: SURVEY.md 8e). */
 int fino_swap01(const void* in, void* out, int64_t a, int64_t b, int64_t inner, void* stream);

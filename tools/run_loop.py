@@ -16,7 +16,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from frameino_b200 import synth  # noqa: E402
-from frameino_b200.sampling import wan_frameino_denoise  # noqa: E402
+from frameino_b200.sampling import wan_frameino_denoise, wan_frameino_denoise_fused  # noqa: E402
 from frameino_b200.ulysses import disable_sequence_parallel, enable_sequence_parallel  # noqa: E402
 
 
@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--height", type=int, default=704)
     ap.add_argument("--width", type=int, default=1280)
     ap.add_argument("--compare", action="store_true")
+    ap.add_argument("--fused", action="store_true", help="device-side loop glue (wan_frameino_denoise_fused)")
+    ap.add_argument("--both", action="store_true", help="time the plain and the fused loop, report both + max diff")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -43,7 +45,7 @@ def main():
     lat = torch.randn(1, c, lat_f, h, w, generator=g)
     cond = torch.zeros(1, c, lat_f, h, w)
     cond[:, :, 0] = torch.randn(1, c, h, w, generator=g)
-    mask = torch.ones(1, c, lat_f, h, w)
+    mask = torch.ones(1, 1, lat_f, h, w)  # the reference's [1,1,F,H,W] first_frame_mask (pipeline :529-532)
     mask[:, :, 0] = 0
     traj = torch.randn(1, c, lat_f + 1, h, w, generator=g)
     traj[:, :, lat_f:] = 0
@@ -53,24 +55,32 @@ def main():
     neg = torch.zeros(1, 512, cfg["text_dim"])
     tensors = [t.to(dev) for t in (lat, cond, mask, traj, idl)] + [pos.to(dev).bfloat16(), neg.to(dev).bfloat16()]
 
-    def run():
+    loop = wan_frameino_denoise_fused if args.fused else wan_frameino_denoise
+
+    def run(loop=loop):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        out = wan_frameino_denoise(model, *tensors, num_steps=args.steps)
+        out = loop(model, *tensors, num_steps=args.steps)
         e.record()
         torch.cuda.synchronize()
         return out, s.elapsed_time(e)
 
     if world > 1:
         enable_sequence_parallel(model)
-    run_warm = wan_frameino_denoise(model, *tensors, num_steps=1)  # warm-up
+    loop(model, *tensors, num_steps=1)  # warm-up
     out_sp, ms_sp = run()
-    res = {"n_gpus": world, "steps": args.steps, "forwards": 2 * args.steps, "loop_ms": ms_sp,
+    res = {"n_gpus": world, "steps": args.steps, "forwards": 2 * args.steps, "loop": loop.__name__, "loop_ms": ms_sp,
            "ms_per_forward": ms_sp / (2 * args.steps), "tokens": (lat_f + 1) * (h // 2) * (w // 2),
            "finite": bool(torch.isfinite(out_sp).all())}
+    if args.both:
+        other = wan_frameino_denoise if args.fused else wan_frameino_denoise_fused
+        other(model, *tensors, num_steps=1)
+        out_o, ms_o = run(other)
+        res[other.__name__ + "_loop_ms"] = ms_o
+        res["max_abs_diff_between_loops"] = float((out_o - out_sp).abs().max())
     if args.compare and world > 1:
         disable_sequence_parallel(model)
         if rank == 0:
