@@ -17,6 +17,11 @@
 // TMEM (512 columns): S0 [0,128) S1 [128,256) O0 [256,256+d) O1 [384,384+d); P_i (bf16) aliases S_i[0,64).
 // MMA issue order per KV tile j:  S0(j), PV1(j-1), S1(j), PV0(j)  -- so the tensor pipe works on one query
 // tile while the other tile's softmax runs on the MUFU/FMA pipes.
+// head_dim 64 (PSEP): the kernel is bound by the exponentials (256 FLOP per exp instead of 512), and O needs only 64
+// columns, so P_i gets its own columns (P0 [320,384), P1 [448,512)) and S_i(j+1) is issued as soon as the softmax
+// warps have pulled S_i(j) into registers (s_free barrier) instead of after P_i(j) V_j: the next scores are ready
+// before the current exponentials finish and the MUFU pipe never waits on the tensor pipe. Order: S0(j), S1(j),
+// PV0(j-1), PV1(j-1); pv_done barriers guard the reuse of P_i and the lazy O rescale.
 // Online softmax keeps (m, l) in registers; the O rescale is lazy (only when the running max grows by more
 // than 2^8, decided per warp), so the common path never touches O between MMAs.
 #include "common.cuh"
@@ -60,13 +65,20 @@ struct AttnCfg {
   static constexpr int kSmemBytes = kQBytes + 2 * kKVStages * kTileBytes + 1024 + 256;
 };
 
-// EMU   = exponentials per group of 8 computed on the FMA/ALU pipes (exp2_emu2) instead of MUFU ex2
+// EMU / EMU_B = exponentials per group of 8 (even / odd groups) computed on the FMA/ALU pipes (exp2_emu2) instead of
+//         MUFU ex2
 // SPLIT = P is published to the MMA warp in two 64-key halves so that P V starts while the second half is still in exp
-template <int HD, int EMU, bool SPLIT>
+// PSEP  = P in its own TMEM columns + early S issue (head_dim 64 only, see the header comment)
+// PING  = the two softmax warpgroups take turns on the exponential phase (named-barrier token): ptxas paces one warp's
+//         MUFU stream at the pipe's own rate (one ex2 per 8 cycles per SM sub-partition), so two warps of a
+//         sub-partition inside that phase together only queue up on the MUFU pipe while it then idles during their
+//         common load / max / store phases; alternating keeps it busy with one warp while the other does the rest
+template <int HD, int EMU, bool SPLIT, bool PSEP, int EMU_B, bool PING>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ AttnParams p) {
   using Cfg = AttnCfg<HD>;
+  static_assert(!PSEP || HD == 64, "separate P columns only fit next to 64-column O accumulators");
   constexpr int KST = Cfg::kKVStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -84,7 +96,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   auto p_full = [&](int i) { return bars + 8u * (3 + 4 * KST + i); };
   auto o_done = [&](int i) { return bars + 8u * (5 + 4 * KST + i); };
   auto p_half = [&](int i) { return bars + 8u * (7 + 4 * KST + i); };  // first 64 keys of P_i written (SPLIT)
-  const uint32_t tmem_ptr_smem = bars + 8u * (9 + 4 * KST);
+  auto s_free = [&](int i) { return bars + 8u * (9 + 4 * KST + i); };    // S_i pulled into registers (PSEP)
+  auto pv_done = [&](int i) { return bars + 8u * (11 + 4 * KST + i); };  // P_i V retired (PSEP)
+  const uint32_t tmem_ptr_smem = bars + 8u * (13 + 4 * KST);
+  const uint32_t zero_slot = tmem_ptr_smem + 8u;  // holds 0.0f (PING: a load ptxas cannot hoist above the token barrier)
 
   // shfl makes the warp index provably warp-uniform for ptxas: role branches become uniform branches and the issue
   // warps keep descriptors / addresses in uniform registers (CUTLASS canonical_warp_idx_sync idiom)
@@ -123,7 +138,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_init(p_full(i), 128);
       mbar_init(p_half(i), 128);
       mbar_init(o_done(i), 1);
+      mbar_init(s_free(i), 128);
+      mbar_init(pv_done(i), 1);
     }
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(zero_slot), "r"(0u) : "memory");
     fence_barrier_init();
   }
   if (warp == 10) {
@@ -179,6 +197,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BM, HD, 1);      // P V   : V is MN-major (d contiguous)
         const uint32_t tmem_s[2] = {tmem_base + 0u, tmem_base + 128u};
         const uint32_t tmem_o[2] = {tmem_base + 256u, tmem_base + 384u};
+        const uint32_t tmem_p[2] = {tmem_base + (PSEP ? 320u : 0u), tmem_base + (PSEP ? 448u : 128u)};
 
         // Descriptors are built once; per KV tile only the stage offset (in 16-byte descriptor units) is added.
         const uint64_t qdesc0 = make_sdesc_sw128(q_smem, 16, 1024);
@@ -197,7 +216,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const uint64_t vd = vdesc0 + (uint64_t)((uint32_t)vstage * kTileUnits);
 #pragma unroll
           for (int g = ks0 / 4; g < ks1 / 4; ++g)  // 64 keys per call; 16 keys = 16 V rows = 2048 B per MMA
-            umma_ts_x4_w(tmem_o[i], tmem_s[i] + g * 32, vd + (uint64_t)(g * 512), idesc_o,
+            umma_ts_x4_w(tmem_o[i], tmem_p[i] + g * 32, vd + (uint64_t)(g * 512), idesc_o,
                          (accumulate || g != ks0 / 4) ? 1u : 0u);
         };
 
@@ -206,6 +225,57 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         int stage = 0;        // K / V stage of tile j
         uint32_t phase = 0;
         int pstage = 0;       // V stage of tile j-1
+        if constexpr (PSEP) {
+          // P_i V_t for tile t (P published in two halves when SPLIT)
+          auto pv_tile = [&](int i, int vstage, int t) {
+            if (SPLIT) {
+              mbar_wait(p_half(i), (uint32_t)(t & 1), 53 + i);
+              tc_fence_after();
+              issue_pv(i, vstage, t > 0, 0, 4);
+              mbar_wait(p_full(i), (uint32_t)(t & 1), 50 + i);
+              tc_fence_after();
+              issue_pv(i, vstage, true, 4, 8);
+            } else {
+              mbar_wait(p_full(i), (uint32_t)(t & 1), 50 + i);
+              tc_fence_after();
+              issue_pv(i, vstage, t > 0, 0, 8);
+            }
+            tc_commit_w(pv_done(i));
+          };
+          uint32_t pphase = 0;
+          for (int j = 0; j < T; ++j) {
+            mbar_wait(k_full(stage), phase, 40 + stage);
+            tc_fence_after();
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              if (j > 0) {  // the softmax warps hold S_i(j-1) in registers: its columns can be overwritten
+                mbar_wait(s_free(i), (uint32_t)((j - 1) & 1), 56 + i);
+                tc_fence_after();
+              }
+              issue_s(i, stage);
+              tc_commit_w(s_full(i));
+            }
+            tc_commit_w(k_empty(stage));
+            if (j > 0) {
+              mbar_wait(v_full(pstage), pphase, 60 + pstage);
+              pv_tile(0, pstage, j - 1);
+              pv_tile(1, pstage, j - 1);
+              tc_commit_w(v_empty(pstage));
+            }
+            pstage = stage;
+            pphase = phase;
+            if (++stage == KST) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          mbar_wait(v_full(pstage), pphase, 60 + pstage);
+          pv_tile(0, pstage, T - 1);
+          tc_commit_w(o_done(0));
+          pv_tile(1, pstage, T - 1);
+          tc_commit_w(v_empty(pstage));
+          tc_commit_w(o_done(1));
+        } else {
         for (int j = 0; j < T; ++j) {
           mbar_wait(k_full(stage), phase, 40 + stage);
           tc_fence_after();
@@ -263,6 +333,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         }
         tc_commit_w(v_empty(pstage));
         tc_commit_w(o_done(1));
+        }  // !PSEP
       }
     }
   } else {
@@ -274,8 +345,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t t_s = tmem_base + lane_base + (wg ? 128u : 0u);
     const uint32_t t_o = tmem_base + lane_base + (wg ? 384u : 256u);
+    const uint32_t t_p = PSEP ? tmem_base + lane_base + (wg ? 448u : 320u) : t_s;
     const float sl2 = p.scale_log2;
 
+    if (PING && wg == 1) named_bar_arrive(1, 256);  // warpgroup 0 takes the first turn
     int keys_left = p.nk - j0 * ATT_BN;  // keys from this CTA's first KV tile to the end of the sequence
     float m_used = -INFINITY;  // running max (raw score units) the exponentials are referenced to
     float l_sum = 0.f;
@@ -289,6 +362,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tmem_ld_32x32b_x32(t_s + 64, s[2]);
       tmem_ld_32x32b_x32(t_s + 96, s[3]);
       tmem_wait_ld();
+      if (PSEP) {  // S_i(j) is in registers: the MMA warp may overwrite it with S_i(j+1)
+        tc_fence_before();
+        mbar_arrive(s_free(wg));
+      }
 
       const int valid = keys_left;  // keys of this tile that exist (>= 1)
       keys_left -= ATT_BN;
@@ -318,7 +395,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       } else {
         const bool need = (m_cand - m_used) * sl2 > ATT_RESCALE_THRESHOLD;
         if (__any_sync(0xffffffffu, need)) {
-          // PV_i(j-1) retired before S_i(j) was committed, so O_i is quiescent here.
+          // PV_i(j-1) retired before S_i(j) was committed, so O_i is quiescent here (PSEP: wait for it explicitly).
+          if (PSEP) {
+            mbar_wait(pv_done(wg), (uint32_t)((j - 1) & 1), 72 + wg);
+            tc_fence_after();
+          }
           const float alpha = need ? ex2_approx((m_used - m_cand) * sl2) : 1.0f;
           if (need) m_used = m_cand;
           l_sum *= alpha;
@@ -336,6 +417,37 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
       const float neg_m = -m_used * sl2;
       float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+      if (PSEP && j > 0) {  // P_i(j-1) V must have retired before P_i is overwritten
+        mbar_wait(pv_done(wg), (uint32_t)((j - 1) & 1), 74 + wg);
+        tc_fence_after();
+      }
+      // The scale-and-subtract of the elements that go through MUFU takes its addend from a shared-memory load placed
+      // after the token barrier, so that ptxas keeps the whole MUFU stream inside the turn (it moves plain arithmetic
+      // across bar.sync freely); the emulated elements' arithmetic stays free to run ahead of the turn.
+      float neg_m_turn = neg_m;
+      if (PING) {
+        // before the turn: the emulated exponentials (FMA/ALU pipes only), results parked in the score registers.
+        // ptxas would sink this arithmetic below the barrier; the barrier id is made to depend on every result (their
+        // sign bits, always 0: 2^x > 0) so that it has to be finished first.
+        uint32_t dep = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int e = 0; e < 32; e += 8)
+#pragma unroll
+            for (int i = 0; i < (((e >> 3) & 1) ? EMU_B : EMU); i += 2) {
+              float x0, x1, p0, p1;
+              ffma2(x0, x1, __uint_as_float(s[c][e + i]), __uint_as_float(s[c][e + i + 1]), sl2, sl2, neg_m, neg_m);
+              exp2_emu2(p0, p1, x0, x1);
+              s[c][e + i] = __float_as_uint(p0);
+              s[c][e + i + 1] = __float_as_uint(p1);
+              dep |= s[c][e + i] | s[c][e + i + 1];
+            }
+        named_bar_sync(1 + wg + (int)(dep >> 31), 256);  // my turn on the MUFU pipe
+        float z;
+        asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(z) : "r"(zero_slot) : "memory");
+        neg_m_turn = neg_m + z;
+      }
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         uint32_t pk[32];
@@ -344,15 +456,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           const int c = half * 2 + c2;
 #pragma unroll
           for (int e = 0; e < 32; e += 8) {
+            const int emu = ((e >> 3) & 1) ? EMU_B : EMU;
             float x[8], pv[8];
 #pragma unroll
-            for (int i = 0; i < 8; i += 2)  // x = s * scale_log2 - m * scale_log2 (packed FFMA2)
-              ffma2(x[i], x[i + 1], __uint_as_float(s[c][e + i]), __uint_as_float(s[c][e + i + 1]), sl2, sl2, neg_m,
-                    neg_m);
+            for (int i = 0; i < 8; i += 2) {  // x = s * scale_log2 - m * scale_log2 (packed FFMA2)
+              if (PING && i < emu) continue;  // already exponentiated
+              const float nm = (i < emu) ? neg_m : neg_m_turn;
+              ffma2(x[i], x[i + 1], __uint_as_float(s[c][e + i]), __uint_as_float(s[c][e + i + 1]), sl2, sl2, nm, nm);
+            }
 #pragma unroll
             for (int i = 0; i < 8; i += 2) {
-              if (i < EMU) {
-                exp2_emu2(pv[i], pv[i + 1], x[i], x[i + 1]);
+              if (i < emu) {
+                if (PING) {
+                  pv[i] = __uint_as_float(s[c][e + i]);
+                  pv[i + 1] = __uint_as_float(s[c][e + i + 1]);
+                } else {
+                  exp2_emu2(pv[i], pv[i + 1], x[i], x[i + 1]);
+                }
               } else {
                 pv[i] = ex2_approx(x[i]);
                 pv[i + 1] = ex2_approx(x[i + 1]);
@@ -366,8 +486,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             for (int i = 0; i < 8; i += 2) pk[c2 * 16 + (e + i) / 2] = pack_bf16x2(pv[i], pv[i + 1]);
           }
         }
-        // P (bf16, 2 keys per 32-bit column) aliases S_i columns [0,64)
-        tmem_st_32x32b_x32(t_s + half * 32, pk);
+        // P (bf16, 2 keys per 32-bit column) aliases S_i columns [0,64) / has its own columns (PSEP)
+        if (PING && half == 1) named_bar_arrive(1 + (wg ^ 1), 256);  // exponentials issued: the other group's turn
+        tmem_st_32x32b_x32(t_p + half * 32, pk);
         if (SPLIT && half == 0) {
           tmem_wait_st();
           tc_fence_before();
@@ -380,6 +501,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_arrive(p_full(wg));
     }
 
+    if (PING && wg == 0) named_bar_sync(1, 256);  // absorb warpgroup 1's last hand-over (barrier left balanced)
     // ---------------- epilogue: O / l -> bf16 -> shared (swizzled) -> coalesced global rows ----------------
     // Every S_i MMA has retired when o_done(i) fires, so the Q_i tile in shared memory is dead: each warp stages its
     // 32 output rows there (16-byte chunks XOR-swizzled by row, conflict-free both ways) and then writes whole
@@ -530,19 +652,20 @@ static int attn_workspace(size_t bytes, void** out) {
   return FINO_OK;
 }
 
-template <int HD, int EMU, bool SPLIT>
+template <int HD, int EMU, bool SPLIT, bool PSEP = false, int EMU_B = EMU, bool PING = false>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        int batch, cudaStream_t stream) {
   using Cfg = AttnCfg<HD>;
   static bool configured = false;
   if (!configured) {
-    FINO_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HD, EMU, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Cfg::kSmemBytes));
+    FINO_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HD, EMU, SPLIT, PSEP, EMU_B, PING>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
   const int n_tiles = p.q_tiles * p.heads * batch;
   const int n_part = (n_tiles - p.n_full) * p.splits;
-  attn_fwd_kernel<HD, EMU, SPLIT><<<p.n_full + n_part, ATT_THREADS, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
+  attn_fwd_kernel<HD, EMU, SPLIT, PSEP, EMU_B, PING>
+      <<<p.n_full + n_part, ATT_THREADS, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
   FINO_CHECK_CUDA(cudaGetLastError());
   if (n_part > 0) {
     const int rows_total = (n_tiles - p.n_full) * 2 * ATT_BM;
@@ -597,8 +720,22 @@ static int dispatch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
     case 3: return launch_attn<HD, 2, false>(tq, tk, tv, p, batch, stream);  // 2/8 emulated
     case 4: return launch_attn<HD, 2, true>(tq, tk, tv, p, batch, stream);
     case 5: return launch_attn<HD, 4, true>(tq, tk, tv, p, batch, stream);   // 4/8 emulated
-    default: return launch_attn<HD, 2, true>(tq, tk, tv, p, batch, stream);
+    default: break;
   }
+  if constexpr (HD == 64) {  // separate P columns + early S issue (variants 6..9; 0 = the measured best of them)
+    switch (g_attn_variant) {
+      case 6: return launch_attn<HD, 2, true, true, 2>(tq, tk, tv, p, batch, stream);   // 2/8 emulated
+      case 7: return launch_attn<HD, 2, true, true, 4>(tq, tk, tv, p, batch, stream);   // 3/8
+      case 8: return launch_attn<HD, 4, true, true, 4>(tq, tk, tv, p, batch, stream);   // 4/8
+      case 9: return launch_attn<HD, 2, false, true, 4>(tq, tk, tv, p, batch, stream);  // 3/8, P published once
+      case 10: return launch_attn<HD, 2, true, true, 2, true>(tq, tk, tv, p, batch, stream);   // 2/8 + turns
+      case 11: return launch_attn<HD, 2, false, true, 2, true>(tq, tk, tv, p, batch, stream);  // 2/8 + turns, no split
+      case 12: return launch_attn<HD, 0, false, true, 0, true>(tq, tk, tv, p, batch, stream);  // all MUFU + turns
+      case 13: return launch_attn<HD, 2, false, true, 4, true>(tq, tk, tv, p, batch, stream);  // 3/8 + turns
+      default: return launch_attn<HD, 2, true, true, 2, true>(tq, tk, tv, p, batch, stream);  // = variant 10
+    }
+  }
+  return launch_attn<HD, 2, true>(tq, tk, tv, p, batch, stream);
 }
 
 // o_owners[num_owners]: output buffers; rows [g*rows_per_owner, (g+1)*rows_per_owner) go to owner g (see AttnParams).

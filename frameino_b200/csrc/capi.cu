@@ -215,8 +215,8 @@ int fino_gemm_plan(int64_t m, int n, int k, int sms, int mode, int* num_full, in
 }
 
 int fino_attention_set_variant(int variant) {
-  if (variant < 0 || variant > 5) {
-    fino::set_last_error("fino_attention_set_variant: variant %d out of range (0..5)", variant);
+  if (variant < 0 || variant > 15) {
+    fino::set_last_error("fino_attention_set_variant: variant %d out of range (0..15)", variant);
     return fino::FINO_ERR_INVALID;
   }
   fino::attention_set_variant(variant);

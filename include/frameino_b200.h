@@ -69,7 +69,7 @@ int fino_attention_fwd(const void* q, const void* k, const void* v, void* o, int
                        int64_t o_row_stride, int64_t q_batch_stride, int64_t k_batch_stride, int64_t v_batch_stride,
                        int64_t o_batch_stride, float scale, void* stream);
 
-/* Tuning / test hook: scheduling variant of the attention kernel (0 = default; 1..5 see attention_tcgen05.cu). */
+/* Tuning / test hook: scheduling variant of the attention kernel (0 = default; 1..9 see attention_tcgen05.cu; 6..9 apply to head_dim 64 only). */
 int fino_attention_set_variant(int variant);
 
 /* Work decomposition of fino_attention_fwd. The kernel runs one CTA per 256-query-row tile of one (batch, head); when

@@ -286,6 +286,25 @@ def test_attention_kv_split_matches_oracle_and_single_pass(ops, hd, splits):
         ops.attention_set_split(-1)
 
 
+@pytest.mark.parametrize("hd,variant", [(128, v) for v in range(1, 6)] + [(64, v) for v in range(1, 14)])
+def test_attention_scheduling_variants_agree(ops, hd, variant):
+    """Every scheduling variant behind fino_attention_set_variant (exponentials on MUFU vs FMA pipes, split P
+    publication, separate P columns + early S issue and softmax turn-taking at head_dim 64) computes the same function:
+    ragged shapes, peaky scores (lazy rescale), KV split on top."""
+    try:
+        ops.attention_set_variant(variant)
+        for (b, h, nq, nk, scale, split) in [(1, 2, 300, 1000, 1.0, -1), (2, 3, 513, 897, 2.5, -1), (1, 1, 64, 129, 1.0, -1),
+                                             (1, 2, 700, 2100, 2.5, 3)]:
+            dm = h * hd
+            q, k, v = bf(b, nq, dm, scale=scale), bf(b, nk, dm, scale=scale, seed=1), bf(b, nk, dm, seed=2)
+            ops.attention_set_split(split)
+            out = ops.attention(q.cuda(), k.cuda(), v.cuda(), h)
+            assert rel_err(out, _sdpa_ref(q, k, v, h)) <= BF16_TOL, (variant, b, h, nq, nk)
+    finally:
+        ops.attention_set_variant(0)
+        ops.attention_set_split(-1)
+
+
 def test_attention_auto_split_on_a_partial_wave(ops):
     """Automatic mode on a shape whose tile count leaves a partly filled last wave (the 8-way Ulysses situation)."""
     sms = torch.cuda.get_device_properties(0).multi_processor_count
