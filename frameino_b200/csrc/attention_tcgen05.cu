@@ -26,6 +26,7 @@
 // than 2^8, decided per warp), so the common path never touches O between MMAs.
 #include "common.cuh"
 #include "ptx.cuh"
+#include <type_traits>
 
 namespace fino {
 
@@ -51,6 +52,7 @@ struct AttnParams {
   // along the KV axis: CTA n_full + r handles KV tiles [s*T/S, (s+1)*T/S) of tile n_full + r/S (s = r%S) and writes an
   // un-normalised fp32 partial (O, m, l) to the workspace; attn_combine_kernel merges them. splits == 1: no partials.
   int q_tiles, n_full, splits;
+  int tile_rows;  // query rows per CTA tile: 256 (attn_fwd_kernel) or 512 (attn64x4_fwd_kernel)
   float* ws_o;    // [(tile - n_full)*splits + s][256][HD] fp32
   float2* ws_ml;  // [(tile - n_full)*splits + s][256] (running max in raw score units, row sum)
 };
@@ -584,23 +586,23 @@ __global__ void __launch_bounds__(256) attn_combine_kernel(const __grid_constant
   const int gw = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (gw >= rows_total) return;
-  const int tl = gw / (2 * ATT_BM), r = gw % (2 * ATT_BM);
+  const int tl = gw / p.tile_rows, r = gw % p.tile_rows;
   const int tile = p.n_full + tl;
   const int qt = tile % p.q_tiles;
   const int head = (tile / p.q_tiles) % p.heads;
   const int batch = tile / (p.q_tiles * p.heads);
-  const int qrow = qt * (2 * ATT_BM) + r;
+  const int qrow = qt * p.tile_rows + r;
   if (qrow >= p.nq) return;
   constexpr int CPL = HD / 32;  // columns per lane
   const int S = p.splits;
   float mmax = -INFINITY;
-  for (int s = 0; s < S; ++s) mmax = fmaxf(mmax, p.ws_ml[(int64_t)(tl * S + s) * (2 * ATT_BM) + r].x);
+  for (int s = 0; s < S; ++s) mmax = fmaxf(mmax, p.ws_ml[(int64_t)(tl * S + s) * p.tile_rows + r].x);
   float acc[CPL];
 #pragma unroll
   for (int i = 0; i < CPL; ++i) acc[i] = 0.f;
   float l = 0.f;
   for (int s = 0; s < S; ++s) {
-    const int64_t prow = (int64_t)(tl * S + s) * (2 * ATT_BM) + r;
+    const int64_t prow = (int64_t)(tl * S + s) * p.tile_rows + r;
     const float2 ml = p.ws_ml[prow];
     const float w = ex2_approx((ml.x - mmax) * p.scale_log2);
     l += w * ml.y;
@@ -668,8 +670,414 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
       <<<p.n_full + n_part, ATT_THREADS, Cfg::kSmemBytes, stream>>>(tq, tk, tv, p);
   FINO_CHECK_CUDA(cudaGetLastError());
   if (n_part > 0) {
-    const int rows_total = (n_tiles - p.n_full) * 2 * ATT_BM;
+    const int rows_total = (n_tiles - p.n_full) * p.tile_rows;
     attn_combine_kernel<HD><<<(rows_total + 7) / 8, 256, 0, stream>>>(p, rows_total);
+    FINO_CHECK_CUDA(cudaGetLastError());
+  }
+  return FINO_OK;
+}
+
+// =====================================================================================================================
+// head_dim 64, four query tiles per CTA against 64-key steps (CogVideoX: 48 heads x 64).
+//
+// At head_dim 64 the kernel is bound by the exponentials, not by the tensor pipe (256 FLOP per exp; measured pipe
+// rates in tools/microbench/pipes.cu: one ex2 warp-instruction per 8 cycles per SM sub-partition), and in the two-tile
+// kernel above each softmax warp's serial chain per tile (TMEM load, max, exponentials, pack, TMEM store, then the
+// P V / next-S round trip through the MMA warp) is far longer than two warps per sub-partition can hide (ncu: MUFU
+// pipe 58-62 % busy, profiles/r01_attn_d64_*). This kernel runs FOUR 128-row query tiles per CTA against 64-key steps,
+// i.e. four softmax warps per sub-partition, each with a half-length chain, served round-robin by the MMA warp:
+//   warps 0-15  softmax warpgroups, one per query tile (thread == query row, TMEM lane == row)
+//   warp  16    TMA producer (Q tiles once, then a 6-stage ring of [64 keys x 64] K and V tiles)
+//   warp  17    TMEM allocator + MMA issuer: per step j, for each tile i:  O_i += P_i(j-1) V(j-1);  S_i(j) = Q_i K(j)^T
+//   warps 18-19 spare (the fifth warpgroup exists so that setmaxnreg can move its registers: the kernel launches at 96
+//               registers per thread, the fifth group drops to 32 and the softmax warps rise to 112)
+// TMEM (512 columns): tile i owns [128 i, 128 i + 128): S_i fp32 [0,64), P_i (bf16) aliases S_i [0,32), O_i [64,128).
+// The softmax step reads the scores in two passes (row maximum over all 64, then the exponentials 32 at a time with
+// the second half read from TMEM again): holding 64 scores next to the packed P and the MUFU latency window spilled.
+// The ragged last step of the sequence is a separate instantiation of the step body, so the common path has no
+// conditional writes to the score registers.
+// Measured at the CogVideoX shape (19 126 x 19 126, 48 heads), isolated: 956 TFLOP/s (two-tile kernel: 820; with P in
+// its own columns + MUFU turn-taking: 885). Dead ends kept out of the tree: three tiles with P in its own columns and
+// early S issue (794: three warps per sub-partition hide less than four), the same with a polling MMA scheduler
+// instead of the fixed round-robin (527: a dozen mbarrier probes per pass put ~400 cycles into every round trip).
+// Work decomposition, partials and the output-owner scatter are those of attn_fwd_kernel with 512-row tiles.
+// =====================================================================================================================
+constexpr int A64_NT = 4;
+constexpr int A64_BN = 64;
+constexpr int A64_THREADS = 640;
+constexpr int A64_KST = 6;
+constexpr int A64_QTILE_BYTES = ATT_BM * 64 * 2;   // 16 KB
+constexpr int A64_KVTILE_BYTES = A64_BN * 64 * 2;  // 8 KB
+constexpr int A64_SMEM_BYTES = A64_NT * A64_QTILE_BYTES + 2 * A64_KST * A64_KVTILE_BYTES + 1024 + 512;
+constexpr int A64_SOFTMAX_WARPS = 4 * A64_NT;
+__host__ __device__ constexpr uint32_t a64_col_s(int i) { return 128u * i; }
+__host__ __device__ constexpr uint32_t a64_col_p(int i) { return 128u * i; }
+__host__ __device__ constexpr uint32_t a64_col_o(int i) { return 128u * i + 64u; }
+
+template <int EMU, int EMU_B>
+__global__ void __launch_bounds__(A64_THREADS, 1)
+attn64x4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                    const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ AttnParams p) {
+  constexpr int HD = 64;
+  constexpr int KST = A64_KST;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_smem = smem_base;
+  const uint32_t k_smem = q_smem + A64_NT * A64_QTILE_BYTES;
+  const uint32_t v_smem = k_smem + KST * A64_KVTILE_BYTES;
+  const uint32_t bars = v_smem + KST * A64_KVTILE_BYTES;
+  const uint32_t q_full = bars;
+  auto k_full = [&](int s) { return bars + 8u * (1 + s); };
+  auto k_empty = [&](int s) { return bars + 8u * (1 + KST + s); };
+  auto v_full = [&](int s) { return bars + 8u * (1 + 2 * KST + s); };
+  auto v_empty = [&](int s) { return bars + 8u * (1 + 3 * KST + s); };
+  auto s_full = [&](int i) { return bars + 8u * (1 + 4 * KST + i); };
+  auto p_full = [&](int i) { return bars + 8u * (1 + 4 * KST + A64_NT + i); };
+  auto o_done = [&](int i) { return bars + 8u * (1 + 4 * KST + 2 * A64_NT + i); };
+  const uint32_t tmem_ptr_smem = bars + 8u * (1 + 4 * KST + 3 * A64_NT);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  int tile = blockIdx.x, j0 = 0, T = p.num_kv_tiles;
+  const bool partial = (int)blockIdx.x >= p.n_full;
+  if (partial) {
+    const int r = (int)blockIdx.x - p.n_full;
+    const int sp = r % p.splits;
+    tile = p.n_full + r / p.splits;
+    j0 = (int)(((int64_t)sp * p.num_kv_tiles) / p.splits);
+    T = (int)(((int64_t)(sp + 1) * p.num_kv_tiles) / p.splits) - j0;
+  }
+  const int qt = tile % p.q_tiles;
+  const int head = (tile / p.q_tiles) % p.heads;
+  const int batch = tile / (p.q_tiles * p.heads);
+  const int q0 = qt * (A64_NT * ATT_BM);
+
+  if (warp == A64_SOFTMAX_WARPS && lane == 0) {
+    prefetch_tmap(&tmap_q);
+    prefetch_tmap(&tmap_k);
+    prefetch_tmap(&tmap_v);
+  }
+  if (warp == A64_SOFTMAX_WARPS + 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < KST; ++s) {
+      mbar_init(k_full(s), 1);
+      mbar_init(k_empty(s), 1);
+      mbar_init(v_full(s), 1);
+      mbar_init(v_empty(s), 1);
+    }
+    for (int i = 0; i < A64_NT; ++i) {
+      mbar_init(s_full(i), 1);
+      mbar_init(p_full(i), 128);
+      mbar_init(o_done(i), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == A64_SOFTMAX_WARPS + 1) {
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_smem));
+
+  if (warp >= A64_SOFTMAX_WARPS) setmaxnreg_dec<32>();  // 4 warps x 64 registers go to the 16 softmax warps (96 -> 112)
+  if (warp == A64_SOFTMAX_WARPS) {
+    // ============================ TMA producer ============================
+    if (lane == 0) {
+      const int c_head = head * HD;
+      mbar_arrive_expect_tx(q_full, A64_NT * A64_QTILE_BYTES);
+#pragma unroll
+      for (int i = 0; i < A64_NT; ++i)
+        tma_load_3d(q_smem + i * A64_QTILE_BYTES, &tmap_q, q_full, c_head, q0 + i * ATT_BM, batch);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < T; ++j) {
+        mbar_wait_relaxed(k_empty(stage), phase ^ 1u, 10 + stage);
+        mbar_arrive_expect_tx(k_full(stage), A64_KVTILE_BYTES);
+        tma_load_3d(k_smem + stage * A64_KVTILE_BYTES, &tmap_k, k_full(stage), c_head, (j0 + j) * A64_BN, batch);
+        mbar_wait_relaxed(v_empty(stage), phase ^ 1u, 20 + stage);
+        mbar_arrive_expect_tx(v_full(stage), A64_KVTILE_BYTES);
+        tma_load_3d(v_smem + stage * A64_KVTILE_BYTES, &tmap_v, v_full(stage), c_head, (j0 + j) * A64_BN, batch);
+        if (++stage == KST) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == A64_SOFTMAX_WARPS + 1) {
+    // ============================ MMA issuer ============================
+    constexpr uint32_t idesc_s = make_idesc_bf16(ATT_BM, A64_BN, 0);  // Q K^T : both K-major
+    constexpr uint32_t idesc_o = make_idesc_bf16(ATT_BM, HD, 1);      // P V   : V is MN-major (d contiguous)
+    const uint64_t qdesc0 = make_sdesc_sw128(q_smem, 16, 1024);
+    const uint64_t kdesc0 = make_sdesc_sw128(k_smem, 16, 1024);
+    const uint64_t vdesc0 = make_sdesc_sw128(v_smem, A64_KVTILE_BYTES, 1024);
+    constexpr uint32_t kQUnits = A64_QTILE_BYTES >> 4, kKVUnits = A64_KVTILE_BYTES >> 4;
+
+    mbar_wait(q_full, 0, 30);
+    mbar_wait(k_full(0), 0, 40);
+    tc_fence_after();
+#pragma unroll
+    for (int i = 0; i < A64_NT; ++i) {
+      umma_ss_x4_w(tmem_base + a64_col_s(i), qdesc0 + (uint64_t)(i * kQUnits), kdesc0, idesc_s, 0u);
+      tc_commit_w(s_full(i));
+    }
+    tc_commit_w(k_empty(0));
+    int stage = 1 % KST;  // K stage of step j
+    uint32_t phase = 0;
+    int pstage = 0;       // V stage of step j-1
+    uint32_t pphase = 0;
+    for (int j = 1; j < T; ++j) {
+      mbar_wait(k_full(stage), phase, 40 + stage);
+      mbar_wait(v_full(pstage), pphase, 60 + pstage);
+      tc_fence_after();
+      const uint64_t kd = kdesc0 + (uint64_t)((uint32_t)stage * kKVUnits);
+      const uint64_t vd = vdesc0 + (uint64_t)((uint32_t)pstage * kKVUnits);
+#pragma unroll
+      for (int i = 0; i < A64_NT; ++i) {
+        mbar_wait(p_full(i), (uint32_t)((j - 1) & 1), 50 + i);
+        tc_fence_after();
+        umma_ts_x4_w(tmem_base + a64_col_o(i), tmem_base + a64_col_p(i), vd, idesc_o, j - 1 > 0 ? 1u : 0u);
+        umma_ss_x4_w(tmem_base + a64_col_s(i), qdesc0 + (uint64_t)(i * kQUnits), kd, idesc_s, 0u);
+        tc_commit_w(s_full(i));
+      }
+      tc_commit_w(k_empty(stage));
+      tc_commit_w(v_empty(pstage));
+      pstage = stage;
+      pphase = phase;
+      if (++stage == KST) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+    mbar_wait(v_full(pstage), pphase, 60 + pstage);
+    tc_fence_after();
+    {
+      const uint64_t vd = vdesc0 + (uint64_t)((uint32_t)pstage * kKVUnits);
+#pragma unroll
+      for (int i = 0; i < A64_NT; ++i) {
+        mbar_wait(p_full(i), (uint32_t)((T - 1) & 1), 50 + i);
+        tc_fence_after();
+        umma_ts_x4_w(tmem_base + a64_col_o(i), tmem_base + a64_col_p(i), vd, idesc_o, T - 1 > 0 ? 1u : 0u);
+        tc_commit_w(o_done(i));
+      }
+      tc_commit_w(v_empty(pstage));
+    }
+  } else if (warp < A64_SOFTMAX_WARPS) {
+    // ============================ softmax warpgroups ============================
+    setmaxnreg_inc<112>();
+    const int wg = warp >> 2;   // query tile handled by this warpgroup
+    const int quad = warp & 3;  // TMEM lane quadrant
+    const int row_in_tile = quad * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t t_s = tmem_base + lane_base + a64_col_s(wg);
+    const uint32_t t_p = tmem_base + lane_base + a64_col_p(wg);
+    const uint32_t t_o = tmem_base + lane_base + a64_col_o(wg);
+    const float sl2 = p.scale_log2;
+
+    int keys_left = p.nk - j0 * A64_BN;
+    float m_used = -INFINITY;
+    float l_sum = 0.f;
+
+    // One KV step. Two instantiations: the ragged last step of the sequence (keys past nk get -inf) is a separate copy
+    // of the body, so that the common path has no conditional writes to the score registers (a branch around the
+    // masking makes ptxas keep the scores in local memory).
+    auto step = [&](int j, auto ragged) {
+      constexpr bool kRagged = decltype(ragged)::value;
+      mbar_wait(s_full(wg), (uint32_t)(j & 1), 70 + wg);
+      tc_fence_after();
+      // Pass 1: row maximum over the 64 scores. Only the first 32 stay in registers; the second half is read from TMEM
+      // again for its exponentials (a second 4 KB tcgen05.ld per warp is cheaper than holding 64 scores next to the
+      // packed P, the exponential temporaries and the MUFU latency window in 112 registers — that version spilled).
+      uint32_t s0[32];
+      float tile_max;
+      {
+        uint32_t s1[32];
+        tmem_ld_32x32b_x32(t_s + 0, s0);
+        tmem_ld_32x32b_x32(t_s + 32, s1);
+        tmem_wait_ld();
+        if constexpr (kRagged) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            if (e >= keys_left) s0[e] = 0xff800000u;  // -inf
+            if (32 + e >= keys_left) s1[e] = 0xff800000u;
+          }
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s0[e + 0]), __uint_as_float(s1[e + 0])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s0[e + 1]), __uint_as_float(s1[e + 1])));
+          mx2 = fmaxf(mx2, fmaxf(__uint_as_float(s0[e + 2]), __uint_as_float(s1[e + 2])));
+          mx3 = fmaxf(mx3, fmaxf(__uint_as_float(s0[e + 3]), __uint_as_float(s1[e + 3])));
+        }
+        tile_max = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      }
+      const float m_cand = fmaxf(m_used, tile_max);
+
+      if (j == 0) {
+        m_used = m_cand;
+      } else {
+        const bool need = (m_cand - m_used) * sl2 > ATT_RESCALE_THRESHOLD;
+        if (__any_sync(0xffffffffu, need)) {
+          // P_i V (j-1) was issued before S_i(j) and retired before s_full fired (in-order pipe): O_i is quiescent.
+          const float alpha = need ? ex2_approx((m_used - m_cand) * sl2) : 1.0f;
+          if (need) m_used = m_cand;
+          l_sum *= alpha;
+#pragma unroll
+          for (int c = 0; c < HD / 16; ++c) {
+            uint32_t o[16];
+            tmem_ld_32x32b_x16(t_o + c * 16, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            tmem_st_32x32b_x16(t_o + c * 16, o);
+          }
+        }
+      }
+
+      const float neg_m = -m_used * sl2;
+      float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (c == 1) {  // pass 2 for the second half: scores [32,64) again
+          tmem_ld_32x32b_x32(t_s + 32, s0);
+          tmem_wait_ld();
+          if constexpr (kRagged) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (32 + e >= keys_left) s0[e] = 0xff800000u;
+          }
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int e = 0; e < 32; e += 8) {
+          const int emu = ((e >> 3) & 1) ? EMU_B : EMU;
+          float x[8], pv[8];
+#pragma unroll
+          for (int i = 0; i < 8; i += 2)
+            ffma2(x[i], x[i + 1], __uint_as_float(s0[e + i]), __uint_as_float(s0[e + i + 1]), sl2, sl2, neg_m, neg_m);
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            if (i < emu) {
+              exp2_emu2(pv[i], pv[i + 1], x[i], x[i + 1]);
+            } else {
+              pv[i] = ex2_approx(x[i]);
+              pv[i + 1] = ex2_approx(x[i + 1]);
+            }
+          }
+          fadd2(sum0, sum1, sum0, sum1, pv[0], pv[1]);
+          fadd2(sum2, sum3, sum2, sum3, pv[2], pv[3]);
+          fadd2(sum0, sum1, sum0, sum1, pv[4], pv[5]);
+          fadd2(sum2, sum3, sum2, sum3, pv[6], pv[7]);
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) pk[(e + i) / 2] = pack_bf16x2(pv[i], pv[i + 1]);
+        }
+        // P (bf16, 2 keys per 32-bit column) over S_i columns [0,32), 16 columns per half. Half 0 lands on score
+        // columns that are already in registers; the scores of half 1 sit in columns [32,64), untouched by it.
+        tmem_st_32x32b_x16(t_p + c * 16, pk);
+      }
+      l_sum += (sum0 + sum1) + (sum2 + sum3);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(p_full(wg));
+    };
+    for (int j = 0; j < T; ++j) {
+      if (keys_left >= A64_BN)
+        step(j, std::false_type{});
+      else
+        step(j, std::true_type{});
+      keys_left -= A64_BN;
+    }
+
+    // ---------------- epilogue (as attn_fwd_kernel: staged through the dead Q tile, coalesced row stores) -----------
+    mbar_wait(o_done(wg), 0, 80 + wg);
+    tc_fence_after();
+    if (partial) {
+      const int64_t prow =
+          (int64_t)((int)blockIdx.x - p.n_full) * (A64_NT * ATT_BM) + wg * ATT_BM + row_in_tile;
+      float4* dst = reinterpret_cast<float4*>(p.ws_o + prow * HD);
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(t_o + c * 32, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          dst[c * 8 + e] = make_float4(__uint_as_float(o[4 * e]), __uint_as_float(o[4 * e + 1]),
+                                       __uint_as_float(o[4 * e + 2]), __uint_as_float(o[4 * e + 3]));
+      }
+      p.ws_ml[prow] = make_float2(m_used, l_sum);
+    } else {
+      const float inv_l = 1.0f / l_sum;
+      constexpr int CH = HD / 8;    // 16-byte chunks per output row
+      constexpr int RPI = 32 / CH;  // rows per store instruction
+      const uint32_t stage = q_smem + wg * A64_QTILE_BYTES + (uint32_t)(quad * 32) * (HD * 2);
+      const uint32_t my_row = stage + (uint32_t)lane * (HD * 2);
+#pragma unroll
+      for (int c = 0; c < HD / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld_32x32b_x32(t_o + c * 32, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t w0 = pack_bf16x2(__uint_as_float(o[8 * e + 0]) * inv_l, __uint_as_float(o[8 * e + 1]) * inv_l);
+          const uint32_t w1 = pack_bf16x2(__uint_as_float(o[8 * e + 2]) * inv_l, __uint_as_float(o[8 * e + 3]) * inv_l);
+          const uint32_t w2 = pack_bf16x2(__uint_as_float(o[8 * e + 4]) * inv_l, __uint_as_float(o[8 * e + 5]) * inv_l);
+          const uint32_t w3 = pack_bf16x2(__uint_as_float(o[8 * e + 6]) * inv_l, __uint_as_float(o[8 * e + 7]) * inv_l);
+          const uint32_t chunk = (uint32_t)(c * 4 + e) ^ (uint32_t)(lane & (CH - 1) & 7);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + chunk * 16), "r"(w0), "r"(w1),
+                       "r"(w2), "r"(w3)
+                       : "memory");
+        }
+      }
+      __syncwarp();
+      const int sub = lane / CH;
+      const int ch = lane % CH;
+#pragma unroll 4
+      for (int it = 0; it < 32 / RPI; ++it) {
+        const int r = it * RPI + sub;
+        const int qrow = q0 + wg * ATT_BM + quad * 32 + r;
+        uint4 w;
+        const uint32_t src = stage + (uint32_t)r * (HD * 2) + (((uint32_t)ch ^ (uint32_t)(r & (CH - 1) & 7)) * 16);
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(src));
+        if (qrow < p.nq) {
+          const int64_t owner = (int64_t)qrow / p.rows_per_owner;
+          const int64_t lrow = (int64_t)qrow - owner * p.rows_per_owner;
+          __nv_bfloat16* dst =
+              p.o[owner] + (int64_t)batch * p.o_batch_stride + lrow * p.o_row_stride + (int64_t)head * HD + ch * 8;
+          *reinterpret_cast<uint4*>(dst) = w;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == A64_SOFTMAX_WARPS + 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int EMU, int EMU_B>
+static int launch_attn64x4(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                           int batch, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    FINO_CHECK_CUDA(cudaFuncSetAttribute(attn64x4_fwd_kernel<EMU, EMU_B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         A64_SMEM_BYTES));
+    configured = true;
+  }
+  const int n_tiles = p.q_tiles * p.heads * batch;
+  const int n_part = (n_tiles - p.n_full) * p.splits;
+  attn64x4_fwd_kernel<EMU, EMU_B><<<p.n_full + n_part, A64_THREADS, A64_SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  FINO_CHECK_CUDA(cudaGetLastError());
+  if (n_part > 0) {
+    const int rows_total = (n_tiles - p.n_full) * p.tile_rows;
+    attn_combine_kernel<64><<<(rows_total + 7) / 8, 256, 0, stream>>>(p, rows_total);
     FINO_CHECK_CUDA(cudaGetLastError());
   }
   return FINO_OK;
@@ -760,17 +1168,22 @@ int attention_fwd_owners(const void* q, const void* k, const void* v, void* cons
 
   CUtensorMap tq, tk, tv;
   const uint64_t inner = (uint64_t)heads * head_dim;
-  auto enc = [&](CUtensorMap* tm, const void* base, int64_t n, int64_t rs, int64_t bs) {
+  // head_dim 64 runs the four-tile kernel (512 query rows per CTA, 64-key steps) unless a variant of the two-tile
+  // kernel is selected through the tuning hook
+  const bool x4 = head_dim == 64 && (g_attn_variant == 0 || g_attn_variant >= 14);
+  const int kv_rows = x4 ? A64_BN : ATT_BN;
+  const int tile_rows = x4 ? A64_NT * ATT_BM : 2 * ATT_BM;
+  auto enc = [&](CUtensorMap* tm, const void* base, int64_t n, int64_t rs, int64_t bs, uint32_t box_rows) {
     uint64_t dims[3] = {inner, (uint64_t)n, (uint64_t)batch};
     // a batch stride of 0 is not encodable; with batch == 1 any legal value works
     uint64_t strides[2] = {(uint64_t)rs * 2, (uint64_t)(batch > 1 ? bs : rs * n) * 2};
-    uint32_t box[3] = {64, 128, 1};
+    uint32_t box[3] = {64, box_rows, 1};
     return encode_tmap_bf16(tm, base, 3, dims, strides, box);
   };
   int r;
-  if ((r = enc(&tq, q, nq, q_row_stride, q_batch_stride))) return r;
-  if ((r = enc(&tk, k, nk, k_row_stride, k_batch_stride))) return r;
-  if ((r = enc(&tv, v, nk, v_row_stride, v_batch_stride))) return r;
+  if ((r = enc(&tq, q, nq, q_row_stride, q_batch_stride, ATT_BM))) return r;
+  if ((r = enc(&tk, k, nk, k_row_stride, k_batch_stride, (uint32_t)kv_rows))) return r;
+  if ((r = enc(&tv, v, nk, v_row_stride, v_batch_stride, (uint32_t)kv_rows))) return r;
 
   AttnParams p;
   for (int g = 0; g < ATT_MAX_OWNERS; ++g)
@@ -782,21 +1195,29 @@ int attention_fwd_owners(const void* q, const void* k, const void* v, void* cons
   p.nk = (int)nk;
   p.heads = heads;
   p.scale_log2 = scale * 1.4426950408889634f;
-  p.num_kv_tiles = (int)((nk + ATT_BN - 1) / ATT_BN);
-  p.q_tiles = (int)((nq + 2 * ATT_BM - 1) / (2 * ATT_BM));
+  p.num_kv_tiles = (int)((nk + kv_rows - 1) / kv_rows);
+  p.q_tiles = (int)((nq + tile_rows - 1) / tile_rows);
+  p.tile_rows = tile_rows;
   FINO_CHECK_ARG((int64_t)p.q_tiles * heads * batch < (int64_t)1 << 30, "attention: too many query tiles");
   const int n_tiles = p.q_tiles * heads * batch;
   attention_plan(n_tiles, p.num_kv_tiles, num_sms(), g_attn_split, &p.n_full, &p.splits);
   p.ws_o = nullptr;
   p.ws_ml = nullptr;
   if (p.splits > 1) {
-    const size_t prow = (size_t)(n_tiles - p.n_full) * p.splits * 2 * ATT_BM;
+    const size_t prow = (size_t)(n_tiles - p.n_full) * p.splits * tile_rows;
     void* ws = nullptr;
     if ((r = attn_workspace(prow * ((size_t)head_dim * 4 + 8), &ws))) return r;
     p.ws_o = reinterpret_cast<float*>(ws);
     p.ws_ml = reinterpret_cast<float2*>(p.ws_o + prow * head_dim);
   }
   if (head_dim == 128) return dispatch_attn<128>(tq, tk, tv, p, batch, stream);
+  if (x4) {
+    switch (g_attn_variant) {
+      case 14: return launch_attn64x4<0, 0>(tq, tk, tv, p, batch, stream);  // all MUFU
+      case 15: return launch_attn64x4<2, 4>(tq, tk, tv, p, batch, stream);  // 3/8 emulated
+      default: return launch_attn64x4<2, 2>(tq, tk, tv, p, batch, stream);  // 2/8 emulated
+    }
+  }
   return dispatch_attn<64>(tq, tk, tv, p, batch, stream);
 }
 
