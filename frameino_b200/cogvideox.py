@@ -259,6 +259,15 @@ class CogVideoXTransformer3DModel(ModelBase):
     def to_inference_dtype(self, dtype: torch.dtype = torch.bfloat16) -> "CogVideoXTransformer3DModel":
         return self.to(dtype)
 
+    def prepare(self) -> "CogVideoXTransformer3DModel":
+        """Concatenated q|k|v projection weights, built once after loading instead of on the first forward."""
+        from .processors import _fused_weights
+
+        for b in self.transformer_blocks:
+            if not (getattr(b.attn1, "fused_projections", False) and hasattr(b.attn1, "to_qkv")):
+                _fused_weights(b.attn1, ("to_q", "to_k", "to_v"), "qkv")
+        return self
+
     # cogvideox_transformer_3d.py:407-444 -------------------------------------------------------------------------
     def fuse_qkv_projections(self):
         self.original_attn_processors = self.attn_processors

@@ -194,6 +194,27 @@ class ModelBase(nn.Module):
         """diffusers CacheMixin.cache_context: a no-op unless a cache hook is enabled (none here)."""
         yield
 
+    # ---- checkpoints (frameino_b200/loading.py; reference app.py:150-156 builds its transformer the same way) -------
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path: str, subfolder: Optional[str] = None,
+                        torch_dtype: torch.dtype = torch.bfloat16, device=None, **kwargs):
+        """Loads a diffusers-format model directory (``config.json`` + ``diffusion_pytorch_model*.safetensors``, single
+        or sharded) with the ``torch_dtype`` + ``_keep_in_fp32_modules`` dtype policy, directly onto ``device``."""
+        from . import loading
+
+        return loading.from_pretrained(cls, pretrained_model_name_or_path, subfolder=subfolder, torch_dtype=torch_dtype,
+                                       device=device, **kwargs)
+
+    def save_pretrained(self, save_directory: str, max_shard_size: int = 10 << 30):
+        from . import loading
+
+        return loading.save_pretrained(self, save_directory, max_shard_bytes=max_shard_size)
+
+    def prepare(self) -> "ModelBase":
+        """Builds the derived weights the kernels read (concatenated projection matrices, cached per attention module)
+        ahead of the first forward. Overridden per model; harmless to skip (they are built lazily otherwise)."""
+        return self
+
     def enable_gradient_checkpointing(self):  # inference-only build
         raise NotImplementedError("frameino_b200 is an inference path; training/backward is out of scope")
 

@@ -232,6 +232,17 @@ class WanTransformer3DModel(ModelBase):
             p.data = p.data.to(torch.float32 if keep else dtype)
         return self
 
+    def prepare(self) -> "WanTransformer3DModel":
+        """Concatenated q|k|v (self-attention) and k|v (cross-attention) projection weights + the stacked modulation
+        tables, built once after loading instead of on the first forward."""
+        from .processors import _fused_weights
+
+        for b in self.blocks:
+            _fused_weights(b.attn1, ("to_q", "to_k", "to_v"), "qkv")
+            _fused_weights(b.attn2, ("to_k", "to_v"), "kv")
+        self._stacked_tables()
+        return self
+
     def _stacked_tables(self) -> torch.Tensor:
         """[L, 6*D] fp32 copy of every block's scale_shift_table (refreshed if a table changes)."""
         key = tuple((b.scale_shift_table.data_ptr(), b.scale_shift_table._version) for b in self.blocks)
