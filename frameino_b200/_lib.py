@@ -10,7 +10,8 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libframeino_b200.so")
+# FINO_LIB_PATH: A/B runs of two builds of the library inside one GPU session (tools/kbench.py); never set in production
+LIB_PATH = os.environ.get("FINO_LIB_PATH") or os.path.join(_HERE, "libframeino_b200.so")
 
 _lib = None
 
