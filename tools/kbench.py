@@ -144,4 +144,17 @@ if "rows" in which:
                name=f"qk_norm_rope 28160x(2x3072) (variant {variant})")
         timeit(lambda: ops.qk_norm_rope(x, wq, None, None, h), bytes_=2.0 * n * d * 2,
                name=f"q_norm (cross) 28160x3072 (variant {variant})")
+if "rows64" in which:  # CogVideoX: per-head LayerNorm(64) + RoPE on the joint [226 text + video] sequence
+    n2, h2, hd2 = 19126, 48, 64
+    qkv = torch.randn(1, n2, 3 * d, device="cuda").bfloat16()
+    w64, b64 = torch.ones(hd2, device="cuda").bfloat16(), torch.zeros(hd2, device="cuda").bfloat16()
+    cos = torch.rand(n2 - 226, hd2, device="cuda")
+    sin = torch.rand(n2 - 226, hd2, device="cuda")
+    for variant in (0, 2):
+        ops.rows_set_variant(3, variant)
+        timeit(lambda: ops.qk_norm_rope(qkv[..., :d], w64, qkv[..., d:2 * d], w64, h2, b0=b64, b1=b64,
+                                        norm_mode=ops.QK_LAYERNORM_PER_HEAD, rope_mode=ops.ROPE_COGVIDEOX, cos=cos,
+                                        sin=sin, seq_len=n2, rope_skip=226),
+               bytes_=4.0 * n2 * d * 2 + 2.0 * n2 * hd2 * 4, name=f"qk LayerNorm(64)+RoPE 19126x(2x3072) (variant {variant})")
+    ops.rows_set_variant(3, 2)
 print("done", which)
