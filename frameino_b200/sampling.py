@@ -46,6 +46,7 @@ def wan_frameino_denoise(
     shift: float = 5.0,
     model_dtype: torch.dtype = torch.bfloat16,
     patch_hw: int = 2,
+    cfg_parallel=None,              # frameino_b200.ulysses.CfgParallel: this rank runs one of the two CFG forwards
 ) -> torch.Tensor:
     dev = latents.device
     sigmas = flow_match_sigmas(num_steps, shift, dev)
@@ -60,8 +61,16 @@ def wan_frameino_denoise(
         ts = torch.cat([ts, ts.new_full((n_id * tokens_per_frame,), float(t))])[None]  # ID tokens carry t (:834-843)
         x_in = torch.cat([x_in, id_latents.to(x_in.dtype)], dim=2)  # :854 frame-wise
         x_in = torch.cat([x_in, traj_latents.to(x_in.dtype)], dim=1).to(model_dtype)  # :858 channel-wise
-        v = transformer(hidden_states=x_in, timestep=ts, encoder_hidden_states=prompt_embeds, return_dict=False)[0]
-        if do_cfg:
+        if cfg_parallel is not None:
+            if not do_cfg:
+                raise ValueError("cfg_parallel needs classifier-free guidance (guidance_scale > 1 and a negative prompt)")
+            mine = prompt_embeds if cfg_parallel.branch == 0 else negative_prompt_embeds
+            v, vu = cfg_parallel.exchange(
+                transformer(hidden_states=x_in, timestep=ts, encoder_hidden_states=mine, return_dict=False)[0])
+            v = vu.float() + guidance_scale * (v.float() - vu.float())  # :882
+        else:
+            v = transformer(hidden_states=x_in, timestep=ts, encoder_hidden_states=prompt_embeds, return_dict=False)[0]
+        if do_cfg and cfg_parallel is None:
             vu = transformer(hidden_states=x_in, timestep=ts, encoder_hidden_states=negative_prompt_embeds,
                              return_dict=False)[0]
             v = vu.float() + guidance_scale * (v.float() - vu.float())  # :882
@@ -83,6 +92,7 @@ def wan_frameino_denoise_fused(
     num_steps: int = 50,
     guidance_scale: float = 5.0,
     shift: float = 5.0,
+    cfg_parallel=None,              # frameino_b200.ulysses.CfgParallel: this rank runs one of the two CFG forwards
 ) -> torch.Tensor:
     """Same contract and result as ``wan_frameino_denoise`` (see the module docstring for what is fused)."""
     from . import ops
@@ -124,8 +134,12 @@ def wan_frameino_denoise_fused(
     sigmas = flow_match_sigmas(num_steps, shift, dev)
     sig_host = sigmas.cpu()
     do_cfg = guidance_scale > 1.0 and negative_prompt_embeds is not None
-    text_c = transformer.prepare_text(prompt_embeds)
-    text_u = transformer.prepare_text(negative_prompt_embeds) if do_cfg else None
+    if cfg_parallel is not None and not do_cfg:
+        raise ValueError("cfg_parallel needs classifier-free guidance (guidance_scale > 1 and a negative prompt)")
+    run_c = cfg_parallel is None or cfg_parallel.branch == 0
+    run_u = do_cfg and (cfg_parallel is None or cfg_parallel.branch == 1)
+    text_c = transformer.prepare_text(prompt_embeds) if run_c else None
+    text_u = transformer.prepare_text(negative_prompt_embeds) if run_u else None
     grid = (f + n_id, h, w)
     tokens = ((f + n_id) // p_t) * (h // p_h) * (w // p_w)
     rows = None
@@ -135,8 +149,10 @@ def wan_frameino_denoise_fused(
         temb, proj = transformer.time_rows(uniq)
         conditioning = (temb, proj, row_index, 0) if mixed else (temb, proj, None, b * tokens)
         rows = ops.wan_pack_model_input(lat, cond, mask, idl, traj, patch, out=rows)
-        y_c = transformer.forward_rows(rows, b, grid, conditioning, text_c)
-        y_u = transformer.forward_rows(rows, b, grid, conditioning, text_u) if do_cfg else None
+        y_c = transformer.forward_rows(rows, b, grid, conditioning, text_c) if run_c else None
+        y_u = transformer.forward_rows(rows, b, grid, conditioning, text_u) if run_u else None
+        if cfg_parallel is not None:  # swap the branch outputs with the partner rank of the other half
+            y_c, y_u = cfg_parallel.exchange(y_c if run_c else y_u)
         dsigma = float(sig_host[i + 1] - sig_host[i])  # fp32 difference, as the tensor form computes it
         ops.wan_cfg_euler_step(lat, y_c, y_u, n_id, patch, guidance_scale, dsigma)
     return lat

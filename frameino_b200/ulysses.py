@@ -238,3 +238,47 @@ def disable_sequence_parallel(model) -> None:
     model.sequence_parallel = None
     for blk in model.blocks:
         blk.attn1.__dict__.pop("_fino_sp", None)
+
+
+class CfgParallel:
+    """Classifier-free-guidance parallelism for the sampler loop (SURVEY.md 8e "other axes", 8f row 1): the reference
+    pipeline runs the conditional and the unconditional forward of a scheduler step one after the other on the same
+    inputs (pipeline_wan_i2v_motion_FrameINO.py:862-882); they are independent, so ranks [0, W/2) run the conditional
+    one and ranks [W/2, W) the unconditional one, each half sharding its forward over its own Ulysses group, and rank r
+    swaps its output rows with rank r + W/2 (one 2-rank all-gather of [N, 192] bf16 per step). A scheduler step then
+    costs one forward at W/2-way sequence parallelism instead of two at W-way, which scales better (fewer, larger
+    shards; half the exchange partners)."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None):
+        if not dist.is_initialized():
+            raise RuntimeError("torch.distributed must be initialised before enabling CFG parallelism")
+        world = dist.get_world_size(group)
+        if world % 2 != 0:
+            raise ValueError(f"CFG parallelism needs an even number of ranks, got {world}")
+        rank = dist.get_rank(group)
+        ranks = dist.get_process_group_ranks(group) if group is not None else list(range(world))
+        half = world // 2
+        self.world, self.rank, self.half = world, rank, half
+        self.branch = 0 if rank < half else 1  # 0: conditional forward, 1: unconditional
+        # every rank creates every group, in the same order (torch.distributed requirement)
+        halves = [dist.new_group(ranks[:half]), dist.new_group(ranks[half:])]
+        pairs = [dist.new_group([ranks[i], ranks[i + half]]) for i in range(half)]
+        self.half_group = halves[self.branch]
+        self.pair_group = pairs[rank % half]
+
+    def exchange(self, y: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """This rank's forward output -> (conditional output, unconditional output)."""
+        out = [torch.empty_like(y), torch.empty_like(y)]
+        dist.all_gather(out, y.contiguous(), group=self.pair_group)  # group rank 0 is the conditional half's member
+        return out[0], out[1]
+
+
+def enable_cfg_parallel(model, group: Optional[dist.ProcessGroup] = None, mode: str = "peer") -> CfgParallel:
+    """Splits ``group`` (default: all ranks) into a conditional and an unconditional half for the sampler loops of
+    ``frameino_b200.sampling`` and turns on Ulysses sequence parallelism inside each half when it has more than one
+    rank. Pass the returned object to the loop as ``cfg_parallel=``."""
+    cp = CfgParallel(group)
+    if cp.half > 1:
+        enable_sequence_parallel(model, group=cp.half_group, mode=mode)
+    model.__dict__["cfg_parallel"] = cp
+    return cp

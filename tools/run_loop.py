@@ -17,7 +17,7 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from frameino_b200 import synth  # noqa: E402
 from frameino_b200.sampling import wan_frameino_denoise, wan_frameino_denoise_fused  # noqa: E402
-from frameino_b200.ulysses import disable_sequence_parallel, enable_sequence_parallel  # noqa: E402
+from frameino_b200.ulysses import disable_sequence_parallel, enable_cfg_parallel, enable_sequence_parallel  # noqa: E402
 
 
 def main():
@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--width", type=int, default=1280)
     ap.add_argument("--compare", action="store_true")
     ap.add_argument("--fused", action="store_true", help="device-side loop glue (wan_frameino_denoise_fused)")
+    ap.add_argument("--cfg-parallel", action="store_true",
+                    help="half of the ranks run the conditional forward, half the unconditional one (Ulysses inside each half)")
     ap.add_argument("--both", action="store_true", help="time the plain and the fused loop, report both + max diff")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -57,32 +59,39 @@ def main():
 
     loop = wan_frameino_denoise_fused if args.fused else wan_frameino_denoise
 
+    extra = {}
+
     def run(loop=loop):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        out = loop(model, *tensors, num_steps=args.steps)
+        out = loop(model, *tensors, num_steps=args.steps, **extra)
         e.record()
         torch.cuda.synchronize()
         return out, s.elapsed_time(e)
 
-    if world > 1:
+    if world > 1 and args.cfg_parallel:
+        extra["cfg_parallel"] = enable_cfg_parallel(model)
+    elif world > 1:
         enable_sequence_parallel(model)
-    loop(model, *tensors, num_steps=1)  # warm-up
+    loop(model, *tensors, num_steps=1, **extra)  # warm-up
     out_sp, ms_sp = run()
-    res = {"n_gpus": world, "steps": args.steps, "forwards": 2 * args.steps, "loop": loop.__name__, "loop_ms": ms_sp,
+    res = {"n_gpus": world, "steps": args.steps, "forwards": 2 * args.steps, "loop": loop.__name__,
+           "parallelism": ("cfg x2, ulysses x%d" % (world // 2)) if (args.cfg_parallel and world > 1) else "ulysses x%d" % world,
+           "ms_per_scheduler_step": ms_sp / args.steps, "loop_ms": ms_sp,
            "ms_per_forward": ms_sp / (2 * args.steps), "tokens": (lat_f + 1) * (h // 2) * (w // 2),
            "finite": bool(torch.isfinite(out_sp).all())}
     if args.both:
         other = wan_frameino_denoise if args.fused else wan_frameino_denoise_fused
-        other(model, *tensors, num_steps=1)
+        other(model, *tensors, num_steps=1, **extra)
         out_o, ms_o = run(other)
         res[other.__name__ + "_loop_ms"] = ms_o
         res["max_abs_diff_between_loops"] = float((out_o - out_sp).abs().max())
     if args.compare and world > 1:
         disable_sequence_parallel(model)
+        extra.clear()
         if rank == 0:
             out_1, ms_1 = run_single(model, tensors, args.steps)
             res["single_gpu_loop_ms"] = ms_1
