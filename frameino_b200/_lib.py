@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int64, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # FINO_LIB_PATH: A/B runs of two builds of the library inside one GPU session (tools/kbench.py); never set in production

@@ -9,7 +9,6 @@ them in every block, cogvideox_transformer_3d.py:155, attention_processor.py:282
 """
 from __future__ import annotations
 
-import math
 from typing import Any, Dict, Optional, Tuple, Union
 
 import torch

@@ -21,7 +21,7 @@ import json
 import os
 import re
 from contextlib import contextmanager
-from typing import Dict, Iterable, Iterator, List, Optional, Tuple, Union
+from typing import Dict, Iterable, Iterator, List, Optional, Union
 
 import torch
 from torch import nn

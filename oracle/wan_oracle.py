@@ -8,7 +8,7 @@ reproduced where the reference has them. Optional ``taps`` dict collects per-lay
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, Optional, Tuple
 
 import torch
