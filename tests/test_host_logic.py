@@ -175,3 +175,59 @@ def test_gemm_round_plan():
     assert ops.gemm_plan(3520, 3072, 512) == (168, 1)
     assert ops.gemm_plan(3520, 3072, 3072, mode=0) == (168, 1)
     assert ops.gemm_plan(512, 512, 2048, mode=4) == (0, 4)
+
+
+def test_cache_context_keys_a_text_state_and_invalidates(monkeypatch):
+    """model.cache_context(name) (pipeline_wan_i2v_motion_FrameINO.py:862, :873) keys the per-prompt text state: the
+    bookkeeping (nesting, reuse, invalidation on in-place edits of the prompt or of a text-side weight, separate
+    contexts) is host logic and runs on CPU with the device work stubbed out."""
+    from frameino_b200.wan import WanTextState
+
+    m = WanTransformer3DModel(**synth.WAN_TINY)
+    calls = []
+
+    def fake_prepare(ehs):
+        calls.append(ehs)
+        return WanTextState(text=ehs, kv=[None] * len(m.blocks), key=m._text_key(ehs), source=ehs)
+
+    monkeypatch.setattr(m, "prepare_text", fake_prepare)
+    a, b = torch.randn(1, 4, 64), torch.randn(1, 4, 64)
+    assert m.__dict__.get("_fino_cache_name") is None
+    s0 = m._text_state(a)
+    assert m._text_state(a) is not s0 and len(calls) == 2          # outside a context nothing is kept
+    with m.cache_context("cond"):
+        s1 = m._text_state(a)
+        assert m._text_state(a) is s1 and len(calls) == 3          # reused
+        with m.cache_context("uncond"):
+            assert m.__dict__["_fino_cache_name"] == "uncond"
+            s2 = m._text_state(b)
+            assert s2 is not s1 and m._text_state(b) is s2
+        assert m.__dict__["_fino_cache_name"] == "cond"           # nesting restores the outer name
+        assert m._text_state(a) is s1
+        a.mul_(2.0)                                                # in-place edit of the prompt
+        s3 = m._text_state(a)
+        assert s3 is not s1 and m._text_state(a) is s3
+        with torch.no_grad():
+            m.blocks[1].attn2.to_k.weight.add_(1.0)               # text-side weight changed
+        assert m._text_state(a) is not s3
+        assert m._text_state(b) is not s2                          # same name, another prompt: recomputed
+    assert m.__dict__.get("_fino_cache_name") is None
+    with m.cache_context("uncond"):
+        assert m._text_state(b) is not s2                          # the weight edit invalidated this context too
+    m.clear_text_cache()
+    assert m.__dict__["_fino_text_cache"] == {}
+
+
+def test_sampler_helpers_on_cpu():
+    from frameino_b200.sampling import flow_match_sigmas, wan_frameino_denoise_fused
+
+    s = flow_match_sigmas(50, 5.0)
+    assert s.shape == (51,) and float(s[0]) == 1.0 and float(s[-1]) == 0.0
+    assert bool((s[:-1] > s[1:]).all())                            # strictly decreasing
+    lin = torch.linspace(1.0, 1e-3, 50)
+    assert torch.allclose(s[:-1], 5.0 * lin / (1.0 + 4.0 * lin))   # static shift 5 (train_wan_motion_FrameINO.yaml:43-50)
+    m = WanTransformer3DModel(**synth.WAN_TINY)
+    z = torch.zeros(1, 16, 2, 8, 8)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        wan_frameino_denoise_fused(m, z, z, torch.ones(1, 1, 2, 8, 8), torch.zeros(1, 16, 3, 8, 8),
+                                   torch.zeros(1, 16, 1, 8, 8), torch.zeros(1, 4, 64), None, num_steps=1)
