@@ -156,3 +156,86 @@ def wan_frameino_denoise_fused(
         dsigma = float(sig_host[i + 1] - sig_host[i])  # fp32 difference, as the tensor form computes it
         ops.wan_cfg_euler_step(lat, y_c, y_u, n_id, patch, guidance_scale, dsigma)
     return lat
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CogVideoX FrameINO sampler loop glue
+# ---------------------------------------------------------------------------------------------------------------------
+def dynamic_cfg_scale(guidance_scale: float, num_inference_steps: int, t: float) -> float:
+    """pipelines/pipeline_cogvideox_i2v_motion_FrameINO.py:906-909 (``use_dynamic_cfg``)."""
+    import math
+
+    return 1 + guidance_scale * ((1 - math.cos(math.pi * ((num_inference_steps - t) / num_inference_steps) ** 5.0)) / 2)
+
+
+def ddim_v_step(model_output: torch.Tensor, sample: torch.Tensor, alpha_t: float, alpha_prev: float) -> torch.Tensor:
+    """One deterministic (eta = 0) DDIM step for a v-prediction model — the scheduler family the CogVideoX pipeline runs
+    (:915-926). The scheduler classes live upstream in diffusers, not in the reference tree, so the step is the textbook
+    one, parameterised by the two cumulative alphas:
+        x0 = sqrt(a_t) x - sqrt(1 - a_t) v;   eps = sqrt(a_t) v + sqrt(1 - a_t) x;
+        x_prev = sqrt(a_prev) x0 + sqrt(1 - a_prev) eps."""
+    a_t, a_p = float(alpha_t), float(alpha_prev)
+    x0 = a_t ** 0.5 * sample - (1 - a_t) ** 0.5 * model_output
+    eps = a_t ** 0.5 * model_output + (1 - a_t) ** 0.5 * sample
+    return a_p ** 0.5 * x0 + (1 - a_p) ** 0.5 * eps
+
+
+def scaled_linear_alphas_cumprod(num_train_timesteps: int = 1000, beta_start: float = 0.00085, beta_end: float = 0.012,
+                                 snr_shift_scale: float = 1.0) -> torch.Tensor:
+    """``scaled_linear`` betas + the SNR shift of the CogVideoX schedulers (upstream defaults, recalled; pass your own
+    table to ``cog_frameino_denoise`` to use another schedule)."""
+    betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float64) ** 2
+    ac = torch.cumprod(1.0 - betas, dim=0)
+    ac = ac / (snr_shift_scale + (1 - snr_shift_scale) * ac)
+    return ac.float()
+
+
+@torch.no_grad()
+def cog_frameino_denoise(
+    transformer: Callable,
+    latents: torch.Tensor,          # [1, F, C, H, W] initial noise (CogVideoX layout: frames before channels)
+    image_latents: torch.Tensor,    # [1, F, C, H, W] first-frame condition (zeros after frame 0)
+    traj_latents: torch.Tensor,     # [1, F, C, H, W] trajectory latents
+    id_latent: Optional[torch.Tensor],  # [1, n_id, C, H, W] or None
+    prompt_embeds: torch.Tensor,    # [2, T, text_dim] = cat(negative, positive) when guidance is on (:767-768), else [1, ...]
+    image_rotary_emb,
+    timesteps,                      # decreasing integer timesteps, e.g. torch.linspace(999, 0, steps).long()
+    alphas_cumprod: torch.Tensor,   # [num_train_timesteps]
+    guidance_scale: float = 6.0,
+    use_dynamic_cfg: bool = False,
+    model_dtype: torch.dtype = torch.bfloat16,
+) -> torch.Tensor:
+    """The hot loop of pipelines/pipeline_cogvideox_i2v_motion_FrameINO.py:846-927 around the transformer forward:
+    batched CFG (:853, :856, :859), frame-wise ID concat with zero padding of the image / trajectory streams (:862-873),
+    channel-wise concat (:877), ID-frame drop (:899-900), dynamic guidance (:904-909), CFG combine (:910-912), scheduler
+    step (here ``ddim_v_step``) and the cast back to the prompt dtype (:927). Plain torch: drives the native model or
+    any callable with the reference forward signature."""
+    do_cfg = guidance_scale > 1.0
+    steps = len(timesteps)
+    n_frames = latents.shape[1]
+    lat = latents
+    for i in range(steps):
+        t = timesteps[i]
+        x = torch.cat([lat] * 2) if do_cfg else lat
+        img = torch.cat([image_latents] * 2) if do_cfg else image_latents
+        traj = torch.cat([traj_latents] * 2) if do_cfg else traj_latents
+        if id_latent is not None:
+            idl = torch.cat([id_latent] * 2) if do_cfg else id_latent
+            x = torch.cat([x, idl.to(x.dtype)], dim=1)
+            pad = x.new_zeros(idl.shape)
+            img = torch.cat([img.to(x.dtype), pad], dim=1)
+            traj = torch.cat([traj.to(x.dtype), pad], dim=1)
+        x = torch.cat([x, img.to(x.dtype), traj.to(x.dtype)], dim=2)
+        ts = torch.as_tensor(t, device=x.device).expand(x.shape[0])
+        v = transformer(hidden_states=x.to(model_dtype), encoder_hidden_states=prompt_embeds, timestep=ts,
+                        image_rotary_emb=image_rotary_emb, return_dict=False)[0].float()
+        if id_latent is not None:
+            v = v[:, :n_frames]
+        g = dynamic_cfg_scale(guidance_scale, steps, float(t)) if use_dynamic_cfg else guidance_scale
+        if do_cfg:
+            v_uncond, v_text = v.chunk(2)
+            v = v_uncond + g * (v_text - v_uncond)
+        a_t = alphas_cumprod[int(t)]
+        a_prev = alphas_cumprod[int(timesteps[i + 1])] if i + 1 < steps else torch.tensor(1.0)
+        lat = ddim_v_step(v, lat.float(), a_t, a_prev).to(prompt_embeds.dtype)
+    return lat
