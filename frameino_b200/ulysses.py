@@ -282,3 +282,9 @@ def enable_cfg_parallel(model, group: Optional[dist.ProcessGroup] = None, mode: 
         enable_sequence_parallel(model, group=cp.half_group, mode=mode)
     model.__dict__["cfg_parallel"] = cp
     return cp
+
+
+def disable_cfg_parallel(model) -> None:
+    """Undoes ``enable_cfg_parallel`` (collective: every rank must call it)."""
+    disable_sequence_parallel(model)
+    model.__dict__.pop("cfg_parallel", None)
