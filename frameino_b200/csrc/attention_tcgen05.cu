@@ -696,7 +696,8 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
 // the second half read from TMEM again): holding 64 scores next to the packed P and the MUFU latency window spilled.
 // The ragged last step of the sequence is a separate instantiation of the step body, so the common path has no
 // conditional writes to the score registers.
-// Measured at the CogVideoX shape (19 126 x 19 126, 48 heads), isolated: 956 TFLOP/s (two-tile kernel: 820; with P in
+// Measured at the CogVideoX shape (19 126 x 19 126, 48 heads), isolated: 956 TFLOP/s, 980 with the tile pairs started
+// half a period apart (STAGGER) (two-tile kernel: 820; with P in
 // its own columns + MUFU turn-taking: 885). Dead ends kept out of the tree: three tiles with P in its own columns and
 // early S issue (794: three warps per sub-partition hide less than four), the same with a polling MMA scheduler
 // instead of the fixed round-robin (527: a dozen mbarrier probes per pass put ~400 cycles into every round trip).
@@ -714,7 +715,7 @@ __host__ __device__ constexpr uint32_t a64_col_s(int i) { return 128u * i; }
 __host__ __device__ constexpr uint32_t a64_col_p(int i) { return 128u * i; }
 __host__ __device__ constexpr uint32_t a64_col_o(int i) { return 128u * i + 64u; }
 
-template <int EMU, int EMU_B>
+template <int EMU, int EMU_B, bool STAGGER>
 __global__ void __launch_bounds__(A64_THREADS, 1)
 attn64x4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                     const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ AttnParams p) {
@@ -821,6 +822,14 @@ attn64x4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     tc_fence_after();
 #pragma unroll
     for (int i = 0; i < A64_NT; ++i) {
+      if (STAGGER && i == A64_NT / 2) {
+        // De-phase the two tile pairs: tiles 2,3 get their first scores only when tile 0 has finished its first
+        // softmax step, i.e. exactly when tiles 0,1 go idle for their P V -> S round trip. Every tile has the same
+        // period, so the offset persists for the whole KV loop: one pair's exponentials fill the MUFU pipe while the
+        // other pair waits for the tensor pipe, and the round-robin service order below matches their readiness.
+        mbar_wait(p_full(0), 0u, 45);
+        tc_fence_after();
+      }
       umma_ss_x4_w(tmem_base + a64_col_s(i), qdesc0 + (uint64_t)(i * kQUnits), kdesc0, idesc_s, 0u);
       tc_commit_w(s_full(i));
     }
@@ -1062,18 +1071,18 @@ attn64x4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   }
 }
 
-template <int EMU, int EMU_B>
+template <int EMU, int EMU_B, bool STAGGER = true>
 static int launch_attn64x4(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                            int batch, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    FINO_CHECK_CUDA(cudaFuncSetAttribute(attn64x4_fwd_kernel<EMU, EMU_B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    FINO_CHECK_CUDA(cudaFuncSetAttribute(attn64x4_fwd_kernel<EMU, EMU_B, STAGGER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          A64_SMEM_BYTES));
     configured = true;
   }
   const int n_tiles = p.q_tiles * p.heads * batch;
   const int n_part = (n_tiles - p.n_full) * p.splits;
-  attn64x4_fwd_kernel<EMU, EMU_B><<<p.n_full + n_part, A64_THREADS, A64_SMEM_BYTES, stream>>>(tq, tk, tv, p);
+  attn64x4_fwd_kernel<EMU, EMU_B, STAGGER><<<p.n_full + n_part, A64_THREADS, A64_SMEM_BYTES, stream>>>(tq, tk, tv, p);
   FINO_CHECK_CUDA(cudaGetLastError());
   if (n_part > 0) {
     const int rows_total = (n_tiles - p.n_full) * p.tile_rows;
@@ -1213,7 +1222,7 @@ int attention_fwd_owners(const void* q, const void* k, const void* v, void* cons
   if (head_dim == 128) return dispatch_attn<128>(tq, tk, tv, p, batch, stream);
   if (x4) {
     switch (g_attn_variant) {
-      case 14: return launch_attn64x4<0, 0>(tq, tk, tv, p, batch, stream);  // all MUFU
+      case 14: return launch_attn64x4<2, 2, false>(tq, tk, tv, p, batch, stream);  // tile pairs in phase
       case 15: return launch_attn64x4<2, 4>(tq, tk, tv, p, batch, stream);  // 3/8 emulated
       default: return launch_attn64x4<2, 2>(tq, tk, tv, p, batch, stream);  // 2/8 emulated
     }
