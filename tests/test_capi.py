@@ -65,3 +65,36 @@ def test_product_package_never_imports_the_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
+
+
+def test_header_is_plain_c_and_links_against_the_library(tmp_path):
+    """include/frameino_b200.h is the contract for bindings in any language: it must compile as C99 (no C++ leaking in),
+    and a C program linked against the library must resolve the entry points and get the no-GPU status from a compute
+    call (or run it, on a GPU box)."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi_check.c"
+    src.write_text(
+        '#include "frameino_b200.h"\n#include <stdio.h>\n'
+        "int main(void) {\n"
+        "  int n_full = -1, splits = -1;\n"
+        "  if (fino_abi_version() != FINO_ABI_VERSION) return 10;\n"
+        "  if (fino_attention_plan(28160, 28160, 3, 1, 148, -1, &n_full, &splits) != 0) return 11;\n"
+        "  if (n_full != 296 || splits < 2) return 12;   /* 330 tiles on 148 SMs: 2 full waves + split last wave */\n"
+        "  if (fino_gemm_set_mode(99) == 0) return 13;    /* bad argument -> status 1 + message */\n"
+        "  if (fino_last_error() == 0 || fino_last_error()[0] == 0) return 14;\n"
+        '  printf("abi %d n_full %d splits %d\\n", fino_abi_version(), n_full, splits);\n'
+        "  return 0;\n}\n")
+    exe = tmp_path / "abi_check"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cmd = [gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+           "-L", libdir, "-l:libframeino_b200.so", f"-Wl,-rpath,{libdir}"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    assert run.stdout.startswith("abi 1 n_full 296")
