@@ -34,6 +34,7 @@ SIGNATURES = {
     "fino_attention_set_variant": (_I, [_I]),
     "fino_attention_set_split": (_I, [_I]),
     "fino_attention_plan": (_I, [_L, _L, _I, _I, _I, _I, _P, _P]),
+    "fino_attention_plan_hd": (_I, [_L, _L, _I, _I, _I, _I, _I, _P, _P, _P]),
     "fino_rows_set_variant": (_I, [_I, _I]),
     "fino_rows_set_tma": (_I, [_I]),
     "fino_ln_modulate": (_I, [_P, _P, _L, _I, _L, _L, _F, _P, _P, _P, _P, _L, _P, _L, _I, _P]),

@@ -246,6 +246,24 @@ int fino_attention_plan(int64_t nq, int64_t nk, int heads, int batch, int sms, i
   return 0;
 }
 
+int fino_attention_plan_hd(int64_t nq, int64_t nk, int heads, int batch, int head_dim, int sms, int mode, int* n_full,
+                           int* splits, int* tile_rows) {
+  if (nq <= 0 || nk <= 0 || heads <= 0 || batch <= 0 || sms <= 0 || !n_full || !splits || !tile_rows ||
+      (head_dim != 64 && head_dim != 128)) {
+    fino::set_last_error("fino_attention_plan_hd: bad arguments (head_dim 64 or 128)");
+    return fino::FINO_ERR_INVALID;
+  }
+  const int rows = head_dim == 64 ? 512 : 256, keys = head_dim == 64 ? 64 : 128;
+  const int64_t tiles = (nq + rows - 1) / rows * heads * batch;
+  if (tiles >= ((int64_t)1 << 30)) {
+    fino::set_last_error("fino_attention_plan_hd: too many query tiles");
+    return fino::FINO_ERR_INVALID;
+  }
+  *tile_rows = rows;
+  fino::attention_plan((int)tiles, (int)((nk + keys - 1) / keys), sms, mode, n_full, splits);
+  return 0;
+}
+
 int fino_rows_set_variant(int ln_block, int qk_block) {
   fino::rows_set_variant(ln_block, qk_block);
   fino::scatter_set_packed(qk_block == 2);

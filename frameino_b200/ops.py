@@ -426,6 +426,16 @@ def attention_plan(nq: int, nk: int, heads: int, batch: int = 1, sms: int = 148,
     return n_full.value, splits.value
 
 
+def attention_plan_hd(nq: int, nk: int, heads: int, head_dim: int, batch: int = 1, sms: int = 148, mode: int = -1):
+    """(n_full, splits, tile_rows) for a head_dim: 128 -> 256-row tiles, 64 -> the four-tile kernel's 512-row tiles."""
+    import ctypes
+
+    n_full, splits, rows = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0)
+    _lib.check(_lib.load().fino_attention_plan_hd(nq, nk, heads, batch, head_dim, sms, mode, ctypes.byref(n_full),
+                                                  ctypes.byref(splits), ctypes.byref(rows)), "fino_attention_plan_hd")
+    return n_full.value, splits.value, rows.value
+
+
 def rows_set_variant(ln_block: int, qk_block: int) -> None:
     """LayerNorm kernel: 0 warp per row, 1 block per row (one row at a time), 2 batched block per row (default for
     1024 <= dim <= 3072). q/k kernel: 0 warp per row, 1 block per token (default)."""

@@ -81,6 +81,10 @@ int fino_attention_set_split(int mode);
 /* The decomposition fino_attention_fwd would use on a device with `sms` SMs (pure host arithmetic; no GPU needed):
  * CTAs [0, n_full) run whole tiles, the remaining tiles run as `splits` partial CTAs each. */
 int fino_attention_plan(int64_t nq, int64_t nk, int heads, int batch, int sms, int mode, int* n_full, int* splits);
+/* Same for a given head_dim: 128 -> 256-query-row tiles against 128-key tiles (what fino_attention_plan describes);
+ * 64 -> the four-tile kernel's 512-query-row tiles against 64-key steps. *tile_rows receives the rows per CTA tile. */
+int fino_attention_plan_hd(int64_t nq, int64_t nk, int heads, int batch, int head_dim, int sms, int mode, int* n_full,
+                           int* splits, int* tile_rows);
 
 /* Tuning / test hook: LayerNorm kernel 0 = warp per row, 1 = block per row, 2 = batched block per row (default for
  * 1024 <= dim <= 3072); q/k-norm kernel 0 = warp per row, 1 = block per token (default). */

@@ -159,6 +159,19 @@ def test_attention_wave_plan():
             assert n_full == tiles
 
 
+def test_attention_wave_plan_per_head_dim():
+    """fino_attention_plan_hd: head_dim 128 is the 256-row / 128-key decomposition, head_dim 64 the four-tile kernel's
+    512-row tiles against 64-key steps (CogVideoX: 38 tiles x 48 heads = 1824 -> 12 full waves + 48 tiles split 3 ways)."""
+    from frameino_b200 import _lib, ops
+
+    assert ops.attention_plan_hd(28160, 28160, 3, 128) == ops.attention_plan(28160, 28160, 3) + (256,)
+    n_full, s, rows = ops.attention_plan_hd(19126, 19126, 48, 64)
+    assert rows == 512 and (n_full, s) == (1776, 3)
+    assert ops.attention_plan_hd(19126, 19126, 48, 64, mode=0) == (1824, 1, 512)
+    with pytest.raises(_lib.FinoError):
+        ops.attention_plan_hd(100, 100, 1, 96)
+
+
 def test_gemm_round_plan():
     """fino_gemm_plan: split-K only where the persistent pair kernel's last round is partly filled."""
     from frameino_b200 import ops
