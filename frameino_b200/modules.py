@@ -194,6 +194,31 @@ class ModelBase(nn.Module):
         """diffusers CacheMixin.cache_context: a no-op unless a cache hook is enabled (none here)."""
         yield
 
+    def _apply(self, fn, *args, **kwargs):
+        """``.to()`` / ``.cuda()`` / ``.cpu()`` (and accelerate's offload hooks, reference app.py:163) move or cast the
+        parameters; everything derived from them (fused projection weights, stacked modulation tables, per-prompt text
+        state, gathered RoPE tables) is dropped so that it is rebuilt from the new tensors and the old device memory is
+        released."""
+        out = super()._apply(fn, *args, **kwargs)
+        self.drop_derived_state()
+        return out
+
+    def drop_derived_state(self) -> None:
+        for mod in self.modules():
+            d = mod.__dict__
+            d.pop("_fino_cache", None)
+            if "_sst_cache" in d:
+                d["_sst_cache"] = None
+            if "_fino_text_cache" in d:
+                d["_fino_text_cache"] = {}
+            if isinstance(d.get("_cache"), dict):
+                d["_cache"] = {}
+            if isinstance(d.get("_pos_cache"), dict):
+                d["_pos_cache"] = {}
+            for k in ("_nf_f32", "_f32"):
+                if k in d:
+                    d[k] = None
+
     # ---- checkpoints (frameino_b200/loading.py; reference app.py:150-156 builds its transformer the same way) -------
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path: str, subfolder: Optional[str] = None,

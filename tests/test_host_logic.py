@@ -244,3 +244,24 @@ def test_sampler_helpers_on_cpu():
     with pytest.raises(RuntimeError, match="no CPU path"):
         wan_frameino_denoise_fused(m, z, z, torch.ones(1, 1, 2, 8, 8), torch.zeros(1, 16, 3, 8, 8),
                                    torch.zeros(1, 16, 1, 8, 8), torch.zeros(1, 4, 64), None, num_steps=1)
+
+
+def test_moving_the_model_drops_derived_state():
+    """.to() / accelerate offload hooks (reference app.py:163): fused weights, stacked tables, text states and gathered
+    RoPE tables are derived from the parameters and must not outlive a move or a cast."""
+    m = WanTransformer3DModel(**synth.WAN_TINY)
+    attn = m.blocks[0].attn1
+    attn.__dict__["_fino_cache"] = {"qkv": ("key", torch.zeros(1), None)}
+    m._stacked_tables()
+    m.rope(torch.zeros(1, 32, 2, 8, 8))
+    m.__dict__["_fino_text_cache"] = {"cond": object()}
+    assert m._sst_cache is not None and m.rope._cache
+    m.to(torch.bfloat16)
+    assert "_fino_cache" not in attn.__dict__ and m._sst_cache is None and m.rope._cache == {}
+    assert m.__dict__["_fino_text_cache"] == {}
+    c = CogVideoXTransformer3DModel(**synth.COG_TINY)
+    blk = c.transformer_blocks[0]
+    blk.norm1.affine_f32()
+    assert blk.norm1._f32 is not None
+    c.to(torch.bfloat16)
+    assert blk.norm1._f32 is None
