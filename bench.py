@@ -166,6 +166,8 @@ def run_reference(args, tokens):
         return
     import torch
 
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm runs on rank 0 alone and may use the whole host
+    torch.set_num_threads(max(torch.get_num_threads(), os.cpu_count() or 1))
     sample = OracleBlockSample(tokens)
     for _ in range(args.warmup):
         sample.step_ms()
