@@ -254,6 +254,7 @@ class CogVideoXTransformer3DModel(ModelBase):
         self.gradient_checkpointing = False
         self.original_attn_processors = None
         self._nf_f32 = None
+        self.sequence_parallel = None  # set by frameino_b200.ulysses.enable_sequence_parallel (mode="nccl")
 
     def to_inference_dtype(self, dtype: torch.dtype = torch.bfloat16) -> "CogVideoXTransformer3DModel":
         return self.to(dtype)
@@ -346,15 +347,34 @@ class CogVideoXTransformer3DModel(ModelBase):
         row_index = (2 * torch.arange(batch, device=dev)[:, None] + (ar[None, :] < text_len)).to(torch.int32)
         row_index = row_index.reshape(-1).contiguous()
 
+        # Ulysses (frameino_b200/ulysses.py): every rank keeps a contiguous slice of the JOINT rows; everything except
+        # the attention core is row-local. Text rows sit at the front, i.e. on rank 0.
+        sp = self.sequence_parallel
+        seq_loc, text_loc, rope_loc = seq, text_len, image_rotary_emb
+        if sp is not None:
+            from .ulysses import shard_joint_rope
+
+            sp.plan(seq)
+            seq_loc = sp.n_loc
+            joint = sp.shard_rows(joint).contiguous()
+            row_index = sp.shard_rows(row_index.view(batch, seq)).reshape(-1).contiguous()
+            if image_rotary_emb is not None:
+                text_loc, c_loc, s_loc = shard_joint_rope(image_rotary_emb[0].reshape(-1, cfg.attention_head_dim).float(),
+                                                          image_rotary_emb[1].reshape(-1, cfg.attention_head_dim).float(),
+                                                          text_len, seq_loc, sp.rank)
+                rope_loc = (c_loc, s_loc)
+            else:
+                text_loc = text_len if sp.rank == 0 else 0
+
         # 3. transformer blocks (:503-529)
         taps = self.__dict__.get("_fino_taps")  # parity tests set this to a dict to collect per-layer outputs
         if taps is not None:
             taps["patch_embed"] = joint.clone()
         for i, block in enumerate(self.transformer_blocks):
-            joint = block(joint, text_len, emb, row_index, image_rotary_emb)
+            joint = block(joint, text_loc, emb, row_index, rope_loc)
             if taps is not None:
-                taps[f"transformer_blocks.{i}.out"] = joint[:, text_len:].clone()
-                taps[f"transformer_blocks.{i}.enc"] = joint[:, :text_len].clone()
+                taps[f"transformer_blocks.{i}.out"] = joint[:, text_loc:].clone()
+                taps[f"transformer_blocks.{i}.enc"] = joint[:, :text_loc].clone()
 
         # 4. final norms + projection (:531-542)
         nf = self.norm_final
@@ -369,12 +389,16 @@ class CogVideoXTransformer3DModel(ModelBase):
         no = self.norm_out
         m = ops.linear_small_m(emb, no.linear.weight, no.linear.bias, act_in=1, round_in=True, round_out=True)  # [B, 2D]
         g2, b2 = no.affine_f32()
-        h = ops.ln_modulate(h, cfg.norm_eps, gamma=g2, beta=b2, shift=m[:, :dim], scale=m[:, dim:], rows_per_group=seq,
-                            bf16_steps=True, out=h)
+        h = ops.ln_modulate(h, cfg.norm_eps, gamma=g2, beta=b2, shift=m[:, :dim], scale=m[:, dim:],
+                            rows_per_group=seq_loc, bf16_steps=True, out=h)
         c_out = self.proj_out.weight.shape[0] // (p * p)
         out = torch.empty(batch, frames, c_out, height, width, dtype=dt, device=dev)
         for b in range(batch):
-            y = ops.linear(h[b, text_len:], self.proj_out.weight, self.proj_out.bias)
+            if sp is not None:  # project the local rows, gather the joint sequence, drop the text rows
+                y_loc = ops.linear(h[b], self.proj_out.weight, self.proj_out.bias)
+                y = sp.gather_rows(y_loc[None])[0, text_len:].contiguous()
+            else:
+                y = ops.linear(h[b, text_len:], self.proj_out.weight, self.proj_out.bias)
             ob = out[b:b + 1]
             so = ob.stride()
             ops.unpatchify(y, ob, (1, c_out, frames, height, width), (so[0], so[2], so[1], so[3], so[4]), (1, p, p),

@@ -206,7 +206,14 @@ class FinoCogVideoXAttnProcessor:
                              cos=cos, sin=sin, seq_len=s, rope_skip=text_len)
         elif mode != ops.ROPE_NONE:
             raise NotImplementedError("RoPE without qk-norm is not used by the reference CogVideoX path")
-        o = ops.attention(q, k, v, heads, scale=getattr(attn, "scale", head_dim ** -0.5))
+        scale = getattr(attn, "scale", head_dim ** -0.5)
+        sp = attn.__dict__.get("_fino_sp")
+        if sp is not None:  # Ulysses: joint rows are sharded over the ranks, one exchange pair per batch element
+            if fino_joint_text_len is None:
+                raise NotImplementedError("sequence parallelism needs the native joint-sequence block")
+            o = torch.cat([sp.attention(qkv[i:i + 1], heads, scale) for i in range(b)], dim=0)
+        else:
+            o = ops.attention(q, k, v, heads, scale=scale)
         if fino_residual is not None:  # x + gate * out (cogvideox_transformer_3d.py:146-147), joint layout only
             x, gate, row_index = fino_residual
             return ops.linear(o, attn.to_out[0].weight, attn.to_out[0].bias, epilogue=ops.EPI_GATE_RESIDUAL,

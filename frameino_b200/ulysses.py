@@ -223,12 +223,25 @@ class SequenceParallel:
         return parts.view(1, self.world * y.shape[1], y.shape[2])[:, : self.n_total]
 
 
+def _self_attention_modules(model):
+    """The self-attention containers of a native model: Wan ``blocks[i].attn1``, CogVideoX ``transformer_blocks[i].attn1``."""
+    blocks = getattr(model, "blocks", None)
+    if blocks is None:
+        blocks = model.transformer_blocks
+    return [blk.attn1 for blk in blocks]
+
+
 def enable_sequence_parallel(model, group: Optional[dist.ProcessGroup] = None, mode: str = "peer") -> SequenceParallel:
-    """Switches a ``frameino_b200.WanTransformer3DModel`` to Ulysses sequence parallelism over ``group``."""
+    """Switches a ``frameino_b200`` transformer to Ulysses sequence parallelism over ``group``. Wan: ``mode="peer"``
+    (exchange fused into the neighbouring kernels over NVLink peer memory) or ``"nccl"``. CogVideoX (joint text + video
+    sequence, per-head LayerNorm): ``"nccl"`` only — the fused prologue kernel is the Wan RMSNorm / RoPE one."""
+    is_wan = hasattr(model, "blocks")
+    if not is_wan and mode != "nccl":
+        raise NotImplementedError("CogVideoX sequence parallelism uses mode='nccl' (the peer-memory prologue is Wan's)")
     sp = SequenceParallel(group, mode)
     model.sequence_parallel = sp
-    for blk in model.blocks:
-        blk.attn1.__dict__["_fino_sp"] = sp
+    for attn in _self_attention_modules(model):
+        attn.__dict__["_fino_sp"] = sp
     return sp
 
 
@@ -236,8 +249,27 @@ def disable_sequence_parallel(model) -> None:
     if model.sequence_parallel is not None:
         model.sequence_parallel.close()
     model.sequence_parallel = None
-    for blk in model.blocks:
-        blk.attn1.__dict__.pop("_fino_sp", None)
+    for attn in _self_attention_modules(model):
+        attn.__dict__.pop("_fino_sp", None)
+
+
+def shard_joint_rope(cos: torch.Tensor, sin: torch.Tensor, text_len: int, n_loc: int, rank: int):
+    """CogVideoX under sequence parallelism: the joint sequence is [text_len text rows | video rows] and rank r owns
+    joint rows [r*n_loc, (r+1)*n_loc). Returns (local_text_len, cos_local, sin_local): the number of leading local rows
+    that are text (not rotated; all text must sit on rank 0) and the RoPE table rows of the local video tokens,
+    zero-padded to n_loc - local_text_len rows (pad rows past the end of the sequence are never used as keys)."""
+    if text_len > n_loc:
+        raise NotImplementedError(f"{text_len} text tokens do not fit the first rank's {n_loc} rows")
+    local_text = text_len if rank == 0 else 0
+    first = rank * n_loc + local_text - text_len  # first video row of this rank
+    want = n_loc - local_text
+    out = []
+    for t in (cos, sin):
+        piece = t[first:first + want]
+        if piece.shape[0] < want:
+            piece = torch.cat([piece, piece.new_zeros(want - piece.shape[0], t.shape[1])], dim=0)
+        out.append(piece.contiguous())
+    return local_text, out[0], out[1]
 
 
 class CfgParallel:

@@ -265,3 +265,24 @@ def test_moving_the_model_drops_derived_state():
     assert blk.norm1._f32 is not None
     c.to(torch.bfloat16)
     assert blk.norm1._f32 is None
+
+
+def test_joint_rope_sharding_for_cogvideox_sequence_parallel():
+    """CogVideoX under Ulysses: joint rows [text | video] are cut into equal slices; each rank gets the RoPE rows of its
+    own video tokens, rank 0 keeps the text rows un-rotated, the tail is zero-padded."""
+    from frameino_b200.ulysses import shard_joint_rope
+
+    text, n_video, hd = 3, 20, 4
+    cos = torch.arange(float(n_video))[:, None].repeat(1, hd)
+    sin = -cos
+    for world in (1, 2, 4, 8):
+        n_loc, n_pad = SequenceParallel.partition(text + n_video, world)
+        seen = []
+        for r in range(world):
+            lt, c, s = shard_joint_rope(cos, sin, text, n_loc, r)
+            assert lt == (text if r == 0 else 0) and c.shape == (n_loc - lt, hd) and torch.equal(s, -c)
+            seen += c[:, 0].tolist()
+        assert seen[:n_video] == list(range(n_video)) and all(v == 0 for v in seen[n_video:])
+        assert len(seen) == n_pad - text
+    with pytest.raises(NotImplementedError):
+        shard_joint_rope(cos, sin, 9, 4, 0)
