@@ -44,6 +44,7 @@ SIGNATURES = {
     "fino_unpatchify": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _L, _L, _L, _L, _L, _L, _I, _P]),
     "fino_timestep_embedding": (_I, [_P, _P, _I, _I, _I, _F, _F, _F, _P]),
     "fino_linear_small_m": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "fino_timestep_dedup": (_I, [_P, _L, _P, _P, _P, _P]),
     "fino_build_mod_table": (_I, [_P, _P, _P, _I, _I, _I, _L, _P]),
     "fino_wan_pack_model_input": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _P]),
     "fino_wan_cfg_euler_step": (_I, [_P, _P, _L, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),

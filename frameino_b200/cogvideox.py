@@ -15,8 +15,8 @@ import torch
 from torch import nn
 
 from . import ops
-from .modules import Attention, FeedForward, ModelBase, TimestepEmbedding, WeightOnlyNorm, logger
-from .processors import FinoCogVideoXAttnProcessor
+from .modules import Attention, FeedForward, ModelBase, TimestepEmbedding, WeightOnlyNorm, compute_dtype, logger
+from .processors import FinoCogVideoXAttnProcessor, tensor_key
 from .wan import Transformer2DModelOutput
 
 
@@ -74,7 +74,7 @@ class CogVideoXPatchEmbed(nn.Module):
         Constant per canvas shape, so it is built once with torch ops and cached."""
         if not (self.use_positional_embeddings or self.use_learned_positional_embeddings):
             return None
-        key = (text_len, frames, height, width, dtype, self.pos_embedding.data_ptr(), self.pos_embedding._version)
+        key = (text_len, frames, height, width, dtype, tensor_key(self.pos_embedding))
         hit = self._pos_cache.get(key)
         if hit is not None:
             return hit
@@ -118,7 +118,7 @@ class LayerNormZero(nn.Module):
         w, b = self.norm.weight, self.norm.bias
         if w is None:
             return None, None
-        key = (w.data_ptr(), w._version, b.data_ptr(), b._version)
+        key = (tensor_key(w), tensor_key(b))
         if self._f32 is None or self._f32[0] != key:
             self._f32 = (key, w.detach().float().contiguous(), b.detach().float().contiguous())
         return self._f32[1], self._f32[2]
@@ -148,6 +148,7 @@ class CogVideoXBlock(nn.Module):
     def forward(self, joint: torch.Tensor, text_len: int, emb_f32: torch.Tensor, row_index: torch.Tensor,
                 image_rotary_emb) -> torch.Tensor:
         dim = joint.shape[-1]
+        tap = self.__dict__.pop("_fino_tap", None)  # parity tests: (dict, "transformer_blocks.i")
         # norm1 + attention + gated residual (:134-147)
         m1 = self._mods(self.norm1, emb_f32)
         g, b = self.norm1.affine_f32()
@@ -163,6 +164,8 @@ class CogVideoXBlock(nn.Module):
             a = torch.cat([a_t, a_v], dim=1).contiguous()
             joint = ops.gate_residual(joint, a, m1[:, 2 * dim:3 * dim], row_index=row_index, round_product=True,
                                       out=joint)
+        if tap is not None:
+            tap[0][tap[1] + ".after_attn"] = joint.clone()  # joint [text | video] rows after :146-147
         # norm2 + feed-forward + gated residual (:150-159)
         m2 = self._mods(self.norm2, emb_f32)
         g, b = self.norm2.affine_f32()
@@ -257,7 +260,7 @@ class CogVideoXTransformer3DModel(ModelBase):
         self.sequence_parallel = None  # set by frameino_b200.ulysses.enable_sequence_parallel (mode="nccl")
 
     def to_inference_dtype(self, dtype: torch.dtype = torch.bfloat16) -> "CogVideoXTransformer3DModel":
-        return self.to(dtype)
+        return self.to(compute_dtype(dtype))  # float16 (reference app.py:156) -> bf16 with a warning
 
     def prepare(self) -> "CogVideoXTransformer3DModel":
         """Concatenated q|k|v projection weights, built once after loading instead of on the first forward."""
@@ -303,7 +306,8 @@ class CogVideoXTransformer3DModel(ModelBase):
             raise RuntimeError("frameino_b200 has no CPU path: move the model and inputs to a CUDA device")
         dt = self.proj_out.weight.dtype
         if dt != torch.bfloat16:
-            raise NotImplementedError(f"model dtype {dt}: call .to_inference_dtype(torch.bfloat16) first")
+            raise NotImplementedError(f"model dtype {dt}: call .to_inference_dtype(torch.bfloat16) first "
+                                      "(torch.float16 is accepted there and converted to bf16)")
         cfg = self.config
         batch, frames, channels, height, width = hidden_states.shape
         p = cfg.patch_size
@@ -371,6 +375,8 @@ class CogVideoXTransformer3DModel(ModelBase):
         if taps is not None:
             taps["patch_embed"] = joint.clone()
         for i, block in enumerate(self.transformer_blocks):
+            if taps is not None:
+                block.__dict__["_fino_tap"] = (taps, f"transformer_blocks.{i}")
             joint = block(joint, text_loc, emb, row_index, rope_loc)
             if taps is not None:
                 taps[f"transformer_blocks.{i}.out"] = joint[:, text_loc:].clone()
@@ -379,7 +385,7 @@ class CogVideoXTransformer3DModel(ModelBase):
         # 4. final norms + projection (:531-542)
         nf = self.norm_final
         if nf.weight is not None:
-            key = (nf.weight.data_ptr(), nf.weight._version, nf.bias._version)
+            key = (tensor_key(nf.weight), tensor_key(nf.bias))
             if self._nf_f32 is None or self._nf_f32[0] != key:
                 self._nf_f32 = (key, nf.weight.detach().float().contiguous(), nf.bias.detach().float().contiguous())
             g, bta = self._nf_f32[1], self._nf_f32[2]

@@ -30,6 +30,7 @@ int timestep_embedding(const float* t, float* out, int n, int dim, int flip_sin_
                        float scale, float max_period, cudaStream_t stream);
 int linear_small_m(const float* x, const void* w, const void* b, float* y, int m, int n, int k, int w_is_bf16,
                    int act_in, int act_out, int round_in, int round_out, cudaStream_t stream);
+int timestep_dedup(const float* t, int64_t n, float* uniq, int32_t* row_index, int32_t* count, cudaStream_t stream);
 int build_mod_table(const float* table, const float* proj, float* out, int layers, int r, int cols,
                     int64_t table_layer_stride, cudaStream_t stream);
 int swap01(const void* in, void* out, int64_t A, int64_t B, int64_t inner, cudaStream_t stream);
@@ -175,6 +176,10 @@ int fino_linear_small_m(const float* x, const void* w, const void* b, float* y, 
                         int act_in, int act_out, int round_in, int round_out, void* stream) {
   FINO_ENTRY(fino::linear_small_m(x, w, b, y, m, n, k, w_is_bf16, act_in, act_out, round_in, round_out,
                                   (cudaStream_t)stream));
+}
+
+int fino_timestep_dedup(const float* t, int64_t n, float* uniq8, int32_t* row_index, int32_t* count, void* stream) {
+  FINO_ENTRY(fino::timestep_dedup(t, n, uniq8, row_index, count, (cudaStream_t)stream));
 }
 
 int fino_build_mod_table(const float* table, const float* proj, float* out, int layers, int r, int cols,

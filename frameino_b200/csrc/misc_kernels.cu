@@ -150,7 +150,9 @@ int timestep_embedding(const float* t, float* out, int n, int dim, int flip_sin_
 }
 
 // ------------------------------------------------------------------------------------------------
-// y[m,n] = act_out( sum_k act_in(x[m,k]) * w[n,k] + b[n] ),  m <= 8.  One warp per output column.
+// y[m,n] = act_out( sum_k act_in(x[m,k]) * w[n,k] + b[n] ).  One warp per output column and 8-row chunk
+//   (blockIdx.y): built for m <= 8 (the de-duplicated time MLP); larger m runs as ceil(m/8) independent chunks, each
+//   row computed exactly as in the m <= 8 case (fp32 FMA chain over k in the same order).
 //   x, y fp32; w/b fp32 or bf16.  act: 0 none, 1 SiLU.  round_in / round_out emulate a bf16 module.
 // ------------------------------------------------------------------------------------------------
 constexpr int SMALL_M_MAX = 8;
@@ -167,9 +169,13 @@ __device__ __forceinline__ float silu_exact(float x) { return x / (1.0f + expf(-
 template <typename WT>
 __global__ void __launch_bounds__(256)
 linear_small_m_kernel(const float* __restrict__ x, const WT* __restrict__ w, const WT* __restrict__ b,
-                      float* __restrict__ y, int m, int n, int k, int act_in, int act_out, int round_in,
+                      float* __restrict__ y, int m_total, int n, int k, int act_in, int act_out, int round_in,
                       int round_out) {
   extern __shared__ float xs[];  // [m, k] after the input activation
+  const int row0 = blockIdx.y * SMALL_M_MAX;
+  const int m = min(SMALL_M_MAX, m_total - row0);
+  x += (int64_t)row0 * k;
+  y += (int64_t)row0 * n;
   for (int i = threadIdx.x; i < m * k; i += blockDim.x) {
     float v = x[i];
     if (act_in == 1) v = silu_exact(v);
@@ -212,12 +218,12 @@ linear_small_m_kernel(const float* __restrict__ x, const WT* __restrict__ w, con
 int linear_small_m(const float* x, const void* w, const void* b, float* y, int m, int n, int k, int w_is_bf16,
                    int act_in, int act_out, int round_in, int round_out, cudaStream_t stream) {
   FINO_CHECK_ARG(x && w && y, "linear_small_m: null pointer");
-  FINO_CHECK_ARG(m > 0 && m <= SMALL_M_MAX, "linear_small_m: m=%d out of range (1..%d)", m, SMALL_M_MAX);
+  FINO_CHECK_ARG(m > 0 && m <= SMALL_M_MAX * 65535, "linear_small_m: m=%d out of range", m);
   FINO_CHECK_ARG(n > 0 && k > 0, "linear_small_m: bad shape");
-  const size_t smem = (size_t)m * k * sizeof(float);
+  const size_t smem = (size_t)(m < SMALL_M_MAX ? m : SMALL_M_MAX) * k * sizeof(float);
   FINO_CHECK_ARG(smem <= 200 * 1024, "linear_small_m: m*k too large for shared memory");
   const int warps = 8;
-  dim3 grid((n + warps - 1) / warps);
+  dim3 grid((n + warps - 1) / warps, (m + SMALL_M_MAX - 1) / SMALL_M_MAX);
   if (w_is_bf16) {
     static bool cfg = false;
     if (!cfg) {
@@ -237,6 +243,84 @@ int linear_small_m(const float* x, const void* w, const void* b, float* y, int m
     linear_small_m_kernel<float><<<grid, warps * 32, smem, stream>>>(x, (const float*)w, (const float*)b, y, m, n, k,
                                                                       act_in, act_out, round_in, round_out);
   }
+  FINO_CHECK_CUDA(cudaGetLastError());
+  return FINO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// De-duplication of the per-token timesteps on the device (replaces the torch.unique radix sort + host sync at the top
+// of every forward): the FrameINO sampler passes two distinct values (0 on the clean first frame, t elsewhere;
+// pipeline_wan_i2v_motion_FrameINO.py:832-843), the general case is capped at 8.
+//   uniq[0..8)   the distinct values in ascending order (torch.unique order), unused slots repeat the largest
+//   row_index[i] the position of t[i] in uniq
+//   count[0]     the number of distinct values; 9 = more than 8 were seen (uniq/row_index are then unusable)
+// One 1024-thread block: a block-wide membership test per 1024-element chunk; a chunk that holds an unseen value adds
+// ONE value (that of the lowest thread that holds one) and re-tests, so the list grows in first-appearance order.
+// ------------------------------------------------------------------------------------------------
+constexpr int DEDUP_MAX = 8;
+
+__global__ void __launch_bounds__(1024)
+timestep_dedup_kernel(const float* __restrict__ t, int64_t n, float* __restrict__ uniq, int32_t* __restrict__ row_index,
+                      int32_t* __restrict__ count) {
+  __shared__ float s_list[DEDUP_MAX];
+  __shared__ int s_n, s_pick, s_over;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    s_n = 0;
+    s_pick = 0x7fffffff;
+    s_over = 0;
+  }
+  __syncthreads();
+  for (int64_t base = 0; base < n && !s_over; base += blockDim.x) {
+    const int64_t i = base + tid;
+    const bool has = i < n;
+    const float x = has ? t[i] : 0.f;
+    while (true) {
+      const int cnt = s_n;
+      bool found = !has;
+      for (int j = 0; j < cnt; ++j) found |= (s_list[j] == x);
+      if (!__syncthreads_or(!found)) break;
+      if (!found) atomicMin(&s_pick, tid);
+      __syncthreads();
+      if (tid == s_pick) {
+        if (s_n < DEDUP_MAX) s_list[s_n++] = x;
+        else s_over = 1;
+        s_pick = 0x7fffffff;
+      }
+      __syncthreads();
+      if (s_over) break;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const int cnt = s_n;
+    for (int a = 1; a < cnt; ++a) {  // insertion sort, ascending
+      const float v = s_list[a];
+      int b = a - 1;
+      while (b >= 0 && s_list[b] > v) {
+        s_list[b + 1] = s_list[b];
+        --b;
+      }
+      s_list[b + 1] = v;
+    }
+    for (int j = 0; j < DEDUP_MAX; ++j) uniq[j] = cnt > 0 ? s_list[j < cnt ? j : cnt - 1] : 0.f;
+    count[0] = s_over ? DEDUP_MAX + 1 : cnt;
+  }
+  __syncthreads();
+  const int cnt = s_n;
+  for (int64_t i = tid; i < n; i += blockDim.x) {
+    const float x = t[i];
+    int idx = 0;
+    for (int j = 0; j < cnt; ++j)
+      if (s_list[j] == x) idx = j;
+    row_index[i] = idx;
+  }
+}
+
+int timestep_dedup(const float* t, int64_t n, float* uniq, int32_t* row_index, int32_t* count, cudaStream_t stream) {
+  FINO_CHECK_ARG(t && uniq && row_index && count && n > 0, "timestep_dedup: bad arguments");
+  timestep_dedup_kernel<<<1, 1024, 0, stream>>>(t, n, uniq, row_index, count);
   FINO_CHECK_CUDA(cudaGetLastError());
   return FINO_OK;
 }

@@ -138,6 +138,10 @@ def from_pretrained(model_cls, path: str, subfolder: Optional[str] = None,
     cfg.update(config_overrides)
     import inspect
 
+    from .modules import compute_dtype
+
+    torch_dtype = compute_dtype(torch_dtype)  # float16 (reference app.py:156) -> bf16 with a warning; fp32 refused
+
     accepted = set(inspect.signature(model_cls.__init__).parameters) - {"self"}
     dropped = sorted(k for k in cfg if k not in accepted)
     if dropped:

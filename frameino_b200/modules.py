@@ -169,6 +169,22 @@ class TextProjection(nn.Module):
         self.linear_2 = nn.Linear(hidden_size, hidden_size)
 
 
+def compute_dtype(requested: torch.dtype) -> torch.dtype:
+    """The dtype the kernels will run a model in when ``requested`` is asked for. The sm_100a kernels compute in bf16
+    (fp32 accumulation and fp32 islands). The reference demo loads its transformer with ``torch_dtype=torch.float16``
+    (app.py:156): that request is honoured by CONVERTING to bf16, loudly — same 16-bit storage, 8 instead of 11
+    significand bits, fp32's exponent range (no fp16 overflow handling needed); ``model.dtype`` then reports bfloat16,
+    which is what the pipeline casts its inputs to (pipeline_wan_i2v_motion_FrameINO.py:746). fp32 is refused."""
+    if requested == torch.bfloat16:
+        return requested
+    if requested == torch.float16:
+        logger.warning("frameino_b200 computes in bfloat16: torch_dtype=float16 weights are converted to bfloat16 "
+                       "(model.dtype reports bfloat16; outputs are bfloat16)")
+        return torch.bfloat16
+    raise NotImplementedError(f"frameino_b200 kernels compute in bf16; cannot run the model in {requested} "
+                              "(use torch.bfloat16, or torch.float16 which is converted to bf16 with a warning)")
+
+
 class ModelBase(nn.Module):
     """The slice of diffusers ModelMixin/ConfigMixin/CacheMixin that the FrameINO pipelines touch."""
 
@@ -202,6 +218,14 @@ class ModelBase(nn.Module):
         out = super()._apply(fn, *args, **kwargs)
         self.drop_derived_state()
         return out
+
+    def invalidate(self) -> "ModelBase":
+        """Call after changing weights IN PLACE through ``.data`` (e.g. merging a LoRA with ``w.data.add_(delta)``):
+        such writes neither move the storage nor bump the version counter the derived-weight caches are keyed on
+        (``processors.tensor_key``), so the concatenated projections / stacked tables / per-prompt text state would be
+        stale. Weights are otherwise treated as frozen once ``prepare()`` or the first forward has run."""
+        self.drop_derived_state()
+        return self
 
     def drop_derived_state(self) -> None:
         for mod in self.modules():

@@ -290,7 +290,8 @@ def timestep_embedding(t: torch.Tensor, dim: int, flip_sin_to_cos: bool = True, 
 
 def linear_small_m(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], *, act_in: int = 0,
                    act_out: int = 0, round_in: bool = False, round_out: bool = False) -> torch.Tensor:
-    """fp32 [m<=8, K] x (fp32|bf16) [N, K] -> fp32 [m, N]."""
+    """fp32 [m, K] x (fp32|bf16) [N, K] -> fp32 [m, N] with fp32 accumulation (built for m <= 8; larger m runs as
+    independent 8-row chunks inside one launch)."""
     assert x.dtype == torch.float32 and x.dim() == 2 and x.is_contiguous()
     assert weight.dtype in (torch.float32, torch.bfloat16) and weight.is_contiguous()
     if bias is not None:
@@ -305,6 +306,19 @@ def linear_small_m(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.T
                                      1 if round_in else 0, 1 if round_out else 0, stream)
     _lib.check(status, "fino_linear_small_m")
     return out
+
+
+def timestep_dedup(t: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Device-side de-duplication of per-token timesteps (no host sync): fp32 [n] -> (uniq fp32 [8] ascending with the
+    unused slots repeating the largest value, row_index int32 [n], count int32 [1] = distinct values, 9 = more than 8)."""
+    assert t.dtype == torch.float32 and t.dim() == 1 and t.is_contiguous() and t.numel() > 0
+    lib, stream = _prep(t)
+    uniq = torch.empty(8, dtype=torch.float32, device=t.device)
+    row_index = torch.empty(t.numel(), dtype=torch.int32, device=t.device)
+    count = torch.empty(1, dtype=torch.int32, device=t.device)
+    _lib.check(lib.fino_timestep_dedup(t.data_ptr(), t.numel(), uniq.data_ptr(), row_index.data_ptr(), count.data_ptr(),
+                                       stream), "fino_timestep_dedup")
+    return uniq, row_index, count
 
 
 def build_mod_table(table: torch.Tensor, proj: torch.Tensor, layers: int, table_layer_stride: int) -> torch.Tensor:

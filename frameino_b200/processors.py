@@ -16,11 +16,31 @@ import torch
 from . import ops
 
 
+def tensor_key(t: Optional[torch.Tensor]):
+    """Identity of a tensor for the derived-weight caches: storage address, shape, dtype and the autograd in-place
+    version counter. Inference tensors (created under ``torch.inference_mode()``) do not track a version — reading
+    ``_version`` on them raises — so they are keyed by address alone.
+
+    CONTRACT: the caches (concatenated q|k|v / k|v weights, stacked modulation tables, fp32 copies of norm affines,
+    the per-prompt ``WanTextState``) see a change only if it bumps ``_version`` or moves the storage. Updates written
+    through ``.data`` (``w.data.add_(delta)``, the usual LoRA-merge idiom) do neither: weights are FROZEN once
+    ``model.prepare()`` or the first forward has run; after changing them in place call ``model.invalidate()``
+    (or ``invalidate_derived(attn)`` for a single attention module on a foreign model)."""
+    if t is None:
+        return None
+    return (t.data_ptr(), None if t.is_inference() else t._version, tuple(t.shape), t.dtype)
+
+
+def invalidate_derived(module) -> None:
+    """Drops the derived weights cached on ``module`` (an attention container the native processors have run on)."""
+    module.__dict__.pop("_fino_cache", None)
+
+
 def _fused_weights(attn, names: Tuple[str, ...], tag: str):
     """Concatenated [sum(out), in] weight (+bias) of several nn.Linear projections, cached on the module and
-    refreshed when any source parameter changes (data_ptr / in-place version)."""
+    refreshed when any source parameter changes (see ``tensor_key`` for what counts as a change)."""
     mods = [getattr(attn, n) for n in names]
-    key = tuple((m.weight.data_ptr(), m.weight._version, None if m.bias is None else m.bias._version) for m in mods)
+    key = tuple((tensor_key(m.weight), tensor_key(m.bias)) for m in mods)
     cache = attn.__dict__.setdefault("_fino_cache", {})
     hit = cache.get(tag)
     if hit is not None and hit[0] == key:

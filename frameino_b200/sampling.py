@@ -190,6 +190,95 @@ def scaled_linear_alphas_cumprod(num_train_timesteps: int = 1000, beta_start: fl
     return ac.float()
 
 
+def rescale_zero_terminal_snr(alphas_cumprod: torch.Tensor) -> torch.Tensor:
+    """Zero-terminal-SNR rescale of a cumulative-alpha table (Lin et al. 2023, algorithm 1), as the CogVideoX schedulers
+    apply it to ``alphas_cumprod`` (upstream diffusers, recalled)."""
+    s = alphas_cumprod.double().sqrt()
+    s0, st = s[0].clone(), s[-1].clone()
+    s = (s - st) * (s0 / (s0 - st))
+    return (s ** 2).to(alphas_cumprod.dtype)
+
+
+class CogVideoXDPMSchedule:
+    """The arithmetic of diffusers' ``CogVideoXDPMScheduler`` that the FrameINO CogVideoX pipeline drives
+    (pipelines/pipeline_cogvideox_i2v_motion_FrameINO.py:30, :915-926: ``step(noise_pred, old_pred_original_sample, t,
+    timesteps[i-1] if i > 0 else None, latents, ...) -> (prev_sample, pred_original_sample)``). The class itself lives
+    upstream in diffusers, not in the reference tree, so this is a restatement of its published algorithm from recalled
+    semantics: DPM-Solver++(2M) SDE on the VP schedule — ``scaled_linear`` betas 0.00085..0.012, SNR shift
+    (``snr_shift_scale`` 1.0 for CogVideoX-5B, 3.0 for 2B), zero-terminal-SNR rescale, ``trailing`` timestep spacing,
+    v-prediction. ``tests/test_cog_loop.py`` checks it against the closed form of the paper (Lu et al. 2022, eq. for the
+    second-order multistep SDE solver) written in (alpha, sigma, lambda) form."""
+
+    def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.00085, beta_end: float = 0.012,
+                 snr_shift_scale: float = 1.0, rescale_betas_zero_snr: bool = True, prediction_type: str = "v_prediction"):
+        ac = scaled_linear_alphas_cumprod(num_train_timesteps, beta_start, beta_end, snr_shift_scale)
+        self.alphas_cumprod = rescale_zero_terminal_snr(ac) if rescale_betas_zero_snr else ac
+        self.final_alpha_cumprod = torch.tensor(1.0)  # set_alpha_to_one
+        self.num_train_timesteps = num_train_timesteps
+        self.prediction_type = prediction_type
+        self.num_inference_steps = None
+        self.timesteps = None
+        self.order = 1
+        self.init_noise_sigma = 1.0
+
+    def set_timesteps(self, num_inference_steps: int, device=None) -> torch.Tensor:
+        """``timestep_spacing="trailing"``: round(arange(T, 0, -T/steps)) - 1."""
+        self.num_inference_steps = num_inference_steps
+        ratio = self.num_train_timesteps / num_inference_steps
+        ts = torch.round(torch.arange(self.num_train_timesteps, 0, -ratio, dtype=torch.float64)).long() - 1
+        self.timesteps = ts.to(device) if device is not None else ts
+        return self.timesteps
+
+    def scale_model_input(self, sample: torch.Tensor, timestep=None) -> torch.Tensor:
+        return sample
+
+    @staticmethod
+    def _lambda(alpha_prod: torch.Tensor) -> torch.Tensor:
+        return ((alpha_prod / (1 - alpha_prod)) ** 0.5).log()
+
+    def coefficients(self, timestep: int, timestep_back: Optional[int]):
+        """(alpha_t, alpha_prev, mult1, mult2, mult3 | None, mult4 | None, mult_noise, prev_timestep) as 0-d tensors."""
+        prev_timestep = int(timestep) - self.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[int(timestep)]
+        a_prev = self.alphas_cumprod[prev_timestep] if prev_timestep >= 0 else self.final_alpha_cumprod
+        a_back = self.alphas_cumprod[int(timestep_back)] if timestep_back is not None else None
+        lamb, lamb_next = self._lambda(a_t), self._lambda(a_prev)
+        h = lamb_next - lamb
+        mult1 = ((1 - a_prev) / (1 - a_t)) ** 0.5 * (-h).exp()
+        mult2 = (-2 * h).expm1() * a_prev ** 0.5
+        mult3 = mult4 = None
+        if a_back is not None:
+            r = (lamb - self._lambda(a_back)) / h
+            mult3, mult4 = 1 + 1 / (2 * r), 1 / (2 * r)
+        mult_noise = (1 - a_prev) ** 0.5 * (1 - (-2 * h).exp()) ** 0.5
+        return a_t, a_prev, mult1, mult2, mult3, mult4, mult_noise, prev_timestep
+
+    def step(self, model_output: torch.Tensor, old_pred_original_sample: Optional[torch.Tensor], timestep,
+             timestep_back, sample: torch.Tensor, eta: float = 0.0, generator=None, noise: Optional[torch.Tensor] = None,
+             return_dict: bool = False):
+        """One solver step. ``noise``: the standard-normal draw to use (else drawn from ``generator`` on the sample's
+        device); the SDE solver adds ``mult_noise * noise`` every step (it vanishes on the last one)."""
+        if self.num_inference_steps is None:
+            raise ValueError("set_timesteps must run before step")
+        a_t, a_prev, m1, m2, m3, m4, m_noise, prev_timestep = self.coefficients(int(timestep), timestep_back)
+        if self.prediction_type == "v_prediction":
+            x0 = a_t ** 0.5 * sample - (1 - a_t) ** 0.5 * model_output
+        elif self.prediction_type == "epsilon":
+            x0 = (sample - (1 - a_t) ** 0.5 * model_output) / a_t ** 0.5
+        elif self.prediction_type == "sample":
+            x0 = model_output
+        else:
+            raise ValueError(f"prediction_type {self.prediction_type!r}")
+        if noise is None:
+            noise = torch.randn(sample.shape, generator=generator, device=sample.device, dtype=sample.dtype)
+        if old_pred_original_sample is None or prev_timestep < 0:
+            prev = m1 * sample - m2 * x0 + m_noise * noise  # first step and last step: first order
+        else:
+            denoised = m3 * x0 - m4 * old_pred_original_sample
+            prev = m1 * sample - m2 * denoised + m_noise * noise
+        return prev, x0
+
+
 @torch.no_grad()
 def cog_frameino_denoise(
     transformer: Callable,
@@ -200,20 +289,24 @@ def cog_frameino_denoise(
     prompt_embeds: torch.Tensor,    # [2, T, text_dim] = cat(negative, positive) when guidance is on (:767-768), else [1, ...]
     image_rotary_emb,
     timesteps,                      # decreasing integer timesteps, e.g. torch.linspace(999, 0, steps).long()
-    alphas_cumprod: torch.Tensor,   # [num_train_timesteps]
+    alphas_cumprod: Optional[torch.Tensor] = None,   # [num_train_timesteps] (DDIM form); unused with ``scheduler``
     guidance_scale: float = 6.0,
     use_dynamic_cfg: bool = False,
     model_dtype: torch.dtype = torch.bfloat16,
+    scheduler: Optional[CogVideoXDPMSchedule] = None,  # the pipeline's CogVideoXDPMScheduler branch (:918-926)
+    generator=None,
 ) -> torch.Tensor:
     """The hot loop of pipelines/pipeline_cogvideox_i2v_motion_FrameINO.py:846-927 around the transformer forward:
     batched CFG (:853, :856, :859), frame-wise ID concat with zero padding of the image / trajectory streams (:862-873),
     channel-wise concat (:877), ID-frame drop (:899-900), dynamic guidance (:904-909), CFG combine (:910-912), scheduler
-    step (here ``ddim_v_step``) and the cast back to the prompt dtype (:927). Plain torch: drives the native model or
-    any callable with the reference forward signature."""
+    step — ``CogVideoXDPMSchedule.step`` with its two history arguments when ``scheduler`` is given (:918-926), else the
+    DDIM-style ``ddim_v_step`` (:916) — and the cast back to the prompt dtype (:927). Plain torch: drives the native model
+    or any callable with the reference forward signature."""
     do_cfg = guidance_scale > 1.0
     steps = len(timesteps)
     n_frames = latents.shape[1]
     lat = latents
+    old_x0 = None  # "for DPM-solver++" (:848)
     for i in range(steps):
         t = timesteps[i]
         x = torch.cat([lat] * 2) if do_cfg else lat
@@ -235,7 +328,12 @@ def cog_frameino_denoise(
         if do_cfg:
             v_uncond, v_text = v.chunk(2)
             v = v_uncond + g * (v_text - v_uncond)
-        a_t = alphas_cumprod[int(t)]
-        a_prev = alphas_cumprod[int(timesteps[i + 1])] if i + 1 < steps else torch.tensor(1.0)
-        lat = ddim_v_step(v, lat.float(), a_t, a_prev).to(prompt_embeds.dtype)
+        if scheduler is not None:
+            lat_new, old_x0 = scheduler.step(v, old_x0, int(t), int(timesteps[i - 1]) if i > 0 else None, lat.float(),
+                                             generator=generator)
+            lat = lat_new.to(prompt_embeds.dtype)
+        else:
+            a_t = alphas_cumprod[int(t)]
+            a_prev = alphas_cumprod[int(timesteps[i + 1])] if i + 1 < steps else torch.tensor(1.0)
+            lat = ddim_v_step(v, lat.float(), a_t, a_prev).to(prompt_embeds.dtype)
     return lat

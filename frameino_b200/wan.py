@@ -20,8 +20,9 @@ import torch
 from torch import nn
 
 from . import ops
-from .modules import Attention, FeedForward, ModelBase, TextProjection, TimestepEmbedding, WeightOnlyNorm, logger
-from .processors import FinoWanAttnProcessor
+from .modules import (Attention, FeedForward, ModelBase, TextProjection, TimestepEmbedding, WeightOnlyNorm,
+                      compute_dtype, logger)
+from .processors import FinoWanAttnProcessor, tensor_key
 
 
 @dataclass
@@ -132,6 +133,18 @@ class WanTransformerBlock(nn.Module):
         self.norm3 = WeightOnlyNorm(dim, eps, elementwise_affine=False)
         self.scale_shift_table = nn.Parameter(torch.randn(1, 6, dim) / dim ** 0.5)
 
+    def _norm2_affine(self):
+        """norm2's gain / bias as fp32 (FP32LayerNorm computes in fp32 whatever dtype the parameters were cast to:
+        ``_keep_in_fp32_modules`` keeps them fp32, a plain ``model.to(torch.bfloat16)`` does not)."""
+        w, b = self.norm2.weight, self.norm2.bias
+        if w.dtype == torch.float32 and b.dtype == torch.float32:
+            return w, b
+        key = (tensor_key(w), tensor_key(b))
+        hit = self.__dict__.get("_fino_cache")
+        if hit is None or hit[0] != key:
+            hit = self.__dict__["_fino_cache"] = (key, w.detach().float().contiguous(), b.detach().float().contiguous())
+        return hit[1], hit[2]
+
     def forward(self, hidden_states: torch.Tensor, encoder_hidden_states: torch.Tensor, mod: torch.Tensor,
                 row_index: Optional[torch.Tensor], rows_per_group: int, rotary_emb, text_kv=None) -> torch.Tensor:
         """``mod``: fp32 [R, 6*dim] = scale_shift_table + timestep_proj rows (shift, scale, gate, c_shift, c_scale,
@@ -139,21 +152,28 @@ class WanTransformerBlock(nn.Module):
         pre-projected cross-attention (k, v) from a ``WanTextState`` (native processor only)."""
         x = hidden_states
         dim = x.shape[-1]
+        tap = self.__dict__.pop("_fino_tap", None)  # parity tests: (dict, "blocks.i") collects intermediate tensors
         shift, scale, gate = mod[:, 0:dim], mod[:, dim:2 * dim], mod[:, 2 * dim:3 * dim]
         c_shift, c_scale, c_gate = mod[:, 3 * dim:4 * dim], mod[:, 4 * dim:5 * dim], mod[:, 5 * dim:6 * dim]
         sel = dict(row_index=row_index, rows_per_group=rows_per_group)
 
         # 1. self-attention (:334-336)
         h = ops.ln_modulate(x, self.eps, shift=shift, scale=scale, **sel)
+        if tap is not None:
+            tap[0][tap[1] + ".norm1"] = h.clone()
         if isinstance(self.attn1.processor, FinoWanAttnProcessor):
             x = self.attn1(hidden_states=h, rotary_emb=rotary_emb, fino_residual=(x, gate, row_index, rows_per_group))
         else:  # foreign processor plugged in through set_processor: keep the reference dataflow
             a = self.attn1(hidden_states=h, rotary_emb=rotary_emb)
             x = ops.gate_residual(x, a.contiguous(), gate, out=x, **sel)
 
+        if tap is not None:
+            tap[0][tap[1] + ".after_attn1"] = x.clone()
+
         # 2. cross-attention (:339-341)
         if isinstance(self.norm2, WeightOnlyNorm):
-            h = ops.ln_modulate(x, self.eps, gamma=self.norm2.weight, beta=self.norm2.bias, out=h)
+            g2, b2 = self._norm2_affine()
+            h = ops.ln_modulate(x, self.eps, gamma=g2, beta=b2, out=h)
         else:
             h = x
         if isinstance(self.attn2.processor, FinoWanAttnProcessor):
@@ -162,6 +182,9 @@ class WanTransformerBlock(nn.Module):
         else:
             a = self.attn2(hidden_states=h, encoder_hidden_states=encoder_hidden_states)
             x = ops.gate_residual(x, a.contiguous(), out=x)
+
+        if tap is not None:
+            tap[0][tap[1] + ".after_attn2"] = x.clone()
 
         # 3. feed-forward (:344-348)
         h = ops.ln_modulate(x, self.eps, shift=c_shift, scale=c_scale, out=h if h is not x else None, **sel)
@@ -226,7 +249,9 @@ class WanTransformer3DModel(ModelBase):
 
     # ------------------------------------------------------------------------------------------------------------
     def to_inference_dtype(self, dtype: torch.dtype = torch.bfloat16) -> "WanTransformer3DModel":
-        """Casts like ``from_pretrained(torch_dtype=bf16)`` + ``_keep_in_fp32_modules`` (transformer_wan.py:393)."""
+        """Casts like ``from_pretrained(torch_dtype=bf16)`` + ``_keep_in_fp32_modules`` (transformer_wan.py:393).
+        ``torch.float16`` (the reference demo's choice, app.py:156) is converted to bf16 with a warning."""
+        dtype = compute_dtype(dtype)
         for name, p in self.named_parameters():
             keep = any(k in name for k in self._keep_in_fp32_modules)
             p.data = p.data.to(torch.float32 if keep else dtype)
@@ -245,21 +270,37 @@ class WanTransformer3DModel(ModelBase):
 
     def _stacked_tables(self) -> torch.Tensor:
         """[L, 6*D] fp32 copy of every block's scale_shift_table (refreshed if a table changes)."""
-        key = tuple((b.scale_shift_table.data_ptr(), b.scale_shift_table._version) for b in self.blocks)
+        key = tuple(tensor_key(b.scale_shift_table) for b in self.blocks)
         if self._sst_cache is None or self._sst_cache[0] != key:
             with torch.no_grad():
                 t = torch.stack([b.scale_shift_table.reshape(-1).float() for b in self.blocks]).contiguous()
             self._sst_cache = (key, t)
         return self._sst_cache[1]
 
-    def _conditioning(self, timestep: torch.Tensor, batch: int, tokens: int):
+    def _conditioning(self, timestep: torch.Tensor, batch: int, tokens: int, dedup: str = "device"):
         """De-duplicated time MLP. Returns (temb_rows fp32-of-bf16 [R, D], proj_rows fp32-of-bf16 [R, 6D],
-        row_index int32 [B*N] or None, rows_per_group)."""
-        if timestep.ndim == 2:  # [B, N] per-token timesteps (wan 2.2 ti2v, transformer_wan.py:490-492)
+        row_index int32 [B*N] or None, rows_per_group).
+
+        Per-token timesteps ([B, N], wan 2.2 ti2v, transformer_wan.py:490-492) are de-duplicated ON THE DEVICE
+        (``fino_timestep_dedup``: up to 8 distinct values, no host round trip; the FrameINO sampler passes two). The
+        number of distinct values is copied to pinned host memory behind an event that ``forward`` checks after it has
+        queued the whole step; only if more than 8 were seen does it re-run with ``dedup="unique"`` (torch.unique)."""
+        if timestep.ndim == 2:
             if timestep.shape != (batch, tokens):
                 raise ValueError(f"timestep shape {tuple(timestep.shape)} != (batch, tokens) = ({batch}, {tokens})")
-            uniq, inverse = torch.unique(timestep.reshape(-1).float(), return_inverse=True)
-            row_index = inverse.to(torch.int32).contiguous()
+            flat = timestep.reshape(-1).float().contiguous()
+            if dedup == "device":
+                uniq, row_index, count = ops.timestep_dedup(flat)
+                host = self.__dict__.get("_fino_dedup_host")
+                if host is None:
+                    host = self.__dict__["_fino_dedup_host"] = torch.zeros(1, dtype=torch.int32).pin_memory()
+                    self.__dict__["_fino_dedup_event"] = torch.cuda.Event()
+                host.copy_(count, non_blocking=True)
+                self.__dict__["_fino_dedup_event"].record()
+                self.__dict__["_fino_dedup_pending"] = True
+            else:
+                uniq, inverse = torch.unique(flat, return_inverse=True)
+                row_index = inverse.to(torch.int32).contiguous()
             rows_per_group = 0
         else:
             if timestep.ndim == 0:
@@ -272,31 +313,31 @@ class WanTransformer3DModel(ModelBase):
         temb, proj = self.time_rows(uniq)
         return temb, proj, row_index, rows_per_group
 
+    def _dedup_overflowed(self) -> bool:
+        """True when the device-side de-duplication of the forward just queued saw more than 8 distinct timesteps.
+        Waits only for the event recorded right after the first kernel of that forward, not for the forward."""
+        if not self.__dict__.pop("_fino_dedup_pending", False):
+            return False
+        self.__dict__["_fino_dedup_event"].synchronize()
+        return int(self.__dict__["_fino_dedup_host"][0]) > 8
+
     def time_rows(self, uniq: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """Time MLP on distinct timestep values (fp32 [R]): (temb [R, D], timestep_proj [R, 6D]), fp32 holding the
         bf16-rounded module outputs (transformer_wan.py:175-183). Row r is what the reference computes for every token
-        whose timestep is uniq[r]."""
+        whose timestep is uniq[r]: the fp32 ``time_embedder`` (``_keep_in_fp32_modules``, :393) runs in fp32 with fp32
+        accumulation for ANY number of rows (8-row chunks inside one launch), its result is rounded to the model dtype
+        (:182) and ``time_proj`` runs as a bf16 module (:183)."""
         ce = self.condition_embedder
-        r = uniq.numel()
         te = ce.time_embedder
         emb = ops.timestep_embedding(uniq.contiguous(), ce.time_freq_dim, True, 0.0)  # :175
         dt = self.proj_out.weight.dtype
-        if r <= 8:
-            w_f32 = te.linear_1.weight.dtype == torch.float32
-            h = ops.linear_small_m(emb, te.linear_1.weight, te.linear_1.bias, act_out=1, round_in=not w_f32,
-                                   round_out=not w_f32)
-            temb = ops.linear_small_m(h, te.linear_2.weight, te.linear_2.bias, round_out=not w_f32)
-            temb = temb.to(dt).float()  # .type_as(encoder_hidden_states), :182
-            proj = ops.linear_small_m(temb, ce.time_proj.weight, ce.time_proj.bias, act_in=1, round_in=True,
-                                      round_out=True)  # :183 (bf16 module)
-        else:
-            # many distinct timesteps: run the MLP on the tensor cores in the model dtype
-            w1, w2 = te.linear_1, te.linear_2
-            h = ops.linear(emb.to(dt), w1.weight.to(dt), w1.bias.to(dt), epilogue=ops.EPI_SILU)
-            temb_b = ops.linear(h, w2.weight.to(dt), w2.bias.to(dt))
-            temb = temb_b.float()
-            s = torch.nn.functional.silu(temb_b)
-            proj = ops.linear(s, ce.time_proj.weight, ce.time_proj.bias).float()
+        w_f32 = te.linear_1.weight.dtype == torch.float32
+        h = ops.linear_small_m(emb, te.linear_1.weight, te.linear_1.bias, act_out=1, round_in=not w_f32,
+                               round_out=not w_f32)
+        temb = ops.linear_small_m(h, te.linear_2.weight, te.linear_2.bias, round_out=not w_f32)
+        temb = temb.to(dt).float()  # .type_as(encoder_hidden_states), :182
+        proj = ops.linear_small_m(temb, ce.time_proj.weight, ce.time_proj.bias, act_in=1, round_in=True,
+                                  round_out=True)  # :183 (bf16 module)
         return temb, proj
 
     # ------------------------------------------------------------------------------------------------------------
@@ -318,11 +359,9 @@ class WanTransformer3DModel(ModelBase):
         self.__dict__["_fino_text_cache"] = {}
 
     def _text_key(self, ehs: torch.Tensor):
-        def ident(t):
-            return None if t is None else (t.data_ptr(), t._version)
-
+        ident = tensor_key  # works for inference-mode prompt embeddings too (no version counter: keyed by address)
         te = self.condition_embedder.text_embedder
-        parts = [ident(ehs), tuple(ehs.shape), tuple(ehs.stride()), ehs.dtype, ehs.device,
+        parts = [ident(ehs), tuple(ehs.stride()), ehs.device,
                  ident(te.linear_1.weight), ident(te.linear_1.bias), ident(te.linear_2.weight), ident(te.linear_2.bias)]
         for b in self.blocks:
             a = b.attn2
@@ -400,6 +439,8 @@ class WanTransformer3DModel(ModelBase):
             taps["patch_embed"] = x.clone()
             taps["text"] = text.clone()
         for i, block in enumerate(self.blocks):  # :516-517
+            if taps is not None:
+                block.__dict__["_fino_tap"] = (taps, f"blocks.{i}")
             x = block(x, text, mod_all[i], row_index, rows_per_group, rotary_emb, text_state.kv[i])
             if taps is not None:
                 taps[f"blocks.{i}.out"] = x.clone()
@@ -419,7 +460,8 @@ class WanTransformer3DModel(ModelBase):
             raise RuntimeError("frameino_b200 has no CPU path: move the model and inputs to a CUDA device")
         dt = self.proj_out.weight.dtype
         if dt != torch.bfloat16:
-            raise NotImplementedError(f"model dtype {dt}: call .to_inference_dtype(torch.bfloat16) first")
+            raise NotImplementedError(f"model dtype {dt}: call .to_inference_dtype(torch.bfloat16) first "
+                                      "(torch.float16 is accepted there and converted to bf16)")
         return dt
 
     @torch.no_grad()
@@ -444,9 +486,12 @@ class WanTransformer3DModel(ModelBase):
 
         hs = hidden_states.to(dt)
         rows = ops.patchify(hs, (batch, channels, frames, height, width), hs.stride(), (p_t, p_h, p_w))
-        conditioning = self._conditioning(timestep, batch, tokens)
         text_state = self._text_state(encoder_hidden_states)
-        y = self.forward_rows(rows, batch, (frames, height, width), conditioning, text_state)
+        for dedup in ("device", "unique"):
+            conditioning = self._conditioning(timestep, batch, tokens, dedup)
+            y = self.forward_rows(rows, batch, (frames, height, width), conditioning, text_state)
+            if not self._dedup_overflowed():
+                break  # (the second pass only runs for > 8 distinct per-token timesteps)
 
         c_out = y.shape[-1] // (p_t * p_h * p_w)
         out = torch.empty(batch, c_out, frames, height, width, dtype=dt, device=y.device)

@@ -137,10 +137,18 @@ int fino_unpatchify(const void* rows, void* out, int b, int c, int f, int h, int
 int fino_timestep_embedding(const float* t, float* out, int n, int dim, int flip_sin_to_cos,
                             float downscale_freq_shift, float scale, float max_period, void* stream);
 
-/* y[m,n] = act_out(act_in(x)[m,k] * w[n,k]^T + b), m <= 8, float activations, w/b float or bf16.
+/* y[m,n] = act_out(act_in(x)[m,k] * w[n,k]^T + b), float activations and accumulation, w/b float or bf16; built for
+ * m <= 8 (larger m runs as independent 8-row chunks, every row computed identically).
  * The de-duplicated time MLP: transformer_wan.py:182-183; cogvideox_transformer_3d.py:485. act: 0 none, 1 SiLU. */
 int fino_linear_small_m(const float* x, const void* w, const void* b, float* y, int m, int n, int k, int w_is_bf16,
                         int act_in, int act_out, int round_in, int round_out, void* stream);
+
+/* De-duplicates the per-token timesteps t[n] (float; transformer_wan.py:490-494 flattens them and runs the time MLP per
+ * token) on the device, without a host round trip: uniq8[8] receives the distinct values in ascending order (unused
+ * slots repeat the largest), row_index[i] the slot of t[i], count[0] the number of distinct values or 9 when more than 8
+ * were seen (the outputs are then unusable and the caller must de-duplicate another way). The FrameINO sampler passes two
+ * values: 0 on the clean first frame, t elsewhere (pipeline_wan_i2v_motion_FrameINO.py:832-843). */
+int fino_timestep_dedup(const float* t, int64_t n, float* uniq8, int32_t* row_index, int32_t* count, void* stream);
 
 /* out[l,r,c] = table[l*table_layer_stride + c] + proj[r,c] (float): the per-layer AdaLN rows
  * scale_shift_table + temb of transformer_wan.py:317-331, 520-527. */

@@ -118,6 +118,8 @@ def cog_block(sd, i: int, cfg: dict, x, enc, temb, rope, taps=None):
     a_x, a_e = cog_attention(sd, p + ".attn1", cfg, xn, en, rope, taps)  # :139
     x = x + gate * a_x  # :146
     enc = enc + e_gate * a_e  # :147
+    if taps is not None:
+        taps[f"{p}.after_attn"] = torch.cat([enc, x], dim=1)
     xn, en, gate_ff, e_gate_ff = layer_norm_zero(sd, p + ".norm2", x, enc, temb, eps)  # :150
     h = torch.cat([en, xn], dim=1)  # :155
     h = linear(F.gelu(linear(h, sd, p + ".ff.net.0.proj"), approximate="tanh"), sd, p + ".ff.net.2")  # :156

@@ -121,8 +121,86 @@ def cog_golden():
     print("wrote cog_golden.pt:", {k: tuple(v.shape) for k, v in out.items() if "sample" in k})
 
 
+def _cast_like_from_pretrained(model, dtype, keep_fp32):
+    """``from_pretrained(torch_dtype=dtype)`` + ``_keep_in_fp32_modules``: every floating parameter/buffer is cast to
+    ``dtype`` except those whose name contains one of the keep patterns (transformer_wan.py:393)."""
+    for name, p in model.named_parameters():
+        p.data = p.data.to(torch.float32 if any(k in name for k in keep_fp32) else dtype)
+    return model
+
+
+def bf16_golden():
+    """The reference classes run IN BF16 on CPU (weights cast as from_pretrained(torch_dtype=bf16) does, keeping
+    ``_keep_in_fp32_modules`` in fp32), so that every bf16 cast point of SURVEY.md §9 is live. The oracle in bf16 mode
+    must reproduce these (tests/test_oracle_golden.py); fixtures hold the bf16 samples + per-block taps."""
+    os.chdir(REF)
+    from architecture.cogvideox_transformer_3d import CogVideoXTransformer3DModel
+    from architecture.embeddings import get_3d_rotary_pos_embed
+    from architecture.transformer_wan import WanTransformer3DModel
+
+    out = {}
+    for name, cfg, shape in (("tiny", synth.WAN_TINY, (5, 16, 16)), ("small", synth.WAN_SMALL, (3, 16, 16))):
+        model = WanTransformer3DModel(**cfg).eval()
+        model.load_state_dict(synth.make_wan_state_dict(cfg, seed=0), strict=True)
+        keep = list(WanTransformer3DModel._keep_in_fp32_modules)
+        assert sorted(keep) == sorted(synth.WAN_KEEP_FP32), keep
+        _cast_like_from_pretrained(model, torch.bfloat16, keep)
+        taps = {}
+        hooks = []
+        for i, blk in enumerate(model.blocks):
+            hooks.append(blk.register_forward_hook(lambda m, a, o, i=i: taps.__setitem__(f"blocks.{i}.out", o.clone())))
+            # attention outputs / conditioning rows: every 8th token row (ROW_STEP) keeps the fixture small
+            hooks.append(blk.attn1.register_forward_hook(lambda m, a, o, i=i: taps.__setitem__(f"blocks.{i}.attn1", o[:, ::8].clone())))
+            hooks.append(blk.attn2.register_forward_hook(lambda m, a, o, i=i: taps.__setitem__(f"blocks.{i}.attn2", o[:, ::8].clone())))
+        hooks.append(model.condition_embedder.register_forward_hook(
+            lambda m, a, o: taps.update(temb=(o[0][:, ::8] if o[0].dim() == 3 else o[0]).clone(),
+                                        timestep_proj=(o[1][:, ::8] if o[1].dim() == 3 else o[1]).clone(),
+                                        text=o[2].clone())))
+        f, h, w = shape
+        for mode in ("per_token", "scalar"):
+            hidden, ts, text = synth.make_wan_inputs(cfg, f, h, w, n_id=1, text_len=16, text_true_len=11,
+                                                     per_token_timestep=(mode == "per_token"), dtype=torch.bfloat16)
+            with torch.no_grad():
+                y = model(hidden_states=hidden, timestep=ts, encoder_hidden_states=text, return_dict=False)[0]
+            assert y.dtype == torch.bfloat16
+            out[f"wan.{name}.{mode}.sample"] = y.clone()
+            for k, v in taps.items():
+                out[f"wan.{name}.{mode}.{k}"] = v.clone()
+        for hk in hooks:
+            hk.remove()
+
+    cfg = synth.COG_TINY
+    model = CogVideoXTransformer3DModel(**cfg).eval()
+    model.load_state_dict(synth.make_cog_state_dict(cfg, seed=0), strict=True)
+    model = model.to(torch.bfloat16)  # CogVideoX keeps nothing in fp32
+    lat_f = (cfg["sample_frames"] - 1) // cfg["temporal_compression_ratio"] + 1
+    h, w = cfg["sample_height"], cfg["sample_width"]
+    hidden, ts, text = synth.make_cog_inputs(cfg, lat_f, h, w, n_id=1, batch=2, dtype=torch.bfloat16)
+    gh, gw = h // cfg["patch_size"], w // cfg["patch_size"]
+    cos, sin = get_3d_rotary_pos_embed(cfg["attention_head_dim"], ((0, 0), (gh, gw)), (gh, gw), lat_f)
+    cos = torch.cat([cos, cos[: gh * gw]], dim=0)
+    sin = torch.cat([sin, sin[: gh * gw]], dim=0)
+    taps = {}
+    hooks = [blk.register_forward_hook(lambda m, a, o, i=i: taps.update({f"blocks.{i}.out": o[0].clone(),
+                                                                         f"blocks.{i}.enc": o[1].clone()}))
+             for i, blk in enumerate(model.transformer_blocks)]
+    with torch.no_grad():
+        y = model(hidden_states=hidden, encoder_hidden_states=text, timestep=ts, image_rotary_emb=(cos, sin),
+                  return_dict=False)[0]
+    assert y.dtype == torch.bfloat16
+    out["cog.tiny.sample"] = y.clone()
+    for k, v in taps.items():
+        out[f"cog.tiny.{k}"] = v.clone()
+    for hk in hooks:
+        hk.remove()
+    torch.save(out, os.path.join(HERE, "bf16_golden.pt"))
+    print("wrote bf16_golden.pt:", {k: (tuple(v.shape), str(v.dtype)) for k, v in out.items() if k.endswith("sample")})
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["wan", "cog"]
+    which = sys.argv[1:] or ["wan", "cog", "bf16"]
+    if "bf16" in which:
+        bf16_golden()
     if "wan" in which:
         wan_golden()
     if "cog" in which:

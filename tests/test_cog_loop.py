@@ -6,8 +6,8 @@ import pytest
 import torch
 
 from frameino_b200 import synth
-from frameino_b200.sampling import (cog_frameino_denoise, ddim_v_step, dynamic_cfg_scale,
-                                    scaled_linear_alphas_cumprod)
+from frameino_b200.sampling import (CogVideoXDPMSchedule, cog_frameino_denoise, ddim_v_step, dynamic_cfg_scale,
+                                    rescale_zero_terminal_snr, scaled_linear_alphas_cumprod)
 
 
 def test_dynamic_cfg_schedule_is_the_pipeline_formula():
@@ -26,6 +26,81 @@ def test_ddim_v_step_identities():
     assert torch.allclose(ddim_v_step(v, x, a, 1.0), x0, atol=1e-6)              # last step lands on the x0 estimate
     ac = scaled_linear_alphas_cumprod()
     assert ac.shape == (1000,) and bool((ac[:-1] > ac[1:]).all()) and 0 < float(ac[-1]) < float(ac[0]) < 1
+
+
+def test_dpm_schedule_tables():
+    sch = CogVideoXDPMSchedule()
+    ac = sch.alphas_cumprod
+    assert float(ac[-1]) == 0.0 and abs(float(ac[0]) - float(scaled_linear_alphas_cumprod()[0])) < 1e-6  # zero terminal SNR
+    assert bool((ac[:-1] > ac[1:]).all())
+    ts = sch.set_timesteps(50)
+    assert ts[0] == 999 and ts[-1] == 19 and len(ts) == 50 and bool((ts[:-1] - ts[1:] == 20).all())  # trailing spacing
+    assert list(CogVideoXDPMSchedule().set_timesteps(3)) == [999, 666, 332]
+    r = rescale_zero_terminal_snr(torch.tensor([0.9, 0.5, 0.1]))
+    assert abs(float(r[0]) - 0.9) < 1e-6 and float(r[-1]) == 0.0
+
+
+def test_dpm_step_is_dpm_solver_pp_2m_sde():
+    """``CogVideoXDPMSchedule.step`` against the closed form of DPM-Solver++(2M) SDE written with
+    alpha = sqrt(a_bar), sigma = sqrt(1 - a_bar), lambda = log(alpha / sigma), h = lambda_prev - lambda_t:
+        x_prev = (sigma_prev / sigma_t) e^{-h} x + alpha_prev (1 - e^{-2h}) D + sigma_prev sqrt(1 - e^{-2h}) z
+        D = x0_t (first / last step),   D = (1 + 1/(2r)) x0_t - (1/(2r)) x0_back,  r = h_last / h
+    in float64, over a whole 10-step trajectory of a linear toy model (v = 0.3 x + c)."""
+    g = torch.Generator().manual_seed(0)
+    sch = CogVideoXDPMSchedule()
+    ts = sch.set_timesteps(10)
+    x = torch.randn(2, 3, 5, generator=g)
+    xd = x.double()
+    c = torch.randn(2, 3, 5, generator=g)
+    old = None
+    old_d = None
+    ab = sch.alphas_cumprod.double()
+    for i, t in enumerate(ts):
+        z = torch.randn(2, 3, 5, generator=g)
+        v = 0.3 * x + c
+        x_new, old_new = sch.step(v, old, int(t), int(ts[i - 1]) if i > 0 else None, x, noise=z)
+        # closed form (float64)
+        vd = 0.3 * xd + c.double()
+        prev_t = int(t) - 1000 // 10
+        a_t, a_p = ab[int(t)], (ab[prev_t] if prev_t >= 0 else torch.tensor(1.0, dtype=torch.float64))
+        al_t, sg_t, al_p, sg_p = a_t.sqrt(), (1 - a_t).sqrt(), a_p.sqrt(), (1 - a_p).sqrt()
+        x0 = al_t * xd - sg_t * vd
+        h = torch.log(al_p / sg_p) - torch.log(al_t / sg_t)
+        d = x0
+        if old_d is not None and prev_t >= 0:
+            a_b = ab[int(ts[i - 1])]
+            h_last = torch.log(al_t / sg_t) - torch.log(a_b.sqrt() / (1 - a_b).sqrt())
+            r = h_last / h
+            d = (1 + 1 / (2 * r)) * x0 - (1 / (2 * r)) * old_d
+        e2h = torch.exp(-2 * h)
+        want = (sg_p / sg_t) * torch.exp(-h) * xd + al_p * (1 - e2h) * d + sg_p * torch.sqrt(1 - e2h) * z.double()
+        assert torch.isfinite(x_new).all()
+        assert torch.allclose(x_new.double(), want, rtol=2e-4, atol=2e-4), (i, float((x_new.double() - want).abs().max()))
+        assert torch.allclose(old_new.double(), x0, rtol=2e-4, atol=2e-4)
+        x, old, xd, old_d = x_new, old_new, want, x0
+    # the last step (prev_timestep < 0) adds no noise and lands on the denoised estimate
+    assert torch.allclose(x.double(), old_d, atol=1e-3)
+
+
+def test_cog_loop_with_the_dpm_scheduler_calls_step_like_the_pipeline():
+    """:918-926 — step(noise_pred, old_pred_original_sample, t, timesteps[i-1] if i > 0 else None, latents)."""
+    cfg, (lat, img, traj, idl, text) = _case(1)
+    calls = []
+
+    class Spy(CogVideoXDPMSchedule):
+        def step(self, model_output, old, timestep, timestep_back, sample, **kw):
+            calls.append((old is None, timestep, timestep_back))
+            return super().step(model_output, old, timestep, timestep_back, sample, **kw)
+
+    def tf(hidden_states, encoder_hidden_states, timestep, image_rotary_emb, return_dict=False):
+        return (hidden_states[:, :, :16] * 0.5,)
+
+    sch = Spy()
+    ts = sch.set_timesteps(4)
+    out = cog_frameino_denoise(tf, lat, img, traj, idl, text, None, ts, guidance_scale=6.0, model_dtype=torch.float32,
+                               scheduler=sch, generator=torch.Generator().manual_seed(1))
+    assert calls == [(True, 999, None), (False, 749, 999), (False, 499, 749), (False, 249, 499)]
+    assert out.shape == lat.shape and torch.isfinite(out).all()
 
 
 def _case(n_id):

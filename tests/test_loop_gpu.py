@@ -179,8 +179,10 @@ def test_fused_loop_equals_plain_loop(n_id, do_cfg):
     assert torch.equal(plain, fused)
 
 
-def test_fused_loop_final_latent_cosine_vs_oracle():
-    """Config 4 at test size through the fused loop: final latent cosine >= 0.999 vs the CPU oracle loop."""
+@pytest.mark.parametrize("num_steps", [10, 50])
+def test_fused_loop_final_latent_cosine_vs_oracle(num_steps):
+    """Config 4 at test size through the fused loop, up to the reference's full 50-step schedule
+    (pipeline_wan_i2v_motion_FrameINO.py:809-908): final latent cosine >= 0.999 vs the CPU oracle loop."""
     from frameino_b200.sampling import wan_frameino_denoise, wan_frameino_denoise_fused
     from oracle import wan_oracle
 
@@ -194,10 +196,11 @@ def test_fused_loop_final_latent_cosine_vs_oracle():
     def oracle_tf(hidden_states, timestep, encoder_hidden_states, return_dict=False):
         return (wan_oracle.wan_forward(sd, ocfg, hidden_states, timestep, encoder_hidden_states),)
 
-    ref = wan_frameino_denoise(oracle_tf, lat, cond, mask.expand(1, 16, -1, -1, -1), traj, idl, pos, neg, num_steps=10)
+    ref = wan_frameino_denoise(oracle_tf, lat, cond, mask.expand(1, 16, -1, -1, -1), traj, idl, pos, neg,
+                               num_steps=num_steps)
     model = _native(cfg, sd)
     out = wan_frameino_denoise_fused(model, lat.cuda(), cond.cuda(), mask.cuda(), traj.cuda(), idl.cuda(), pos.cuda(),
-                                     neg.cuda(), num_steps=10)
+                                     neg.cuda(), num_steps=num_steps)
     assert cosine(out, ref) >= COS_TOL
 
 

@@ -109,3 +109,54 @@ def test_cog_oracle_resized_canvas(cog_golden):
     cos, sin = cog_oracle.cog_rope_3d(64, (8, 6), 3, 1)
     out = cog_oracle.cog_forward(sd, cfg, hidden, text, ts, (cos, sin))
     assert torch.allclose(out, cog_golden["tiny.sample_resized"], atol=1e-4)
+
+
+# ---- bf16 goldens: the reference classes run in bf16 (from_pretrained(torch_dtype=bf16) + _keep_in_fp32_modules), so
+# ---- every cast point of SURVEY.md §9 is live; the oracle in bf16 mode must land on the same bf16 values ------------
+@pytest.fixture(scope="module")
+def bf16_golden(golden_dir):
+    return torch.load(os.path.join(golden_dir, "bf16_golden.pt"))
+
+
+def _bf16_close(a, b, what):
+    """Same cast points => the same bf16 values up to the summation order inside CPU kernels that differ between the
+    module path and the functional path (none observed: the bar is exact equality on >= 99.9 % of the elements and
+    at most one bf16 ulp elsewhere)."""
+    a, b = a.float(), b.float()
+    assert a.shape == b.shape, what
+    exact = float((a == b).float().mean())
+    ulp = float(((a - b).abs() / b.abs().clamp_min(1e-3)).max())
+    assert exact >= 0.999 and ulp <= 2 ** -6, f"{what}: exact fraction {exact}, worst relative gap {ulp}"
+
+
+@pytest.mark.parametrize("name,cfg,shape", WAN_CASES)
+@pytest.mark.parametrize("mode", ["per_token", "scalar"])
+def test_wan_oracle_bf16_cast_points_match_reference(bf16_golden, name, cfg, shape, mode):
+    sd = synth.make_wan_state_dict(cfg, seed=0, dtype=torch.bfloat16)
+    hidden, ts, text = synth.make_wan_inputs(cfg, *shape, n_id=1, text_len=16, text_true_len=11,
+                                             per_token_timestep=(mode == "per_token"), dtype=torch.bfloat16)
+    taps = {}
+    out = wan_oracle.wan_forward(sd, wan_oracle.WanConfig(**cfg), hidden, ts, text, taps=taps)
+    pre = f"wan.{name}.{mode}."
+    assert out.dtype == torch.bfloat16
+    _bf16_close(taps["text"], bf16_golden[pre + "text"], "text")
+    temb = taps["temb"][:, ::8] if taps["temb"].dim() == 3 else taps["temb"]
+    _bf16_close(temb, bf16_golden[pre + "temb"], "temb")
+    for i in range(cfg["num_layers"]):
+        _bf16_close(taps[f"blocks.{i}.out"], bf16_golden[pre + f"blocks.{i}.out"], f"blocks.{i}.out")
+    _bf16_close(out, bf16_golden[pre + "sample"], "sample")
+
+
+def test_cog_oracle_bf16_cast_points_match_reference(bf16_golden):
+    cfg = synth.COG_TINY
+    sd = synth.make_cog_state_dict(cfg, seed=0, dtype=torch.bfloat16)
+    lat_f = (cfg["sample_frames"] - 1) // cfg["temporal_compression_ratio"] + 1
+    h, w = cfg["sample_height"], cfg["sample_width"]
+    hidden, ts, text = synth.make_cog_inputs(cfg, lat_f, h, w, n_id=1, batch=2, dtype=torch.bfloat16)
+    cos, sin = cog_oracle.cog_rope_3d(cfg["attention_head_dim"], (h // 2, w // 2), lat_f, 1)
+    taps = {}
+    out = cog_oracle.cog_forward(sd, cfg, hidden, text, ts, (cos, sin), taps=taps)
+    for i in range(cfg["num_layers"]):
+        _bf16_close(taps[f"transformer_blocks.{i}.out"], bf16_golden[f"cog.tiny.blocks.{i}.out"], f"block {i} video")
+        _bf16_close(taps[f"transformer_blocks.{i}.enc"], bf16_golden[f"cog.tiny.blocks.{i}.enc"], f"block {i} text")
+    _bf16_close(out, bf16_golden["cog.tiny.sample"], "sample")
