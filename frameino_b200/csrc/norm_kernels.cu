@@ -821,6 +821,94 @@ __global__ void __launch_bounds__(ROW_WARPS * 32) qk_norm_rope_kernel(const QkPa
   }
 }
 
+// Per-head LayerNorm(64) + CogVideoX RoPE (attention_processor.py:2848-2860, embeddings.py:1247-1256), dim = CPL * 256.
+// Warp per row; lane l owns the 16-byte chunk c = i*32 + l of every 256-column group i, so a 64-wide head is the 8
+// consecutive lanes [8g, 8g+8) of ONE group and a lane's 8 columns sit at the same position (l % 8) of 12 different
+// heads: the norm gain/bias and the token's cos/sin values are loaded once per row, and the per-head statistics are
+// 3-step butterflies over 8 lanes that run side by side for all CPL heads of the lane (two rounds of 3 shuffle steps,
+// each step CPL independent shuffles — the generic kernel above walks the heads one after the other, 72 dependent
+// shuffles per row). The row stays packed (bf16) in registers, 16 warps per SM. q rows on even CTAs, k rows on odd
+// ones, so the two rows of a token run side by side and share the cos/sin lines.
+template <int CPL, int G>  // G = 256-column groups in flight per pass (CPL % G == 0)
+__global__ void __launch_bounds__(ROW_WARPS * 32, (G <= 2 ? 4 : G <= 6 ? 3 : 2)) qk_ln64_rope_kernel(const QkParams p) {
+  const int lane = threadIdx.x & 31;
+  const int which = blockIdx.x & 1;
+  const QkTensor& t = p.t[which];
+  const int64_t row = (int64_t)(blockIdx.x >> 1) * ROW_WARPS + (threadIdx.x >> 5);
+  if (row >= t.rows) return;
+  uint4* xr = reinterpret_cast<uint4*>(t.ptr + row * t.row_stride) + lane;
+  const int hc = lane & 7;  // chunk inside the head
+  const int64_t s_in_seq = row % p.seq_len;
+  const bool do_rope = t.rope && p.rope_mode == ROPE_COGVIDEOX && s_in_seq >= p.rope_skip;
+  uint4 wq = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);  // bf16 ones
+  uint4 bq = make_uint4(0u, 0u, 0u, 0u);
+  if (t.weight != nullptr) wq = __ldg(reinterpret_cast<const uint4*>(t.weight) + hc);
+  if (t.bias != nullptr) bq = __ldg(reinterpret_cast<const uint4*>(t.bias) + hc);
+  float cs[8], sn[8];
+  if (do_rope) {
+    ld8f(p.cos + (s_in_seq - p.rope_skip) * 64 + hc * 8, cs);
+    ld8f(p.sin + (s_in_seq - p.rope_skip) * 64 + hc * 8, sn);
+  }
+#pragma unroll 1
+  for (int g0 = 0; g0 < CPL; g0 += G) {
+    uint4 raw[G];
+#pragma unroll
+    for (int i = 0; i < G; ++i) raw[i] = xr[(g0 + i) * 32];
+    float mean[G], rstd[G];
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      float v[8];
+      unpack8(raw[i], v);
+      mean[i] = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1)
+#pragma unroll
+      for (int i = 0; i < G; ++i) mean[i] += __shfl_xor_sync(0xffffffffu, mean[i], o);
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      mean[i] *= (1.0f / 64.0f);
+      float v[8];
+      unpack8(raw[i], v);
+      float sq = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = v[e] - mean[i];
+        sq = fmaf(d, d, sq);
+      }
+      rstd[i] = sq;
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1)
+#pragma unroll
+      for (int i = 0; i < G; ++i) rstd[i] += __shfl_xor_sync(0xffffffffu, rstd[i], o);
+    float w[8], b[8];
+    unpack8(wq, w);
+    unpack8(bq, b);
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const float r = rsqrtf(rstd[i] * (1.0f / 64.0f) + p.eps);
+      float v[8];
+      unpack8(raw[i], v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = rbf((v[e] - mean[i]) * r * w[e] + b[e]);
+      if (do_rope) {
+        // x*cos + rotate(x)*sin with rotate = (-x_odd, x_even), separate roundings as the reference's elementwise ops
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          const float xe = v[e], xo = v[e + 1];
+          o[e] = __fadd_rn(__fmul_rn(xe, cs[e]), __fmul_rn(-xo, sn[e]));
+          o[e + 1] = __fadd_rn(__fmul_rn(xo, cs[e + 1]), __fmul_rn(xe, sn[e + 1]));
+        }
+        xr[(g0 + i) * 32] = pack8(o);
+      } else {
+        xr[(g0 + i) * 32] = pack8(v);
+      }
+    }
+  }
+}
+
 // Warp-per-row RMSNorm-across-heads (+ Wan RoPE) in the 4-column-group layout with packed f32x2 arithmetic (see
 // ln_modulate_kernel2): dim == GPL * 128. With head_dim == 128 a lane's 4 columns sit at the same position of every
 // head, so ONE float4 of cos and one of sin per token serve all heads of the row. Even CTAs take tensor 0 (q), odd
@@ -1048,6 +1136,24 @@ int qk_norm_rope(void* x0, int64_t rows0, int64_t stride0, const void* w0, const
   p.rope_skip = rope_skip;
   p.blocks0 = (rows0 + ROW_WARPS - 1) / ROW_WARPS;
   const int64_t blocks1 = x1 ? (rows1 + ROW_WARPS - 1) / ROW_WARPS : 0;
+  // CogVideoX: per-head LayerNorm over 64-wide heads (+ RoPE on the video tokens), rows of CPL * 256 columns
+  if (g_qk_block_kernel != 0 && norm_mode == QK_LAYERNORM_PER_HEAD && head_dim == 64 && (dim == 3072 || dim == 256) &&
+      (p.rope_mode == ROPE_NONE || p.rope_mode == ROPE_COGVIDEOX)) {
+    const int64_t nb = std::max(p.blocks0, blocks1);
+    dim3 g2((unsigned)(2 * nb));
+    if (x1 == nullptr) p.t[1].rows = 0;
+    if (dim == 3072) {
+      if (g_qk_block_kernel == 3) qk_ln64_rope_kernel<12, 12><<<g2, ROW_WARPS * 32, 0, stream>>>(p);
+      else if (g_qk_block_kernel == 4) qk_ln64_rope_kernel<12, 6><<<g2, ROW_WARPS * 32, 0, stream>>>(p);
+      else if (g_qk_block_kernel == 5) qk_ln64_rope_kernel<12, 3><<<g2, ROW_WARPS * 32, 0, stream>>>(p);
+      else if (g_qk_block_kernel == 6) qk_ln64_rope_kernel<12, 2><<<g2, ROW_WARPS * 32, 0, stream>>>(p);
+      else qk_ln64_rope_kernel<12, 4><<<g2, ROW_WARPS * 32, 0, stream>>>(p);  // measured best: 90.7 us, 5.3 TB/s
+    } else {
+      qk_ln64_rope_kernel<1, 1><<<g2, ROW_WARPS * 32, 0, stream>>>(p);
+    }
+    FINO_CHECK_CUDA(cudaGetLastError());
+    return FINO_OK;
+  }
   // packed warp-per-row kernel: RMS across heads, dim 3072 / 5120, head_dim 128 when rotating, no bias, row strides
   // that keep the 8-byte pieces aligned (always true: strides are multiples of 8 elements)
   if (g_qk_block_kernel == 2 && norm_mode == QK_RMS_ACROSS_HEADS && (dim == 3072 || dim == 5120) && b0 == nullptr &&

@@ -87,7 +87,9 @@ int fino_attention_plan_hd(int64_t nq, int64_t nk, int heads, int batch, int hea
                            int* splits, int* tile_rows);
 
 /* Tuning / test hook: LayerNorm kernel 0 = warp per row, 1 = block per row, 2 = batched block per row (default for
- * 1024 <= dim <= 3072); q/k-norm kernel 0 = warp per row, 1 = block per token (default). */
+ * 1024 <= dim <= 3072), 3 = packed warp per row (default); q/k-norm kernel 0 = generic warp per row, 1 = block per
+ * token, 2 = packed warp per row (default; per-head LayerNorm(64): the 6-groups-in-flight kernel), 3 / 4 = per-head
+ * LayerNorm(64) kernel with 12 / 4 groups in flight. */
 int fino_rows_set_variant(int ln_block, int qk_block);
 /* Tuning / test hook: 1 = wide rows (1024 <= dim <= 4096) go through the experimental TMA-staged persistent row
  * kernels (bulk async copies through a shared-memory ring); 0 (default) = the register-resident row kernels. */

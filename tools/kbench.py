@@ -150,7 +150,7 @@ if "rows64" in which:  # CogVideoX: per-head LayerNorm(64) + RoPE on the joint [
     w64, b64 = torch.ones(hd2, device="cuda").bfloat16(), torch.zeros(hd2, device="cuda").bfloat16()
     cos = torch.rand(n2 - 226, hd2, device="cuda")
     sin = torch.rand(n2 - 226, hd2, device="cuda")
-    for variant in (0, 2):
+    for variant in (0, 2, 3, 4, 5, 6):  # 0 generic warp-per-row; ln64 kernel with G groups in flight: 2 (default) G=4; 3: 12; 4: 6; 5: 3; 6: 2
         ops.rows_set_variant(3, variant)
         timeit(lambda: ops.qk_norm_rope(qkv[..., :d], w64, qkv[..., d:2 * d], w64, h2, b0=b64, b1=b64,
                                         norm_mode=ops.QK_LAYERNORM_PER_HEAD, rope_mode=ops.ROPE_COGVIDEOX, cos=cos,
