@@ -306,6 +306,31 @@ def native_block_parity(model, d_in, lat_f, h, w, dev):
     return parity, cpu_leg
 
 
+def sharded_vs_unsharded(model, fn, y_sharded, rank):
+    """Rank 0 switches sequence parallelism off, re-runs ``fn`` (no collectives on that path) and returns
+    {"rel_err", "cosine"} of the sharded output against it; other ranks return None (the caller barriers)."""
+    import torch
+
+    from frameino_b200.ulysses import _self_attention_modules
+
+    if rank != 0:
+        return None
+    sp_saved = model.sequence_parallel
+    model.sequence_parallel = None
+    for a in _self_attention_modules(model):
+        a.__dict__.pop("_fino_sp", None)
+    try:
+        y_single = fn()
+        torch.cuda.synchronize()
+    finally:
+        model.sequence_parallel = sp_saved
+        for a in _self_attention_modules(model):
+            a.__dict__["_fino_sp"] = sp_saved
+    a32, b32 = y_sharded.float().flatten(), y_single.float().flatten()
+    return {"rel_err": float((a32 - b32).abs().max() / b32.abs().max()),
+            "cosine": float(torch.nn.functional.cosine_similarity(a32, b32, dim=0))}
+
+
 def _time_steps(fn, steps, warmup, barrier):
     import torch
 
@@ -338,13 +363,15 @@ def run_secondary(args, world, rank, dev, wan_model, barrier):
         hidden, ts, text = synth.make_wan_inputs(synth.WAN22_5B, lat_f, h, w, n_id=1, text_len=512, text_true_len=120,
                                                  dtype=torch.bfloat16)
         d5 = [t.to(dev) for t in (hidden, ts, text)]
-        ms, y = _time_steps(lambda: wan_model(hidden_states=d5[0], timestep=d5[1], encoder_hidden_states=d5[2],
-                                              return_dict=False)[0], steps, warmup, barrier)
+        fn5 = lambda: wan_model(hidden_states=d5[0], timestep=d5[1], encoder_hidden_states=d5[2], return_dict=False)[0]  # noqa: E731
+        ms, y = _time_steps(fn5, steps, warmup, barrier)
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cmp5 = sharded_vs_unsharded(wan_model, fn5, y, rank)
+        barrier()
         out["config5_wan_40k_tokens"] = {
             "metric": METRIC, "value": float(t.item()), "unit": "ms", "n_gpus": world, "steps": steps, "warmup": warmup,
-            "finite": bool(torch.isfinite(y.float()).all()),
+            "finite": bool(torch.isfinite(y.float()).all()), "parity_sharded_vs_unsharded": cmp5,
             "config": {"workload": f"Wan2.2-TI2V-5B FrameINO one denoise-step forward, 832x1536x121 + 1 ID frame, {tokens} "
                                    f"tokens, B=1, ulysses x{world} ({args.sp_mode})"}}
         del d5, y
@@ -499,25 +526,11 @@ def run_native(args, lat_f, h, w, tokens):
     parity = {}
     if world > 1:
         # rank 0 re-runs the SAME forward un-sharded (no collectives on that path) and compares
-        from frameino_b200.ulysses import _self_attention_modules
-
-        if rank == 0:
-            sp_saved = model.sequence_parallel
-            model.sequence_parallel = None
-            for a in _self_attention_modules(model):
-                a.__dict__.pop("_fino_sp", None)
-            y_single = step_device()
-            torch.cuda.synchronize()
-            model.sequence_parallel = sp_saved
-            for a in _self_attention_modules(model):
-                a.__dict__["_fino_sp"] = sp_saved
-            a32, b32 = y_timed.float().flatten(), y_single.float().flatten()
-            parity["sharded_vs_unsharded"] = {
-                "rel_err": float((a32 - b32).abs().max() / b32.abs().max()),
-                "cosine": float(torch.nn.functional.cosine_similarity(a32, b32, dim=0)),
-                "what": f"full 30-layer forward, {world}-way Ulysses ({args.sp_mode}) output vs the same forward on rank 0 "
-                        "alone; rel_err = max|a-b| / max|b| over the whole [1,48,32,44,80] sample"}
-            del y_single
+        cmp = sharded_vs_unsharded(model, step_device, y_timed, rank)
+        if cmp is not None:
+            cmp["what"] = (f"full 30-layer forward, {world}-way Ulysses ({args.sp_mode}) output vs the same forward on rank 0 "
+                           "alone; rel_err = max|a-b| / max|b| over the whole [1,48,32,44,80] sample")
+            parity["sharded_vs_unsharded"] = cmp
         barrier()
     elif not args.no_cpu_baseline:
         parity, cpu_leg = native_block_parity(model, d_in, lat_f, h, w, dev)

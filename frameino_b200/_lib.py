@@ -48,6 +48,15 @@ SIGNATURES = {
     "fino_build_mod_table": (_I, [_P, _P, _P, _I, _I, _I, _L, _P]),
     "fino_wan_pack_model_input": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _L, _P]),
     "fino_wan_cfg_euler_step": (_I, [_P, _P, _L, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _F, _F, _P]),
+    "fino_conv3d_cl_bf16": (_I, [_P, _I, _I, _I, _I, _L, _L, _L, _P, _L, _P, _P, _I, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I,
+                                 _I, _I, _I, _P, _I, _P]),
+    "fino_rms_act_cl": (_I, [_P, _P, _L, _I, _L, _L, _P, _P, _I, _P]),
+    "fino_upsample2x_cl": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "fino_dupup_add_cl": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "fino_avgdown_add_cl": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "fino_softmax_rows": (_I, [_P, _P, _L, _I, _L, _L, _F, _P]),
+    "fino_vae_to_cl": (_I, [_P, _I, _P, _I, _I, _I, _I, _L, _L, _L, _L, _I, _I, _P]),
+    "fino_vae_from_cl": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _L, _P]),
     "fino_swap01": (_I, [_P, _P, _L, _L, _L, _P]),
     "fino_peer_alloc": (_I, [_L, _P]),
     "fino_peer_free": (_I, [_P]),

@@ -55,6 +55,22 @@ int wan_pack_model_input(const float* latents, const float* condition, const flo
 int wan_cfg_euler_step(const void* y_cond, const void* y_uncond, int64_t ld, float* latents, int B, int C, int F,
                        int NID, int H, int W, int pt, int ph, int pw, float guidance, float dsigma,
                        cudaStream_t stream);
+int conv3d_cl(const void* x, int t_in, int h_in, int w_in, int c_in, int64_t in_st, int64_t in_sh, int64_t in_sw,
+              const void* w, int64_t ldw, const void* bias, void* y, int t_out, int h_out, int w_out, int c_out,
+              int64_t out_st, int64_t out_sh, int64_t out_sw, int kt, int kh, int kw, int pad_h, int pad_w,
+              int stride_hw, int stride_t, const void* residual, int epilogue, cudaStream_t stream);
+int rms_act_cl(const void* x, void* out, int64_t rows, int C, int64_t x_stride, int64_t out_stride, const float* gamma,
+               const float* bias, int silu, cudaStream_t stream);
+int upsample2x_cl(const void* in, void* out, int T, int H, int W, int C, cudaStream_t stream);
+int dupup_add_cl(void* y, const void* src, int To, int Ho, int Wo, int Co, int Ti, int Hi, int Wi, int Ci, int ft, int fs,
+                 int t_drop, cudaStream_t stream);
+int avgdown_add_cl(void* y, const void* src, int To, int Ho, int Wo, int Co, int Ti, int Hi, int Wi, int Ci, int ft, int fs,
+                   cudaStream_t stream);
+int softmax_rows(const float* s, void* p, int64_t rows, int cols, int64_t ls, int64_t lp, float scale, cudaStream_t stream);
+int vae_to_cl(const void* in, int in_fp32, void* out, int C, int T, int H, int W, int64_t sc, int64_t st, int64_t sh,
+              int64_t sw, int ps, int cpad, cudaStream_t stream);
+int vae_from_cl(const void* in, void* out, int out_fp32, int C, int T, int Hi, int Wi, int cstride, int ps, int clamp,
+                int64_t out_sc, cudaStream_t stream);
 void gemm_set_mode(int mode);
 void gemm_set_split(int mode);
 void gemm_plan(int tiles, int num_kb, int clusters, int mode, int* num_full, int* splits);
@@ -319,6 +335,43 @@ int fino_wan_cfg_euler_step(const void* y_cond, const void* y_uncond, int64_t ld
                             void* stream) {
   FINO_ENTRY(fino::wan_cfg_euler_step(y_cond, y_uncond, ld, latents, b, c, f, n_id, h, w, pt, ph, pw, guidance, dsigma,
                                       (cudaStream_t)stream));
+}
+
+// ---- Wan VAE ----
+int fino_conv3d_cl_bf16(const void* x, int t_in, int h_in, int w_in, int c_in, int64_t in_st, int64_t in_sh,
+                        int64_t in_sw, const void* w, int64_t ldw, const void* bias, void* y, int t_out, int h_out,
+                        int w_out, int c_out, int64_t out_st, int64_t out_sh, int64_t out_sw, int kt, int kh, int kw,
+                        int pad_h, int pad_w, int stride_hw, int stride_t, const void* residual, int epilogue,
+                        void* stream) {
+  FINO_ENTRY(fino::conv3d_cl(x, t_in, h_in, w_in, c_in, in_st, in_sh, in_sw, w, ldw, bias, y, t_out, h_out, w_out, c_out,
+                             out_st, out_sh, out_sw, kt, kh, kw, pad_h, pad_w, stride_hw, stride_t, residual, epilogue,
+                             (cudaStream_t)stream));
+}
+int fino_rms_act_cl(const void* x, void* out, int64_t rows, int c, int64_t x_stride, int64_t out_stride,
+                    const float* gamma, const float* bias, int silu, void* stream) {
+  FINO_ENTRY(fino::rms_act_cl(x, out, rows, c, x_stride, out_stride, gamma, bias, silu, (cudaStream_t)stream));
+}
+int fino_upsample2x_cl(const void* in, void* out, int t, int h, int w, int c, void* stream) {
+  FINO_ENTRY(fino::upsample2x_cl(in, out, t, h, w, c, (cudaStream_t)stream));
+}
+int fino_dupup_add_cl(void* y, const void* src, int to, int ho, int wo, int co, int ti, int hi, int wi, int ci, int ft,
+                      int fs, int t_drop, void* stream) {
+  FINO_ENTRY(fino::dupup_add_cl(y, src, to, ho, wo, co, ti, hi, wi, ci, ft, fs, t_drop, (cudaStream_t)stream));
+}
+int fino_avgdown_add_cl(void* y, const void* src, int to, int ho, int wo, int co, int ti, int hi, int wi, int ci, int ft,
+                        int fs, void* stream) {
+  FINO_ENTRY(fino::avgdown_add_cl(y, src, to, ho, wo, co, ti, hi, wi, ci, ft, fs, (cudaStream_t)stream));
+}
+int fino_softmax_rows(const float* s, void* p, int64_t rows, int cols, int64_t ls, int64_t lp, float scale, void* stream) {
+  FINO_ENTRY(fino::softmax_rows(s, p, rows, cols, ls, lp, scale, (cudaStream_t)stream));
+}
+int fino_vae_to_cl(const void* in, int in_fp32, void* out, int c, int t, int h, int w, int64_t sc, int64_t st, int64_t sh,
+                   int64_t sw, int ps, int cpad, void* stream) {
+  FINO_ENTRY(fino::vae_to_cl(in, in_fp32, out, c, t, h, w, sc, st, sh, sw, ps, cpad, (cudaStream_t)stream));
+}
+int fino_vae_from_cl(const void* in, void* out, int out_fp32, int c, int t, int hi, int wi, int cstride, int ps, int clamp,
+                     int64_t out_sc, void* stream) {
+  FINO_ENTRY(fino::vae_from_cl(in, out, out_fp32, c, t, hi, wi, cstride, ps, clamp, out_sc, (cudaStream_t)stream));
 }
 
 // allocation / IPC: no kernel launch, not counted

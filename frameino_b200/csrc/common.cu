@@ -34,7 +34,7 @@ static PFN_cuTensorMapEncodeTiled_t get_encode_fn() {
 }
 
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                     const uint32_t* box) {
+                     const uint32_t* box, const uint32_t* elem_strides) {
   PFN_cuTensorMapEncodeTiled_t fn = get_encode_fn();
   if (!fn) return FINO_ERR_CUDA;
   cuuint64_t gdim[5];
@@ -44,7 +44,7 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bdim[i] = box[i];
-    estr[i] = 1;
+    estr[i] = elem_strides ? elem_strides[i] : 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {

@@ -38,8 +38,10 @@ const char* get_last_error();
 
 // Encodes a bf16 tiled tensor map with 128-byte swizzle. dims/strides innermost first; strides in bytes for
 // dims 1..rank-1. Returns 0 on success.
+// elem_strides (optional): traversal stride per dimension (1 = every element); a box of `box[i]` elements then yields
+// ceil(box[i] / elem_strides[i]) elements in shared memory. Out-of-bounds elements (also negative coordinates) read as 0.
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                     const uint32_t* box);
+                     const uint32_t* box, const uint32_t* elem_strides = nullptr);
 
 int num_sms();
 

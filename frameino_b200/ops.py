@@ -389,6 +389,117 @@ def wan_cfg_euler_step(latents: torch.Tensor, y_cond: torch.Tensor, y_uncond: Op
     return latents
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# Wan VAE (include/frameino_b200.h "Wan VAE" section): channels-last bf16 activations [T, H, W, C]
+# ---------------------------------------------------------------------------------------------------------------
+def conv3d_cl(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], kernel: Tuple[int, int, int],
+              out: Optional[torch.Tensor] = None, pad_hw: Tuple[int, int] = (0, 0), stride_hw: int = 1, stride_t: int = 1,
+              residual: Optional[torch.Tensor] = None, out_hw: Optional[Tuple[int, int]] = None,
+              c_out: Optional[int] = None) -> torch.Tensor:
+    """Implicit-GEMM convolution, valid along time (prepend the causal history). x: bf16 [T_in, H, W, C_in] (pixel rows
+    contiguous, any frame / row / pixel strides); weight: packed bf16 [C_out, kt*kh*kw*ceil(C_in/64)*64]; out: bf16
+    [T_out, H_out, W_out, C_out] view (frame / row strides multiples of the pixel stride); residual: same geometry."""
+    assert x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and x.dim() == 4 and x.stride(3) == 1
+    lib, stream = _prep(x, weight, bias, out, residual)
+    kt, kh, kw = kernel
+    t_in, h_in, w_in, c_in = x.shape
+    t_out = (t_in - kt) // stride_t + 1
+    if out_hw is None:
+        h_out = (h_in + 2 * pad_hw[0] - kh) // stride_hw + 1
+        w_out = (w_in + 2 * pad_hw[1] - kw) // stride_hw + 1
+    else:
+        h_out, w_out = out_hw
+    n = weight.shape[0] if c_out is None else c_out
+    if out is None:
+        out = torch.empty(t_out, h_out, w_out, n, dtype=torch.bfloat16, device=x.device)
+    assert out.dtype == torch.bfloat16 and tuple(out.shape) == (t_out, h_out, w_out, n) and out.stride(3) == 1
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16 and residual.shape == out.shape and residual.stride() == out.stride()
+    if bias is not None:
+        assert bias.dtype == torch.bfloat16 and bias.is_contiguous() and bias.numel() >= n
+    status = lib.fino_conv3d_cl_bf16(
+        x.data_ptr(), t_in, h_in, w_in, c_in, x.stride(0), x.stride(1), x.stride(2), weight.data_ptr(), weight.stride(0),
+        _ptr(bias), out.data_ptr(), t_out, h_out, w_out, n, out.stride(0), out.stride(1), out.stride(2), kt, kh, kw,
+        pad_hw[0], pad_hw[1], stride_hw, stride_t, _ptr(residual), EPI_GATE_RESIDUAL if residual is not None else EPI_NONE,
+        stream)
+    _lib.check(status, "fino_conv3d_cl_bf16")
+    return out
+
+
+def rms_act_cl(x: torch.Tensor, gamma: torch.Tensor, bias: Optional[torch.Tensor] = None, silu: bool = True,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """WanRMS_norm over the channels of every pixel (+ SiLU). x/out: bf16 [..., C] with contiguous pixels."""
+    assert x.dtype == torch.bfloat16 and gamma.dtype == torch.float32 and gamma.is_contiguous()
+    lib, stream = _prep(x, gamma, bias, out)
+    rows, c, xs = _rows2d(x)
+    if out is None:
+        out = torch.empty_like(x)
+    orows, oc, os_ = _rows2d(out)
+    assert (orows, oc) == (rows, c) and gamma.numel() == c
+    _lib.check(lib.fino_rms_act_cl(x.data_ptr(), out.data_ptr(), rows, c, xs, os_, gamma.data_ptr(), _ptr(bias),
+                                   1 if silu else 0, stream), "fino_rms_act_cl")
+    return out
+
+
+def upsample2x_cl(x: torch.Tensor) -> torch.Tensor:
+    assert x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous()
+    lib, stream = _prep(x)
+    t, h, w, c = x.shape
+    out = torch.empty(t, 2 * h, 2 * w, c, dtype=x.dtype, device=x.device)
+    _lib.check(lib.fino_upsample2x_cl(x.data_ptr(), out.data_ptr(), t, h, w, c, stream), "fino_upsample2x_cl")
+    return out
+
+
+def dupup_add_cl(y: torch.Tensor, src: torch.Tensor, ft: int, fs: int, first_chunk: bool) -> torch.Tensor:
+    assert y.dtype == src.dtype == torch.bfloat16 and y.is_contiguous() and src.is_contiguous()
+    lib, stream = _prep(y, src)
+    _lib.check(lib.fino_dupup_add_cl(y.data_ptr(), src.data_ptr(), *y.shape, *src.shape, ft, fs,
+                                     ft - 1 if first_chunk else 0, stream), "fino_dupup_add_cl")
+    return y
+
+
+def avgdown_add_cl(y: torch.Tensor, src: torch.Tensor, ft: int, fs: int) -> torch.Tensor:
+    assert y.dtype == src.dtype == torch.bfloat16 and y.is_contiguous() and src.is_contiguous()
+    lib, stream = _prep(y, src)
+    _lib.check(lib.fino_avgdown_add_cl(y.data_ptr(), src.data_ptr(), *y.shape, *src.shape, ft, fs, stream),
+               "fino_avgdown_add_cl")
+    return y
+
+
+def softmax_rows(s: torch.Tensor, scale: float, out: torch.Tensor) -> torch.Tensor:
+    """out[r, :cols] = softmax(s[r] * scale) as bf16; out's extra columns (row stride padding) are zeroed."""
+    assert s.dtype == torch.float32 and s.dim() == 2 and s.stride(1) == 1 and out.dtype == torch.bfloat16
+    assert out.dim() == 2 and out.stride(1) == 1 and out.shape[0] == s.shape[0] and out.shape[1] >= s.shape[1]
+    lib, stream = _prep(s, out)
+    _lib.check(lib.fino_softmax_rows(s.data_ptr(), out.data_ptr(), s.shape[0], s.shape[1], s.stride(0), out.stride(0),
+                                     float(scale), stream), "fino_softmax_rows")
+    return out
+
+
+def vae_to_cl(x: torch.Tensor, patch: int, cpad: int) -> torch.Tensor:
+    """[C, T, H, W] fp32 | bf16 (any strides) -> channels-last bf16 [T, H/patch, W/patch, cpad] (patchified, zero padded)."""
+    assert x.dim() == 4 and x.dtype in (torch.float32, torch.bfloat16)
+    lib, stream = _prep(x)
+    c, t, h, w = x.shape
+    out = torch.empty(t, h // patch, w // patch, cpad, dtype=torch.bfloat16, device=x.device)
+    _lib.check(lib.fino_vae_to_cl(x.data_ptr(), 1 if x.dtype == torch.float32 else 0, out.data_ptr(), c, t, h, w,
+                                  *x.stride(), patch, cpad, stream), "fino_vae_to_cl")
+    return out
+
+
+def vae_from_cl(x: torch.Tensor, out: torch.Tensor, channels: int, patch: int, clamp: bool) -> torch.Tensor:
+    """channels-last bf16 [T, Hi, Wi, cstride] -> out[channels, T, Hi*patch, Wi*patch] (a [C, T, H, W] view whose frames,
+    rows and pixels are contiguous; fp32 | bf16), un-patchified and optionally clamped to [-1, 1]."""
+    assert x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous() and out.dtype in (torch.float32, torch.bfloat16)
+    t, hi, wi, cs = x.shape
+    assert tuple(out.shape) == (channels, t, hi * patch, wi * patch)
+    assert out.stride(3) == 1 and out.stride(2) == wi * patch and out.stride(1) == hi * patch * wi * patch
+    lib, stream = _prep(x, out)
+    _lib.check(lib.fino_vae_from_cl(x.data_ptr(), out.data_ptr(), 1 if out.dtype == torch.float32 else 0, channels, t, hi,
+                                    wi, cs, patch, 1 if clamp else 0, out.stride(0), stream), "fino_vae_from_cl")
+    return out
+
+
 def swap01(x: torch.Tensor, a: int, b: int, inner: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Contiguous [a, b, inner] -> [b, a, inner] (bf16, inner % 8 == 0)."""
     assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() == a * b * inner

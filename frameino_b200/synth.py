@@ -75,7 +75,7 @@ def _fill(name: str, shape: Tuple[int, ...], gen: torch.Generator, device) -> to
         return torch.randn(shape, generator=gen, device=device) * 0.02
     if name.endswith(".bias"):
         return torch.randn(shape, generator=gen, device=device) * 0.02
-    if len(shape) == 1:  # norm gains
+    if len(shape) == 1 or name.endswith(".gamma"):  # norm gains
         return 1.0 + 0.1 * torch.randn(shape, generator=gen, device=device)
     fan_in = 1
     for s in shape[1:]:
@@ -286,3 +286,102 @@ def cog_rope_tables(head_dim: int, grid_h: int, grid_w: int, frames: int, n_id: 
             tab = torch.cat([tab] + [tab[: grid_h * grid_w]] * n_id, dim=0)
         out.append(tab.contiguous().to(device))
     return out[0], out[1]
+
+
+# ---- Wan VAE -------------------------------------------------------------------------------
+# Wan2.2-TI2V-5B VAE (upstream HF config, recalled — SURVEY.md §10) and a small config of the same shape for tests
+WAN22_VAE = dict(base_dim=160, decoder_base_dim=256, z_dim=48, dim_mult=[1, 2, 4, 4], num_res_blocks=2,
+                 temperal_downsample=[False, True, True], is_residual=True, in_channels=12, out_channels=12, patch_size=2,
+                 scale_factor_temporal=4, scale_factor_spatial=16)
+VAE_TINY = dict(base_dim=32, decoder_base_dim=64, z_dim=16, dim_mult=[1, 2, 4, 4], num_res_blocks=2,
+                temperal_downsample=[False, True, True], is_residual=True, in_channels=12, out_channels=12, patch_size=2,
+                scale_factor_temporal=4, scale_factor_spatial=16)
+
+
+def _vae_dims(cfg: dict, decoder: bool):
+    mult = list(cfg["dim_mult"])
+    if decoder:
+        dim = cfg.get("decoder_base_dim") or cfg["base_dim"]
+        return [dim * u for u in [mult[-1]] + mult[::-1]]  # autoencoder_kl_wan.py:821
+    return [cfg["base_dim"] * u for u in [1] + mult]  # :545
+
+
+def vae_param_shapes(cfg: dict) -> Dict[str, tuple]:
+    """State-dict layout of the reference AutoencoderKLWan (is_residual) — names from :505-584, :783-872, :1022-1050."""
+    shapes: Dict[str, tuple] = {}
+    z = cfg["z_dim"]
+
+    def conv3(name, cin, cout, k):
+        shapes[name + ".weight"] = (cout, cin, *k)
+        shapes[name + ".bias"] = (cout,)
+
+    def res(name, cin, cout):
+        shapes[name + ".norm1.gamma"] = (cin, 1, 1, 1)
+        conv3(name + ".conv1", cin, cout, (3, 3, 3))
+        shapes[name + ".norm2.gamma"] = (cout, 1, 1, 1)
+        conv3(name + ".conv2", cout, cout, (3, 3, 3))
+        if cin != cout:
+            conv3(name + ".conv_shortcut", cin, cout, (1, 1, 1))
+
+    def mid(name, c):
+        res(name + ".resnets.0", c, c)
+        shapes[name + ".attentions.0.norm.gamma"] = (c, 1, 1)
+        shapes[name + ".attentions.0.to_qkv.weight"] = (3 * c, c, 1, 1)
+        shapes[name + ".attentions.0.to_qkv.bias"] = (3 * c,)
+        shapes[name + ".attentions.0.proj.weight"] = (c, c, 1, 1)
+        shapes[name + ".attentions.0.proj.bias"] = (c,)
+        res(name + ".resnets.1", c, c)
+
+    n = len(cfg["dim_mult"])
+    # encoder
+    dims = _vae_dims(cfg, False)
+    conv3("encoder.conv_in", cfg["in_channels"], dims[0], (3, 3, 3))
+    for i, (cin, cout) in enumerate(zip(dims[:-1], dims[1:])):
+        p = f"encoder.down_blocks.{i}"
+        c = cin
+        for j in range(cfg["num_res_blocks"]):
+            res(f"{p}.resnets.{j}", c, cout)
+            c = cout
+        if i != n - 1:
+            shapes[f"{p}.downsampler.resample.1.weight"] = (cout, cout, 3, 3)
+            shapes[f"{p}.downsampler.resample.1.bias"] = (cout,)
+            if cfg["temperal_downsample"][i]:
+                conv3(f"{p}.downsampler.time_conv", cout, cout, (3, 1, 1))
+    mid("encoder.mid_block", dims[-1])
+    shapes["encoder.norm_out.gamma"] = (dims[-1], 1, 1, 1)
+    conv3("encoder.conv_out", dims[-1], 2 * z, (3, 3, 3))
+    conv3("quant_conv", 2 * z, 2 * z, (1, 1, 1))
+    conv3("post_quant_conv", z, z, (1, 1, 1))
+    # decoder
+    dims = _vae_dims(cfg, True)
+    t_up = list(cfg["temperal_downsample"])[::-1]
+    conv3("decoder.conv_in", z, dims[0], (3, 3, 3))
+    mid("decoder.mid_block", dims[0])
+    for i, (cin, cout) in enumerate(zip(dims[:-1], dims[1:])):
+        p = f"decoder.up_blocks.{i}"
+        c = cin
+        for j in range(cfg["num_res_blocks"] + 1):
+            res(f"{p}.resnets.{j}", c, cout)
+            c = cout
+        if i != n - 1:
+            shapes[f"{p}.upsampler.resample.1.weight"] = (cout, cout, 3, 3)
+            shapes[f"{p}.upsampler.resample.1.bias"] = (cout,)
+            if t_up[i]:
+                conv3(f"{p}.upsampler.time_conv", cout, 2 * cout, (3, 1, 1))
+    shapes["decoder.norm_out.gamma"] = (dims[-1], 1, 1, 1)
+    conv3("decoder.conv_out", dims[-1], cfg["out_channels"], (3, 3, 3))
+    return shapes
+
+
+def make_vae_state_dict(cfg: dict, seed: int = 0, dtype: torch.dtype = torch.float32, device="cpu"):
+    return make_state_dict(vae_param_shapes(cfg), seed, dtype, (), device)
+
+
+def make_vae_inputs(cfg: dict, latent_frames: int = 3, h: int = 4, w: int = 6, seed: int = 5, device="cpu"):
+    """(z, x): a latent [1, z_dim, T, h, w] for decode and a clip [1, 3, 1 + 4 (T - 1), h*s, w*s] in [-1, 1] for encode
+    (s = scale_factor_spatial), from one seeded generator."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    s_ = cfg["scale_factor_spatial"]
+    z = torch.randn(1, cfg["z_dim"], latent_frames, h, w, generator=g, device=device)
+    x = torch.randn(1, 3, 1 + 4 * (latent_frames - 1), h * s_, w * s_, generator=g, device=device).clamp(-1, 1)
+    return z, x

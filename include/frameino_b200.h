@@ -216,6 +216,49 @@ int fino_attention_fwd_scatter(const void* q, const void* k, const void* v, void
                                int64_t q_batch_stride, int64_t k_batch_stride, int64_t v_batch_stride,
                                int64_t o_batch_stride, float scale, void* stream);
 
+/* ---- Wan VAE encode / decode (reference architecture/autoencoder_kl_wan.py). Activations are
+ * channels-last bf16 [T, H, W, C]: a pixel is a contiguous row of C channels. ----
+ *
+ * Causal 3-D / 2-D convolution as an implicit GEMM on the tcgen05 tensor cores (WanCausalConv3d :134-176, the Conv2d
+ * of WanResample :245-262):  y[t,h,w,:] = bias + sum_{kt,kh,kw} W[:,kt,kh,kw,:] . x[t*stride_t + kt, h*s + kh - pad_h,
+ * w*s + kw - pad_w, :].  "Valid" along time — the caller prepends the causal history frames (the reference's
+ * feat_cache, :169-176); spatial out-of-range reads are zero. x: [t_in, h_in, w_in, c_in], element strides in_st /
+ * in_sh / in_sw (frame / row / pixel). w: [c_out, kt*kh*kw * ceil(c_in/64)*64] (tap-major, each tap's channels
+ * zero-padded to a multiple of 64), row stride ldw. y (and residual, same geometry): element strides out_st / out_sh /
+ * out_sw with out_st, out_sh multiples of out_sw. c_in, c_out multiples of 8. epilogue: FINO_EPI_NONE, or
+ * FINO_EPI_GATE_RESIDUAL = residual + bf16(conv + bias) (the block's skip connection, :382). */
+int fino_conv3d_cl_bf16(const void* x, int t_in, int h_in, int w_in, int c_in, int64_t in_st, int64_t in_sh,
+                        int64_t in_sw, const void* w, int64_t ldw, const void* bias, void* y, int t_out, int h_out,
+                        int w_out, int c_out, int64_t out_st, int64_t out_sh, int64_t out_sw, int kt, int kh, int kw,
+                        int pad_h, int pad_w, int stride_hw, int stride_t, const void* residual, int epilogue,
+                        void* stream);
+/* out[r,:] = act(x[r,:] / max(||x[r,:]||, 1e-12) * sqrt(c) * gamma + bias): WanRMS_norm (:179-202) fused with the SiLU
+ * that follows it (silu = 1) or alone (silu = 0, the attention block's norm :406). gamma / bias float [c], bias optional. */
+int fino_rms_act_cl(const void* x, void* out, int64_t rows, int c, int64_t x_stride, int64_t out_stride,
+                    const float* gamma, const float* bias, int silu, void* stream);
+/* out[t, 2h+i, 2w+j, :] = in[t, h, w, :]: WanUpsample(scale_factor 2, "nearest-exact") (:205-217). */
+int fino_upsample2x_cl(const void* in, void* out, int t, int h, int w, int c, void* stream);
+/* y += DupUp3D(src) (:90-131, :709-710), y [to,ho,wo,co], src [ti,hi,wi,ci], ho = hi*fs, wo = wi*fs; t_drop = ft - 1 for
+ * the first chunk (first_chunk=True drops the first ft - 1 duplicated frames), else 0. */
+int fino_dupup_add_cl(void* y, const void* src, int to, int ho, int wo, int co, int ti, int hi, int wi, int ci, int ft,
+                      int fs, int t_drop, void* stream);
+/* y += AvgDown3D(src) (:37-87, :502), y [to,ho,wo,co], src [ti,hi,wi,ci], hi = ho*fs, wi = wo*fs, frames zero-padded at
+ * the front to a multiple of ft. */
+int fino_avgdown_add_cl(void* y, const void* src, int to, int ho, int wo, int co, int ti, int hi, int wi, int ci, int ft,
+                        int fs, void* stream);
+/* p[r,:] = softmax(s[r,:cols] * scale) (float in, row stride ls; bf16 out, row stride lp, columns [cols, lp) zeroed):
+ * the single-head attention of WanAttentionBlock (:413). cols <= 16384. */
+int fino_softmax_rows(const float* s, void* p, int64_t rows, int cols, int64_t ls, int64_t lp, float scale, void* stream);
+/* [c,t,h,w] (float when in_fp32 else bf16; element strides sc/st/sh/sw) -> channels-last bf16 [t, h/ps, w/ps, cpad] with
+ * the patchify of :912-932 (channel c*ps*ps + (w%ps)*ps + h%ps), channels [c*ps*ps, cpad) zero. */
+int fino_vae_to_cl(const void* in, int in_fp32, void* out, int c, int t, int h, int w, int64_t sc, int64_t st, int64_t sh,
+                   int64_t sw, int ps, int cpad, void* stream);
+/* channels-last bf16 [t, hi, wi, cstride] -> [c, t, hi*ps, wi*ps] (float when out_fp32 else bf16; channel stride out_sc
+ * elements, the rest contiguous — a chunk of frames written into the full video): the unpatchify of :935-952, clamped
+ * to [-1, 1] when clamp != 0 (:1224). */
+int fino_vae_from_cl(const void* in, void* out, int out_fp32, int c, int t, int hi, int wi, int cstride, int ps, int clamp,
+                     int64_t out_sc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

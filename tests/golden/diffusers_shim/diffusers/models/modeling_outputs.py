@@ -6,3 +6,8 @@ import torch
 @dataclass
 class Transformer2DModelOutput:
     sample: torch.Tensor
+
+
+@dataclass
+class AutoencoderKLOutput:
+    latent_dist: "DiagonalGaussianDistribution"  # noqa: F821

@@ -197,8 +197,35 @@ def bf16_golden():
     print("wrote bf16_golden.pt:", {k: (tuple(v.shape), str(v.dtype)) for k, v in out.items() if k.endswith("sample")})
 
 
+def vae_golden():
+    """The reference AutoencoderKLWan (Wan2.2 form: is_residual, patch_size 2) executed on CPU in fp32 — its own chunked
+    encode / decode with feat_cache — on the small VAE_TINY config: decode of a 3-latent-frame latent (9 frames out),
+    encode of a 9-frame clip, and decode of a single latent frame (the first_chunk-only path)."""
+    os.chdir(REF)
+    from architecture.autoencoder_kl_wan import AutoencoderKLWan
+
+    cfg = dict(synth.VAE_TINY)
+    torch.manual_seed(0)
+    vae = AutoencoderKLWan(**cfg, latents_mean=[0.0] * cfg["z_dim"], latents_std=[1.0] * cfg["z_dim"]).eval()
+    sd = synth.make_vae_state_dict(cfg, seed=0)
+    assert set(sd) == set(vae.state_dict()), sorted(set(sd) ^ set(vae.state_dict()))[:10]
+    vae.load_state_dict(sd, strict=True)
+    z, x = synth.make_vae_inputs(cfg, 3, 4, 6, seed=5)
+    out = {}
+    with torch.no_grad():
+        out["decode.sample"] = vae.decode(z, return_dict=False)[0].clone()
+        out["decode1.sample"] = vae.decode(z[:, :, :1], return_dict=False)[0].clone()
+        post = vae.encode(x).latent_dist
+        out["encode.parameters"] = post.parameters.clone()
+        assert torch.equal(post.mode(), post.parameters[:, : cfg["z_dim"]])
+    torch.save(out, os.path.join(HERE, "vae_golden.pt"))
+    print("wrote vae_golden.pt:", {k: tuple(v.shape) for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["wan", "cog", "bf16"]
+    which = sys.argv[1:] or ["wan", "cog", "bf16", "vae"]
+    if "vae" in which:
+        vae_golden()
     if "bf16" in which:
         bf16_golden()
     if "wan" in which:

@@ -160,3 +160,21 @@ def test_cog_oracle_bf16_cast_points_match_reference(bf16_golden):
         _bf16_close(taps[f"transformer_blocks.{i}.out"], bf16_golden[f"cog.tiny.blocks.{i}.out"], f"block {i} video")
         _bf16_close(taps[f"transformer_blocks.{i}.enc"], bf16_golden[f"cog.tiny.blocks.{i}.enc"], f"block {i} text")
     _bf16_close(out, bf16_golden["cog.tiny.sample"], "sample")
+
+
+# ---- Wan VAE: the whole-sequence oracle against the reference's own chunked encode / decode (feat_cache) -----------
+def test_vae_oracle_matches_reference_chunked_execution(golden_dir):
+    from oracle import vae_oracle
+
+    g = torch.load(os.path.join(golden_dir, "vae_golden.pt"))
+    cfg = synth.VAE_TINY
+    sd = synth.make_vae_state_dict(cfg, seed=0)
+    z, x = synth.make_vae_inputs(cfg, 3, 4, 6, seed=5)
+    with torch.no_grad():
+        dec = vae_oracle.decode(sd, cfg, z)
+        dec1 = vae_oracle.decode(sd, cfg, z[:, :, :1])
+        enc = vae_oracle.encode(sd, cfg, x)
+    assert dec.shape == (1, 3, 9, 64, 96) and enc.shape == (1, 2 * cfg["z_dim"], 3, 4, 6)
+    assert torch.allclose(dec, g["decode.sample"], rtol=0, atol=1e-5), float((dec - g["decode.sample"]).abs().max())
+    assert torch.allclose(dec1, g["decode1.sample"], rtol=0, atol=1e-5)
+    assert torch.allclose(enc, g["encode.parameters"], rtol=0, atol=1e-5), float((enc - g["encode.parameters"]).abs().max())
