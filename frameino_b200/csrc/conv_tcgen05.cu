@@ -36,12 +36,12 @@ struct ConvGeom {
 
 template <int BN>
 struct ConvCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN > 128) ? 4 : 6;
   static constexpr int kABytes = GEMM_BM * GEMM_BK * 2;
   static constexpr int kBBytes = BN * GEMM_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
-  static constexpr int kTmemCols = (2 * BN < 32) ? 32 : 2 * BN;
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
 template <int BN, int EPI>
@@ -216,6 +216,7 @@ template <int EPI>
 static int launch_conv_bn(int BN, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, const ConvGeom& g,
                           cudaStream_t stream) {
   if (BN == 256) return launch_conv<256, EPI>(ta, tb, p, g, stream);
+  if (BN == 160) return launch_conv<160, EPI>(ta, tb, p, g, stream);
   if (BN == 128) return launch_conv<128, EPI>(ta, tb, p, g, stream);
   return launch_conv<32, EPI>(ta, tb, p, g, stream);
 }
@@ -245,7 +246,8 @@ int conv3d_cl(const void* x, int t_in, int h_in, int w_in, int c_in, int64_t in_
                  (long long)ldw);
   FINO_CHECK_ARG(((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(residual) |
                    reinterpret_cast<uintptr_t>(bias)) & 15) == 0, "conv3d_cl: y / residual / bias must be 16-byte aligned");
-  const int BN = c_out > 128 ? 256 : (c_out > 32 ? 128 : 32);
+  // N tile: 160 for the encoder widths (160 / 320 / 640 = whole tiles; 256-wide tiles would idle 37 % / 17 % of the MMA)
+  const int BN = (c_out % 160 == 0 && c_out % 256 != 0) ? 160 : c_out > 128 ? 256 : (c_out > 32 ? 128 : 32);
   ConvGeom g;
   g.T = t_out, g.Ho = h_out, g.Wo = w_out;
   g.nhb = (h_out + CONV_TH - 1) / CONV_TH;

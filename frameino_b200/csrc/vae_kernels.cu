@@ -29,58 +29,91 @@ __device__ __forceinline__ void unpack8f(const uint4& u, float* f) {
 __device__ __forceinline__ uint4 pack8f(const float* f) {
   return make_uint4(pk2(f[0], f[1]), pk2(f[2], f[3]), pk2(f[4], f[5]), pk2(f[6], f[7]));
 }
+// streaming 16-byte load (read once: do not allocate in L1)
+__device__ __forceinline__ uint4 ld_stream16(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
 }  // namespace
+
+// These kernels are HBM-bound with one pass over the data, so what sets their speed is the number of bytes each SM keeps
+// in flight: ~6.5 TB/s x ~1.5 us of loaded-DRAM latency / 148 SMs = ~66 KB per SM. One 16-byte load per thread at full
+// occupancy is 32 KB (measured: 3.0-3.5 TB/s); every kernel below therefore issues 4-8 independent 16-byte loads per
+// thread before it consumes the first one.
 
 // ------------------------------------------------------------------------------------------------
 // out[r, :] = act( x[r, :] / max(||x[r, :]||_2, 1e-12) * sqrt(C) * gamma + bias ),  act = SiLU or identity.
 // Warp per pixel row, C <= 1024 (multiple of 8): lane l holds the 16-byte chunks l, l+32, l+64, l+96.
 // ------------------------------------------------------------------------------------------------
-template <int CPL>
-__global__ void __launch_bounds__(256) rms_act_cl_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+template <int CPL, int RPW>  // 16-byte chunks per lane and row; rows per warp (narrow rows: more bytes in flight per warp)
+__global__ void __launch_bounds__(256, 3) rms_act_cl_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                                         int64_t rows, int C, int64_t xs, int64_t os,
                                                         const float* __restrict__ gamma, const float* __restrict__ bias,
                                                         float scale, int silu) {
   const int lane = threadIdx.x & 31;
-  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const int64_t row0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * RPW;
+  if (row0 >= rows) return;
   const int nch = C >> 3;
-  const uint4* xr = reinterpret_cast<const uint4*>(x + row * xs);
-  float v[CPL][8];
-  float sq = 0.f;
+  uint4 raw[RPW][CPL];
 #pragma unroll
-  for (int i = 0; i < CPL; ++i) {
-    const int c = i * 32 + lane;
-    if (c < nch) {
-      unpack8f(xr[c], v[i]);
+  for (int r = 0; r < RPW; ++r) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + (row0 + r) * xs);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) sq = fmaf(v[i][e], v[i][e], sq);
+    for (int i = 0; i < CPL; ++i) {
+      const int c = i * 32 + lane;
+      raw[r][i] = (c < nch && row0 + r < rows) ? ld_stream16(xr + c) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  float sq[RPW];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    sq[r] = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+      float v[8];
+      unpack8f(raw[r][i], v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sq[r] = fmaf(v[e], v[e], sq[r]);
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float inv = 1.0f / fmaxf(sqrtf(sq), 1e-12f);  // F.normalize: x / max(||x||, eps)
-  uint4* orow = reinterpret_cast<uint4*>(out + row * os);
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) sq[r] += __shfl_xor_sync(0xffffffffu, sq[r], o);
 #pragma unroll
   for (int i = 0; i < CPL; ++i) {
     const int c = i * 32 + lane;
-    if (c < nch) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c);
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c + 1);
-      const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      float bs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (bias != nullptr) {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * c);
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * c + 1);
-        bs[0] = b0.x, bs[1] = b0.y, bs[2] = b0.z, bs[3] = b0.w, bs[4] = b1.x, bs[5] = b1.y, bs[6] = b1.z, bs[7] = b1.w;
-      }
-      float o[8];
+    if (c >= nch) continue;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c);
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c + 1);
+    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    float bs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (bias != nullptr) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * c);
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias) + 2 * c + 1);
+      bs[0] = b0.x, bs[1] = b0.y, bs[2] = b0.z, bs[3] = b0.w, bs[4] = b1.x, bs[5] = b1.y, bs[6] = b1.z, bs[7] = b1.w;
+    }
+#pragma unroll
+    for (int r = 0; r < RPW; ++r) {
+      if (row0 + r >= rows) continue;
+      const float inv = scale / fmaxf(sqrtf(sq[r]), 1e-12f);  // F.normalize: x / max(||x||, eps), times sqrt(C)
+      float v[8], o[8];
+      unpack8f(raw[r][i], v);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        float y = v[i][e] * inv * scale * gm[e] + bs[e];
-        if (silu) y = y / (1.0f + __expf(-y));
+        float y = fmaf(v[e] * inv, gm[e], bs[e]);
+        if (silu) {  // y * sigmoid(y) = y / (1 + 2^(-y log2 e)): two MUFU ops (ex2, rcp) and three FP32 ops per element
+          float ex, rc;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-1.4426950408889634f * y));
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(1.0f + ex));
+          y *= rc;
+        }
         o[e] = y;
       }
-      orow[c] = pack8f(o);
+      reinterpret_cast<uint4*>(out + (row0 + r) * os)[c] = pack8f(o);
     }
   }
 }
@@ -91,14 +124,17 @@ int rms_act_cl(const void* x, void* out, int64_t rows, int C, int64_t x_stride, 
   FINO_CHECK_ARG(C >= 8 && C <= 1024 && C % 8 == 0, "rms_act_cl: C=%d (multiple of 8, <= 1024)", C);
   FINO_CHECK_ARG(x_stride % 8 == 0 && out_stride % 8 == 0, "rms_act_cl: strides must be multiples of 8");
   const float scale = sqrtf((float)C);
-  const unsigned grid = (unsigned)((rows + 7) / 8);
   const __nv_bfloat16* xi = (const __nv_bfloat16*)x;
   __nv_bfloat16* oo = (__nv_bfloat16*)out;
   const int cpl = (C / 8 + 31) / 32;
-  if (cpl <= 1) rms_act_cl_kernel<1><<<grid, 256, 0, stream>>>(xi, oo, rows, C, x_stride, out_stride, gamma, bias, scale, silu);
-  else if (cpl <= 2) rms_act_cl_kernel<2><<<grid, 256, 0, stream>>>(xi, oo, rows, C, x_stride, out_stride, gamma, bias, scale, silu);
-  else if (cpl <= 3) rms_act_cl_kernel<3><<<grid, 256, 0, stream>>>(xi, oo, rows, C, x_stride, out_stride, gamma, bias, scale, silu);
-  else rms_act_cl_kernel<4><<<grid, 256, 0, stream>>>(xi, oo, rows, C, x_stride, out_stride, gamma, bias, scale, silu);
+#define FINO_RMS(CPL_, RPW_)                                                                                    \
+  rms_act_cl_kernel<CPL_, RPW_><<<(unsigned)((rows + 8 * RPW_ - 1) / (8 * RPW_)), 256, 0, stream>>>(             \
+      xi, oo, rows, C, x_stride, out_stride, gamma, bias, scale, silu)
+  if (cpl <= 1) FINO_RMS(1, 4);
+  else if (cpl <= 2) FINO_RMS(2, 2);
+  else if (cpl <= 3) FINO_RMS(3, 1);
+  else FINO_RMS(4, 1);
+#undef FINO_RMS
   FINO_CHECK_CUDA(cudaGetLastError());
   return FINO_OK;
 }
@@ -108,23 +144,40 @@ int rms_act_cl(const void* x, void* out, int64_t rows, int C, int64_t x_stride, 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) upsample2x_cl_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int T,
                                                            int H, int W, int vec) {
-  const int64_t total = (int64_t)T * 2 * H * 2 * W * vec;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int v = (int)(idx % vec);
-    int64_t r = idx / vec;
-    const int wo = (int)(r % (2 * W));
-    r /= 2 * W;
-    const int ho = (int)(r % (2 * H));
-    const int t = (int)(r / (2 * H));
-    out[idx] = __ldg(in + (((int64_t)t * H + (ho >> 1)) * W + (wo >> 1)) * vec + v);
+  // one thread = four input vectors (4 independent loads), each stored to its 2 x 2 output pixels
+  const int64_t total = (int64_t)T * H * W * vec;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < total; base += 4 * stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t idx = base + u * stride;
+      if (idx < total) v[u] = ld_stream16(in + idx);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t idx = base + u * stride;
+      if (idx >= total) continue;
+      const int c = (int)(idx % vec);
+      int64_t r = idx / vec;
+      const int w = (int)(r % W);
+      r /= W;
+      const int h = (int)(r % H);
+      const int t = (int)(r / H);
+      uint4* o = out + (((int64_t)t * 2 * H + 2 * h) * 2 * W + 2 * w) * vec + c;
+      o[0] = v[u];
+      o[vec] = v[u];
+      o[(int64_t)2 * W * vec] = v[u];
+      o[(int64_t)2 * W * vec + vec] = v[u];
+    }
   }
 }
 
 int upsample2x_cl(const void* in, void* out, int T, int H, int W, int C, cudaStream_t stream) {
   FINO_CHECK_ARG(in && out && T > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "upsample2x_cl: bad arguments");
-  const int64_t total = (int64_t)T * 4 * H * W * (C / 8);
-  int64_t blocks = (total + 255) / 256;
-  const int64_t cap = (int64_t)num_sms() * 32;
+  const int64_t total = (int64_t)T * H * W * (C / 8);
+  int64_t blocks = (total + 4 * 256 - 1) / (4 * 256);
+  const int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   upsample2x_cl_kernel<<<(unsigned)blocks, 256, 0, stream>>>((const uint4*)in, (uint4*)out, T, H, W, C / 8);
   FINO_CHECK_CUDA(cudaGetLastError());
@@ -138,38 +191,64 @@ int upsample2x_cl(const void* in, void* out, int T, int H, int W, int C, cudaStr
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 dupup_add_cl_kernel(__nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ src, int To, int Ho, int Wo, int Co,
-                    int Hi, int Wi, int Ci, int ft, int fs, int repeats, int t_drop) {
-  const int64_t total = (int64_t)To * Ho * Wo * (Co >> 1);
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % (Co >> 1)) * 2;
-    int64_t r = idx / (Co >> 1);
-    const int wo = (int)(r % Wo);
-    r /= Wo;
-    const int ho = (int)(r % Ho);
-    const int to = (int)(r / Ho);
-    const int fr = to + t_drop;
-    const int ti = fr / ft, a = fr % ft, hi = ho / fs, b = ho % fs, wi = wo / fs, d = wo % fs;
-    const __nv_bfloat16* sp = src + (((int64_t)ti * Hi + hi) * Wi + wi) * Ci;
-    const int k0 = ((c * ft + a) * fs + b) * fs + d;
-    const int k1 = (((c + 1) * ft + a) * fs + b) * fs + d;
-    __nv_bfloat162* yp = reinterpret_cast<__nv_bfloat162*>(y + (((int64_t)to * Ho + ho) * Wo + wo) * Co + c);
-    const float2 cur = __bfloat1622float2(*yp);
-    *yp = __floats2bfloat162_rn(cur.x + __bfloat162float(sp[k0 / repeats]), cur.y + __bfloat162float(sp[k1 / repeats]));
+                    int Hi, int Wi, int Ci, int ft, int fs, int repeats, int rshift, int t_drop) {
+  const int groups = Co >> 3;  // 8 output channels (one 16-byte vector of y) per item, 4 items per thread
+  const int64_t total = (int64_t)To * Ho * Wo * groups;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < total; base += 4 * stride) {
+    uint4 yv[4];
+    uint4* yp[4];
+    const __nv_bfloat16* sp[4];
+    int kb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t idx = base + u * stride;
+      yp[u] = nullptr;
+      if (idx >= total) continue;
+      const int c0 = (int)(idx % groups) * 8;
+      int64_t r = idx / groups;
+      const int wo = (int)(r % Wo);
+      r /= Wo;
+      const int ho = (int)(r % Ho);
+      const int to = (int)(r / Ho);
+      const int fr = to + t_drop;
+      const int ti = fr / ft, a = fr % ft, hi = ho / fs, b = ho % fs, wi = wo / fs, d = wo % fs;
+      sp[u] = src + (((int64_t)ti * Hi + hi) * Wi + wi) * Ci;
+      yp[u] = reinterpret_cast<uint4*>(y + (((int64_t)to * Ho + ho) * Wo + wo) * Co + c0);
+      kb[u] = ((c0 * ft + a) * fs + b) * fs + d;  // folded channel of output channel c0; + e * ft*fs*fs for c0 + e
+      yv[u] = *yp[u];
+    }
+    const int kstep = ft * fs * fs;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (yp[u] == nullptr) continue;
+      float v[8];
+      unpack8f(yv[u], v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = kb[u] + e * kstep;
+        v[e] += __bfloat162float(sp[u][rshift >= 0 ? (k >> rshift) : (k / repeats)]);
+      }
+      *yp[u] = pack8f(v);
+    }
   }
 }
 
 int dupup_add_cl(void* y, const void* src, int To, int Ho, int Wo, int Co, int Ti, int Hi, int Wi, int Ci, int ft, int fs,
                  int t_drop, cudaStream_t stream) {
-  FINO_CHECK_ARG(y && src && To > 0 && Ho > 0 && Wo > 0 && Co > 0 && Co % 2 == 0 && Ci > 0, "dupup_add_cl: bad arguments");
+  FINO_CHECK_ARG(y && src && To > 0 && Ho > 0 && Wo > 0 && Co > 0 && Co % 8 == 0 && Ci > 0, "dupup_add_cl: bad arguments");
   FINO_CHECK_ARG(ft >= 1 && fs >= 1 && (Co * ft * fs * fs) % Ci == 0, "dupup_add_cl: out_channels*factor %% in_channels");
   FINO_CHECK_ARG(Ho == Hi * fs && Wo == Wi * fs && To + t_drop <= Ti * ft, "dupup_add_cl: shape mismatch");
   const int repeats = Co * ft * fs * fs / Ci;
-  const int64_t total = (int64_t)To * Ho * Wo * (Co / 2);
-  int64_t blocks = (total + 255) / 256;
-  const int64_t cap = (int64_t)num_sms() * 32;
+  int rshift = -1;
+  for (int sft = 0; sft < 16; ++sft)
+    if ((1 << sft) == repeats) rshift = sft;
+  const int64_t total = (int64_t)To * Ho * Wo * (Co / 8);
+  int64_t blocks = (total + 4 * 256 - 1) / (4 * 256);
+  const int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   dupup_add_cl_kernel<<<(unsigned)blocks, 256, 0, stream>>>((__nv_bfloat16*)y, (const __nv_bfloat16*)src, To, Ho, Wo, Co,
-                                                           Hi, Wi, Ci, ft, fs, repeats, t_drop);
+                                                           Hi, Wi, Ci, ft, fs, repeats, rshift, t_drop);
   FINO_CHECK_CUDA(cudaGetLastError());
   return FINO_OK;
 }

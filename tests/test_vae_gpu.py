@@ -40,6 +40,8 @@ def _pack(w):  # [Co, Ci, kt, kh, kw] -> [up8(Co), taps * ceil(Ci/64)*64] bf16, 
     (4, 12, 20, 72, 72, (3, 1, 1), 1, 1),     # time_conv
     (5, 10, 14, 64, 64, (3, 1, 1), 1, 2),     # stride-2 time_conv (downsample3d)
     (2, 18, 34, 32, 32, (1, 3, 3), 2, 1),     # stride-2 Conv2d behind ZeroPad2d((0,1,0,1)) (downsample2d)
+    (2, 10, 18, 160, 320, (3, 3, 3), 1, 1),   # encoder widths: 2.5 K chunks per tap (OOB channel fill), N tile 160 x 2
+    (1, 8, 16, 320, 160, (3, 3, 3), 1, 1),    # N tile 160, one tile
 ])
 def test_conv3d_cl_matches_torch(ops, t, h, w, ci, co, k, stride, st):
     g = torch.Generator().manual_seed(0)
@@ -219,3 +221,31 @@ def test_vae_wider_channels_and_batch(ops):
     assert rel_err(out, ref) <= 0.1 and cosine(out, ref) >= COS  # clamped output: see the every-stage test
     enc = vae.encode(x.cuda()).latent_dist.parameters
     assert rel_err(enc, ref_e) <= TOL
+
+
+def test_vae_full_width_decoder_and_encoder(ops):
+    """The real Wan2.2-TI2V-5B VAE widths (decoder 1024/1024/512/256, encoder 160/320/640/640, z 48; 704.7 M parameters)
+    on a small canvas (latent 2 x 2 x 4 -> 5 frames of 32 x 64), every stage against the fp32 CPU oracle."""
+    from oracle import vae_oracle
+
+    cfg = synth.WAN22_VAE
+    sd = synth.make_vae_state_dict(cfg, seed=1)
+    z, x = synth.make_vae_inputs(cfg, 2, 2, 4, seed=3)
+    ref_taps, ref_taps_e = {}, {}
+    with torch.no_grad():
+        ref = vae_oracle.decode(sd, cfg, z, taps=ref_taps)
+        ref_e = vae_oracle.encode(sd, cfg, x, taps=ref_taps_e)
+    vae = _native(cfg, sd)
+    taps = {}
+    vae.__dict__["_fino_taps"] = taps
+    out = vae.decode(z.cuda(), return_dict=False)[0]
+    errs = {k: rel_err(_chunks_to_ncthw(v), ref_taps[k]) for k, v in taps.items()}
+    print("vae full-width decode taps:", {k: f"{e:.2e}" for k, e in errs.items()})
+    assert all(e <= TOL for e in errs.values()), errs
+    assert cosine(out, ref) >= COS
+    taps.clear()
+    enc = vae.encode(x.cuda()).latent_dist.parameters
+    errs = {k: rel_err(_chunks_to_ncthw(v), ref_taps_e[k]) for k, v in taps.items()}
+    errs["parameters"] = rel_err(enc, ref_e)
+    print("vae full-width encode taps:", {k: f"{e:.2e}" for k, e in errs.items()})
+    assert all(e <= TOL for e in errs.values()), errs

@@ -15,7 +15,7 @@ args = [a for a in sys.argv[1:] if not a.startswith("--")]
 iters = 10
 if "--iters" in sys.argv:
     iters = int(sys.argv[sys.argv.index("--iters") + 1])
-which = args or ["attn", "attn64", "cross", "gemm", "rows"]
+which = args or ["attn", "attn64", "cross", "gemm", "rows"]  # also: gemm8 rows64 vae
 if os.environ.get("FINO_GEMM_MODE"):
     ops.gemm_set_mode(int(os.environ["FINO_GEMM_MODE"]))
 if os.environ.get("FINO_ATTN_VARIANT"):
@@ -158,3 +158,15 @@ if "rows64" in which:  # CogVideoX: per-head LayerNorm(64) + RoPE on the joint [
                bytes_=4.0 * n2 * d * 2 + 2.0 * n2 * hd2 * 4, name=f"qk LayerNorm(64)+RoPE 19126x(2x3072) (variant {variant})")
     ops.rows_set_variant(3, 2)
 print("done", which)
+if "vae" in which:  # Wan VAE row kernels at the decoder's widest stages (4 frames of 352x640x256, 176x320x512, ...)
+    for rows_, c_ in [(4 * 352 * 640, 256), (4 * 176 * 320, 512), (2 * 88 * 160, 1024), (4 * 352 * 640, 160)]:
+        xx = torch.randn(rows_, c_, device="cuda").bfloat16()
+        oo = torch.empty_like(xx)
+        gm = torch.ones(c_, device="cuda")
+        timeit(lambda: ops.rms_act_cl(xx, gm, silu=True, out=oo), bytes_=2.0 * rows_ * c_ * 2, name=f"rms_act_cl {rows_}x{c_}")
+        del xx, oo
+    yy = torch.randn(4, 352, 640, 512, device="cuda").bfloat16()
+    ss = torch.randn(4, 176, 320, 1024, device="cuda").bfloat16()
+    timeit(lambda: ops.dupup_add_cl(yy, ss, 1, 2, False), bytes_=2.0 * yy.numel() * 2 + ss.numel() * 2, name="dupup_add_cl 4x352x640x512")
+    timeit(lambda: ops.upsample2x_cl(ss), bytes_=5.0 * ss.numel() * 2, name="upsample2x_cl 4x176x320x1024")
+    del yy, ss
