@@ -46,6 +46,8 @@ class WanTextState:
     kv: List[Optional[Tuple[torch.Tensor, torch.Tensor]]]      # per block; None where a foreign processor is plugged in
     key: Any = None                                            # validity key (input + weight identities/versions)
     source: Optional[torch.Tensor] = None                      # strong reference: keeps the keyed memory from being reused
+    ready: Optional[List[Any]] = None                          # per block: CUDA event recorded on the side stream that
+                                                               # produced kv[i]; None once the main stream has waited
 
 
 def _rope_1d(dim: int, max_len: int, theta: float = 10000.0) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -370,7 +372,13 @@ class WanTransformer3DModel(ModelBase):
         return tuple(parts)
 
     def prepare_text(self, encoder_hidden_states: torch.Tensor) -> WanTextState:
-        """Runs the text embedder (:185) and every block's cross-attention key/value projection + key norm once."""
+        """Runs the text embedder (:185) and every block's cross-attention key/value projection + key norm once.
+
+        The 30 (kv GEMM, k-norm) pairs depend only on the prompt, not on the latents, so they are queued on a SIDE
+        stream (``overlap_text_projection``, default on): they fill the SMs whenever the main stream leaves them idle —
+        under sequence parallelism that is the NVLink-bound exchange and the skew absorbed by the peer barriers — instead
+        of sitting on the critical path in front of every cross-attention. Block i's cross-attention waits on the event
+        recorded after kv[i] (``forward_rows``). Nothing is reordered arithmetically: same kernels, same inputs."""
         if not encoder_hidden_states.is_cuda:
             raise RuntimeError("frameino_b200 has no CPU path: move the model and inputs to a CUDA device")
         dt = self.proj_out.weight.dtype
@@ -379,10 +387,28 @@ class WanTransformer3DModel(ModelBase):
         t1, t2 = ce.text_embedder.linear_1, ce.text_embedder.linear_2
         text = ops.linear(ops.linear(text_in, t1.weight, t1.bias, epilogue=ops.EPI_GELU_TANH), t2.weight, t2.bias)  # :185
         kv: List[Optional[Tuple[torch.Tensor, torch.Tensor]]] = []
-        for b in self.blocks:
-            proc = b.attn2.processor
-            kv.append(proc.project_text(b.attn2, text) if isinstance(proc, FinoWanAttnProcessor) else None)
-        return WanTextState(text=text, kv=kv, key=self._text_key(encoder_hidden_states), source=encoder_hidden_states)
+        ready: Optional[List[Any]] = None
+        dev = text.device
+        if self.__dict__.get("overlap_text_projection", True):
+            main = torch.cuda.current_stream(dev)
+            side = self.__dict__.get("_fino_side_stream")
+            if side is None or side.device != dev:
+                side = self.__dict__["_fino_side_stream"] = torch.cuda.Stream(device=dev)
+            side.wait_stream(main)  # `text` is ready; everything the previous forward queued on `main` has been
+            ready = []              # ordered before, so blocks freed back to the side stream's pool are not in use
+            with torch.cuda.stream(side):
+                for b in self.blocks:
+                    proc = b.attn2.processor
+                    kv.append(proc.project_text(b.attn2, text) if isinstance(proc, FinoWanAttnProcessor) else None)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    ready.append(ev)
+        else:
+            for b in self.blocks:
+                proc = b.attn2.processor
+                kv.append(proc.project_text(b.attn2, text) if isinstance(proc, FinoWanAttnProcessor) else None)
+        return WanTextState(text=text, kv=kv, key=self._text_key(encoder_hidden_states), source=encoder_hidden_states,
+                            ready=ready)
 
     def _text_state(self, encoder_hidden_states: torch.Tensor) -> WanTextState:
         name = self.__dict__.get("_fino_cache_name")
@@ -438,12 +464,17 @@ class WanTransformer3DModel(ModelBase):
         if taps is not None:
             taps["patch_embed"] = x.clone()
             taps["text"] = text.clone()
+        ready = text_state.ready
         for i, block in enumerate(self.blocks):  # :516-517
             if taps is not None:
                 block.__dict__["_fino_tap"] = (taps, f"blocks.{i}")
+            if ready is not None:  # kv[i] was produced on the side stream (prepare_text)
+                torch.cuda.current_stream(x.device).wait_event(ready[i])
             x = block(x, text, mod_all[i], row_index, rows_per_group, rotary_emb, text_state.kv[i])
             if taps is not None:
                 taps[f"blocks.{i}.out"] = x.clone()
+
+        text_state.ready = None  # the main stream is now ordered after every kv[i]; later forwards need not wait again
 
         # output modulation (:520-536): scale_shift_table[1,2,D] + temb
         out_mod = ops.build_mod_table(self.scale_shift_table.reshape(1, 2 * dim).float(),
