@@ -658,11 +658,12 @@ template <int HD, int EMU, bool SPLIT, bool PSEP = false, int EMU_B = EMU, bool 
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        int batch, cudaStream_t stream) {
   using Cfg = AttnCfg<HD>;
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;  // one bit per device: the opt-in is a per-device function attribute
+  const uint64_t dev_bit = 1ull << (current_device() & 63);
+  if (!(configured & dev_bit)) {
     FINO_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<HD, EMU, SPLIT, PSEP, EMU_B, PING>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
+    configured |= dev_bit;
   }
   const int n_tiles = p.q_tiles * p.heads * batch;
   const int n_part = (n_tiles - p.n_full) * p.splits;
@@ -1074,11 +1075,12 @@ attn64x4_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 template <int EMU, int EMU_B, bool STAGGER = true>
 static int launch_attn64x4(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                            int batch, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;  // one bit per device: the opt-in is a per-device function attribute
+  const uint64_t dev_bit = 1ull << (current_device() & 63);
+  if (!(configured & dev_bit)) {
     FINO_CHECK_CUDA(cudaFuncSetAttribute(attn64x4_fwd_kernel<EMU, EMU_B, STAGGER>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          A64_SMEM_BYTES));
-    configured = true;
+    configured |= dev_bit;
   }
   const int n_tiles = p.q_tiles * p.heads * batch;
   const int n_part = (n_tiles - p.n_full) * p.splits;

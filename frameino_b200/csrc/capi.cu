@@ -45,6 +45,7 @@ int peer_export(const void* ptr, void* handle64);
 int peer_import(const void* handle64, void** ptr);
 int peer_release(void* ptr);
 int peer_barrier(void* const* flag_ptrs, int rank, int world, uint32_t epoch, cudaStream_t stream);
+int peer_status(const void* own_flags, uint32_t* status8, cudaStream_t stream);
 int qkv_norm_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride, const void* wq, const void* wk,
                           int heads, int head_dim, float eps, const float* cos, const float* sin,
                           void* const* dst_ptrs, int world, int rank, int64_t rows_per_rank, int64_t dst_row_stride,
@@ -86,8 +87,41 @@ void scatter_set_packed(int on);
 static std::atomic<int64_t> g_launches{0};
 static int g_device = -1;
 
-// Every compute entry point: make sure a usable device is bound, then run and count the launch.
-static int ensure_device() {
+// Every compute entry point: make the bound device current for the duration of the call and put the caller's current
+// device back afterwards (the library must not move torch's current device behind its back; per-device state such as
+// the dynamic-shared-memory opt-in and the split workspaces is keyed by the device that is current inside the call).
+struct DeviceGuard {
+  int prev = -1;
+  int status = 0;
+  DeviceGuard() {
+    if (g_device >= 0) {
+      if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+      if (prev != g_device) {
+        cudaError_t e = cudaSetDevice(g_device);
+        if (e != cudaSuccess) {
+          fino::set_last_error("cudaSetDevice(%d) failed: %s", g_device, cudaGetErrorString(e));
+          status = fino::FINO_ERR_CUDA;
+          prev = -1;
+        }
+      } else {
+        prev = -1;  // nothing to restore
+      }
+      return;
+    }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+      fino::set_last_error("no CUDA device available (%s); frameino_b200 has no CPU fallback",
+                           e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+      status = fino::FINO_ERR_CUDA;
+    }
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+static int ensure_device() {  // allocation / IPC entry points: bind without restoring (they are device management)
   if (g_device >= 0) {
     cudaError_t e = cudaSetDevice(g_device);
     if (e != cudaSuccess) {
@@ -106,13 +140,13 @@ static int ensure_device() {
   return 0;
 }
 
-#define FINO_ENTRY(call)            \
-  do {                              \
-    int _d = ensure_device();       \
-    if (_d) return _d;              \
-    int _r = (call);                \
+#define FINO_ENTRY(call)                  \
+  do {                                    \
+    DeviceGuard _g;                       \
+    if (_g.status) return _g.status;      \
+    int _r = (call);                      \
     if (_r == 0) g_launches.fetch_add(1, std::memory_order_relaxed); \
-    return _r;                      \
+    return _r;                            \
   } while (0)
 
 extern "C" {
@@ -321,6 +355,11 @@ int fino_qkv_norm_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride
 
 int fino_peer_barrier(void* const* flag_ptrs, int rank, int world, uint32_t epoch, void* stream) {
   FINO_ENTRY(fino::peer_barrier(flag_ptrs, rank, world, epoch, (cudaStream_t)stream));
+}
+
+int fino_peer_status(const void* own_flags, uint32_t* status8, void* stream) {
+  int d = ensure_device();
+  return d ? d : fino::peer_status(own_flags, status8, (cudaStream_t)stream);
 }
 
 int fino_wan_pack_model_input(const float* latents, const float* condition, const float* mask,

@@ -43,6 +43,7 @@ const char* get_last_error();
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box, const uint32_t* elem_strides = nullptr);
 
-int num_sms();
+int num_sms();         // SM count of the CURRENT device (cached per device)
+int current_device();  // cudaGetDevice
 
 }  // namespace fino

@@ -541,11 +541,12 @@ void gemm_plan(int tiles, int num_kb, int clusters, int mode, int* num_full, int
 template <int BN, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;  // one bit per device: the opt-in is a per-device function attribute
+  const uint64_t dev_bit = 1ull << (current_device() & 63);
+  if (!(configured & dev_bit)) {
     FINO_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes));
-    configured = true;
+    configured |= dev_bit;
   }
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int grid = tiles < num_sms() ? tiles : num_sms();
@@ -557,11 +558,12 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 template <int MH, int EPI>
 static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<MH>;
-  static bool configured = false;
-  if (!configured) {
+  static uint64_t configured = 0;  // one bit per device: the opt-in is a per-device function attribute
+  const uint64_t dev_bit = 1ull << (current_device() & 63);
+  if (!(configured & dev_bit)) {
     FINO_CHECK_CUDA(cudaFuncSetAttribute(gemm2_bf16_kernel<MH, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes));
-    configured = true;
+    configured |= dev_bit;
   }
   int tiles = p.num_m_tiles * p.num_n_tiles;
   int units = p.num_full + (tiles - p.num_full) * p.splits;

@@ -11,6 +11,7 @@
 //   peer_barrier            flag exchange through peer memory between the two (all ranks' stores have landed).
 //
 // Nothing here calls NCCL; torch.distributed is only used once, on the host, to swap the 64-byte IPC handles.
+#include <stdlib.h>
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -69,10 +70,21 @@ int peer_release(void* ptr) {
 // barrier through peer memory
 // ------------------------------------------------------------------------------------------------
 struct BarrierParams {
-  uint32_t* flags[PEER_MAX_RANKS];  // flags[r] = rank r's flag array (PEER_MAX_RANKS words), peer-mapped
+  uint32_t* flags[PEER_MAX_RANKS];  // flags[r] = rank r's flag array (>= 2 * PEER_MAX_RANKS words), peer-mapped
   int rank, world;
   uint32_t epoch;
+  unsigned long long timeout_ns;  // 0 = wait forever
 };
+
+// Word PEER_MAX_RANKS + t of a rank's own flag array: non-zero once a wait on rank t timed out (epoch it was waiting
+// for). The host reads it (fino_peer_status); the kernel does NOT trap — a trap is a sticky context error on this rank
+// and a hang on the others — it gives up the wait, so the step that follows computes on stale data and the host check
+// turns that into an exception.
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // Thread t < world: tell rank t that `rank` reached `epoch`, then wait until rank t told us the same. The kernel is
 // stream-ordered after the producer kernel, whose (peer) stores are complete when it retires; the release/acquire
@@ -85,18 +97,38 @@ __global__ void peer_barrier_kernel(const __grid_constant__ BarrierParams p) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(p.epoch) : "memory");
     const uint32_t* mine = p.flags[p.rank] + t;
     uint32_t v;
-    unsigned long long spins = 0;
+    unsigned long long t0 = 0;
+    unsigned spins = 0;
     do {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
       if ((int32_t)(v - p.epoch) >= 0) break;
       __nanosleep(64);
-      if (++spins > (1ull << 28)) {  // ~20 s: a peer died; trap instead of hanging the GPU forever
-        printf("fino peer_barrier timeout: rank %d waiting for rank %d at epoch %u (saw %u)\n", p.rank, t, p.epoch, v);
-        __trap();
+      if ((++spins & 0xfffu) == 0 && p.timeout_ns != 0) {  // look at the clock every 4096 polls
+        const unsigned long long now = global_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > p.timeout_ns) {
+          printf("fino peer_barrier timeout: rank %d gave up waiting for rank %d at epoch %u (saw %u)\n", p.rank, t,
+                 p.epoch, v);
+          p.flags[p.rank][PEER_MAX_RANKS + t] = p.epoch ? p.epoch : 1u;
+          break;
+        }
       }
     } while (true);
     __threadfence_system();
   }
+}
+
+// Wait limit of the barrier: FINO_PEER_TIMEOUT_S seconds (default 600; 0 = wait forever). Rank skew far beyond a kernel's
+// duration is legitimate (lazy module loads, host-side preprocessing on one rank, a debugger), so the default is generous.
+static unsigned long long peer_timeout_ns() {
+  static long long cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("FINO_PEER_TIMEOUT_S");
+    double s = e ? atof(e) : 600.0;
+    if (s < 0) s = 0;
+    cached = (long long)(s * 1e9);
+  }
+  return (unsigned long long)cached;
 }
 
 int peer_barrier(void* const* flag_ptrs, int rank, int world, uint32_t epoch, cudaStream_t stream) {
@@ -108,8 +140,19 @@ int peer_barrier(void* const* flag_ptrs, int rank, int world, uint32_t epoch, cu
   p.rank = rank;
   p.world = world;
   p.epoch = epoch;
+  p.timeout_ns = peer_timeout_ns();
   peer_barrier_kernel<<<1, 32, 0, stream>>>(p);
   FINO_CHECK_CUDA(cudaGetLastError());
+  return FINO_OK;
+}
+
+// Copies the calling rank's timeout words (see above) to the host: status[t] != 0 means a barrier gave up waiting for
+// rank t. Synchronises the stream.
+int peer_status(const void* own_flags, uint32_t* status8, cudaStream_t stream) {
+  FINO_CHECK_ARG(own_flags && status8, "peer_status: null pointer");
+  FINO_CHECK_CUDA(cudaMemcpyAsync(status8, reinterpret_cast<const uint32_t*>(own_flags) + PEER_MAX_RANKS,
+                                  PEER_MAX_RANKS * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+  FINO_CHECK_CUDA(cudaStreamSynchronize(stream));
   return FINO_OK;
 }
 

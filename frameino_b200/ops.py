@@ -660,6 +660,17 @@ def peer_barrier(flag_ptrs, rank: int, world: int, epoch: int) -> None:
     _lib.check(lib.fino_peer_barrier(flag_ptrs, rank, world, epoch & 0xFFFFFFFF, stream), "fino_peer_barrier")
 
 
+def peer_status(own_flags_ptr: int):
+    """[8] ints: entry t != 0 means a peer barrier on this rank gave up waiting for rank t (see fino_peer_barrier).
+    Synchronises the current stream."""
+    import ctypes
+
+    lib = _bind_current_device()
+    out = (ctypes.c_uint32 * PEER_MAX_RANKS)()
+    _lib.check(lib.fino_peer_status(own_flags_ptr, out, torch.cuda.current_stream().cuda_stream), "fino_peer_status")
+    return list(out)
+
+
 def qkv_norm_rope_scatter(qkv: torch.Tensor, wq: Optional[torch.Tensor], wk: Optional[torch.Tensor], heads: int,
                           eps: float, cos: Optional[torch.Tensor], sin: Optional[torch.Tensor], dst_ptrs, world: int,
                           rank: int, rows_per_rank: int, dst_row_stride: int) -> None:

@@ -80,12 +80,24 @@ class PeerExchange:
         self.epoch += 1
         self.prims.peer_barrier(self.flag_ptrs, self.rank, self.world, self.epoch)
 
+    def check(self) -> None:
+        """Raises if a peer barrier on this rank timed out (FINO_PEER_TIMEOUT_S): the results since then are invalid.
+        Synchronises the stream — called from close() and available to callers at any point they already sync."""
+        status = getattr(self.prims, "peer_status", None)
+        if status is None or self.base is None:
+            return
+        bad = [(t, e) for t, e in enumerate(status(self.base + self.layout["flags_off"])) if e]
+        if bad:
+            raise RuntimeError(f"rank {self.rank}: peer barrier timed out waiting for rank(s) "
+                               f"{[t for t, _ in bad]} (epochs {[e for _, e in bad]}); outputs after that are invalid")
+
     def close(self) -> None:
         if self.base is None:
             return
         ops = self.prims
         if torch.cuda.is_available():
             torch.cuda.synchronize()
+            self.check()
         dist.barrier(group=self.group)  # nobody is still storing into a buffer that is about to go away
         self.qkv_local = self.o_local = None
         for p in self.imported.values():

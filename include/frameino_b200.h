@@ -193,9 +193,14 @@ int fino_peer_export(const void* ptr, void* handle64);  /* handle64: 64-byte hos
 int fino_peer_import(const void* handle64, void** ptr); /* maps a peer's buffer (enables peer access lazily)       */
 int fino_peer_release(void* ptr);                       /* unmaps an imported buffer                               */
 
-/* Barrier between the ranks' streams through peer memory: flag_ptrs[r] = rank r's flag array (>= 8 uint32, zeroed).
- * `epoch` must increase by one per call (same sequence on every rank). Stream-ordered; no host synchronisation. */
+/* Barrier between the ranks' streams through peer memory: flag_ptrs[r] = rank r's flag array (>= 16 uint32, zeroed).
+ * `epoch` must increase by one per call (same sequence on every rank). Stream-ordered; no host synchronisation. A wait
+ * that exceeds FINO_PEER_TIMEOUT_S seconds (environment, default 600, 0 = forever) is given up WITHOUT trapping: the
+ * kernel records the epoch in word 8 + t of the rank's own flag array and returns; fino_peer_status reads those words. */
 int fino_peer_barrier(void* const* flag_ptrs, int rank, int world, uint32_t epoch, void* stream);
+/* status8[t] (HOST array of 8) = 0, or the epoch at which a barrier on this rank gave up waiting for rank t.
+ * own_flags = this rank's flag array. Synchronises `stream`. */
+int fino_peer_status(const void* own_flags, uint32_t* status8, void* stream);
 
 /* First all-to-all fused into the q/k prologue: RMSNorm across heads (+ Wan RoPE when cos/sin != NULL; transformer_wan.py
  * :64-90) of the local fused projection rows qkv[rows, row_stride] (q | k | v, heads*head_dim columns each), stored

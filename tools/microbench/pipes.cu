@@ -11,10 +11,11 @@
 constexpr int ITER = 2048;
 constexpr int ILP = 8;
 
-enum Op { EX2, CVT, EX2_CVT, FMNMX, FMNMX3, FFMA2, FADD2, FFMA, FADDRM, PRMT, SHL, IADD, EX2_PRMT, LOP, NOPS };
+enum Op { EX2, CVT, EX2_CVT, FMNMX, FMNMX3, FFMA2, FADD2, FFMA, FADDRM, PRMT, SHL, IADD, EX2_PRMT, LOP, EX2_BF16X2, EX2_F16X2,
+          HFMA2_BF16, NOPS };
 static const char* names[] = {"ex2.approx", "cvt.bf16x2", "ex2+cvt(1:0.5)", "max.f32", "max.f32 x3", "fma.f32x2",
                               "add.f32x2", "fma.f32", "add.rm.f32", "prmt", "shl", "add.s32", "ex2+prmt(1:0.5)",
-                              "and.b32"};
+                              "and.b32", "ex2.bf16x2", "ex2.f16x2", "fma.bf16x2"};
 
 template <int OP>
 __global__ void __launch_bounds__(1024) k(float* out, long long* cyc, float seed) {
@@ -42,6 +43,9 @@ __global__ void __launch_bounds__(1024) k(float* out, long long* cyc, float seed
         if (i & 1)
           asm volatile("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(u[i]) : "r"(__float_as_uint(a[i - 1])), "r"(__float_as_uint(a[i])));
       }
+      if (OP == EX2_BF16X2) asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(u[i]));
+      if (OP == EX2_F16X2) asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(u[i]));
+      if (OP == HFMA2_BF16) asm volatile("fma.rn.bf16x2 %0, %0, %1, %2;" : "+r"(u[i]) : "r"(u[(i + 1) % ILP]), "r"(u[(i + 2) % ILP]));
       if (OP == FMNMX) asm volatile("max.f32 %0, %0, %1;" : "+f"(a[i]) : "f"(b[i]));
       if (OP == FMNMX3) asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(a[i]) : "f"(b[i]), "f"(b[(i + 1) % ILP]));
       if (OP == FFMA2) {
@@ -118,6 +122,9 @@ int main() {
     run<SHL>(w, out, cyc);
     run<IADD>(w, out, cyc);
     run<LOP>(w, out, cyc);
+    run<EX2_BF16X2>(w, out, cyc);
+    run<EX2_F16X2>(w, out, cyc);
+    run<HFMA2_BF16>(w, out, cyc);
   }
   return 0;
 }
