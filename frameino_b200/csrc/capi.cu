@@ -50,6 +50,10 @@ int qkv_norm_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride, con
                           int heads, int head_dim, float eps, const float* cos, const float* sin,
                           void* const* dst_ptrs, int world, int rank, int64_t rows_per_rank, int64_t dst_row_stride,
                           cudaStream_t stream);
+int qkv_ln_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride, const void* wq, const void* bq, const void* wk,
+                        const void* bk, int heads, int head_dim, float eps, const float* cos, const float* sin,
+                        int64_t rope_skip, void* const* dst_ptrs, int world, int rank, int64_t rows_per_rank,
+                        int64_t dst_row_stride, cudaStream_t stream);
 int wan_pack_model_input(const float* latents, const float* condition, const float* mask, const float* id_latents,
                          const float* traj, void* rows, int B, int C, int F, int NID, int H, int W, int pt, int ph,
                          int pw, int64_t ld, cudaStream_t stream);
@@ -351,6 +355,14 @@ int fino_qkv_norm_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride
                                int64_t dst_row_stride, void* stream) {
   FINO_ENTRY(fino::qkv_norm_rope_scatter(qkv, rows, row_stride, wq, wk, heads, head_dim, eps, cos, sin, dst_ptrs, world,
                                          rank, rows_per_rank, dst_row_stride, (cudaStream_t)stream));
+}
+
+int fino_qkv_ln_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride, const void* wq, const void* bq,
+                             const void* wk, const void* bk, int heads, int head_dim, float eps, const float* cos,
+                             const float* sin, int64_t rope_skip, void* const* dst_ptrs, int world, int rank,
+                             int64_t rows_per_rank, int64_t dst_row_stride, void* stream) {
+  FINO_ENTRY(fino::qkv_ln_rope_scatter(qkv, rows, row_stride, wq, bq, wk, bk, heads, head_dim, eps, cos, sin, rope_skip,
+                                       dst_ptrs, world, rank, rows_per_rank, dst_row_stride, (cudaStream_t)stream));
 }
 
 int fino_peer_barrier(void* const* flag_ptrs, int rank, int world, uint32_t epoch, void* stream) {

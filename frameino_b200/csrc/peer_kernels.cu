@@ -375,6 +375,171 @@ qkv_norm_rope_scatter_kernel2(const __grid_constant__ ScatterParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// CogVideoX prologue of the fused exchange: per-head LayerNorm(64) (+ CogVideoX RoPE on the video rows) of the local
+// fused projection rows, stored straight into the owning ranks' buffers (attention_processor.py:2848-2860 followed by
+// the first Ulysses all-to-all). Same lane layout as qk_ln64_rope_kernel (norm_kernels.cu): lane l holds the 16-byte
+// chunk i*32 + l of every 256-column group i, a 64-wide head is 8 consecutive lanes of one group, so the chunk's
+// destination rank (head / heads_per_rank) and its column inside that rank's (q | k | v) row are cheap integer math
+// and every 8-lane group writes one head's 128 contiguous bytes. CTA x handles q (x % 3 == 0), k (1) or v (2: copy).
+// ------------------------------------------------------------------------------------------------
+struct LnScatterParams {
+  const __nv_bfloat16* qkv;
+  int64_t rows, row_stride;
+  const __nv_bfloat16 *wq, *bq, *wk, *bk;  // [64] each (null: no affine)
+  int heads;
+  float eps;
+  const float* cos;  // [rows - rope_skip, 64] fp32 rows of the LOCAL video tokens (null: no RoPE)
+  const float* sin;
+  int64_t rope_skip;  // leading local rows that are text (not rotated)
+  __nv_bfloat16* dst[PEER_MAX_RANKS];
+  int world, rank;
+  int64_t rows_per_rank, dst_row_stride;
+  int inner;  // heads * 64 / world
+};
+
+template <int CPL, int G>
+__global__ void __launch_bounds__(256, 3) qkv_ln64_rope_scatter_kernel(const __grid_constant__ LnScatterParams p) {
+  constexpr int dim = CPL * 256;
+  const int lane = threadIdx.x & 31;
+  const int which = blockIdx.x % 3;
+  const int64_t row = (int64_t)(blockIdx.x / 3) * 8 + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  const uint4* src = reinterpret_cast<const uint4*>(p.qkv + row * p.row_stride + which * dim) + lane;
+  const int64_t drow = ((int64_t)p.rank * p.rows_per_rank + row) * p.dst_row_stride + which * p.inner;
+  const int hc = lane & 7;
+  const bool do_rope = which < 2 && p.cos != nullptr && row >= p.rope_skip;
+  uint4 wq = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u), bq = make_uint4(0u, 0u, 0u, 0u);
+  float cs[8], sn[8];
+  if (which < 2) {
+    const __nv_bfloat16* wt = which ? p.wk : p.wq;
+    const __nv_bfloat16* bt = which ? p.bk : p.bq;
+    if (wt != nullptr) wq = __ldg(reinterpret_cast<const uint4*>(wt) + hc);
+    if (bt != nullptr) bq = __ldg(reinterpret_cast<const uint4*>(bt) + hc);
+    if (do_rope) {
+      const float4* cp = reinterpret_cast<const float4*>(p.cos + (row - p.rope_skip) * 64 + hc * 8);
+      const float4* sp = reinterpret_cast<const float4*>(p.sin + (row - p.rope_skip) * 64 + hc * 8);
+      const float4 a = __ldg(cp), b = __ldg(cp + 1), s0 = __ldg(sp), s1 = __ldg(sp + 1);
+      cs[0] = a.x, cs[1] = a.y, cs[2] = a.z, cs[3] = a.w, cs[4] = b.x, cs[5] = b.y, cs[6] = b.z, cs[7] = b.w;
+      sn[0] = s0.x, sn[1] = s0.y, sn[2] = s0.z, sn[3] = s0.w, sn[4] = s1.x, sn[5] = s1.y, sn[6] = s1.z, sn[7] = s1.w;
+    }
+  }
+#pragma unroll 1
+  for (int g0 = 0; g0 < CPL; g0 += G) {
+    uint4 raw[G];
+#pragma unroll
+    for (int i = 0; i < G; ++i) raw[i] = src[(g0 + i) * 32];
+    float mean[G], rstd[G];
+    if (which < 2) {
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        float v[8];
+        unpack8_f(raw[i], v);
+        mean[i] = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1)
+#pragma unroll
+        for (int i = 0; i < G; ++i) mean[i] += __shfl_xor_sync(0xffffffffu, mean[i], o);
+#pragma unroll
+      for (int i = 0; i < G; ++i) {
+        mean[i] *= (1.0f / 64.0f);
+        float v[8];
+        unpack8_f(raw[i], v);
+        float sq = 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float d = v[e] - mean[i];
+          sq = fmaf(d, d, sq);
+        }
+        rstd[i] = sq;
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1)
+#pragma unroll
+        for (int i = 0; i < G; ++i) rstd[i] += __shfl_xor_sync(0xffffffffu, rstd[i], o);
+    }
+    float w[8], b[8];
+    unpack8_f(wq, w);
+    unpack8_f(bq, b);
+#pragma unroll
+    for (int i = 0; i < G; ++i) {
+      const int col = (g0 + i) * 256 + lane * 8;
+      const int g = col / p.inner;  // destination rank (a chunk never straddles a head, hence never a rank)
+      uint4* d16 = reinterpret_cast<uint4*>(p.dst[g] + drow + (col - g * p.inner));
+      if (which == 2) {
+        *d16 = raw[i];
+        continue;
+      }
+      const float r = rsqrtf(rstd[i] * (1.0f / 64.0f) + p.eps);
+      float v[8];
+      unpack8_f(raw[i], v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = rbf_f((v[e] - mean[i]) * r * w[e] + b[e]);
+      if (do_rope) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {
+          const float xe = v[e], xo = v[e + 1];
+          o[e] = __fadd_rn(__fmul_rn(xe, cs[e]), __fmul_rn(-xo, sn[e]));
+          o[e + 1] = __fadd_rn(__fmul_rn(xo, cs[e + 1]), __fmul_rn(xe, sn[e + 1]));
+        }
+        *d16 = pack8_f(o);
+      } else {
+        *d16 = pack8_f(v);
+      }
+    }
+  }
+}
+
+int qkv_ln_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride, const void* wq, const void* bq, const void* wk,
+                        const void* bk, int heads, int head_dim, float eps, const float* cos, const float* sin,
+                        int64_t rope_skip, void* const* dst_ptrs, int world, int rank, int64_t rows_per_rank,
+                        int64_t dst_row_stride, cudaStream_t stream) {
+  FINO_CHECK_ARG(qkv != nullptr && rows > 0 && dst_ptrs != nullptr, "qkv_ln_rope_scatter: null / empty input");
+  FINO_CHECK_ARG(world >= 1 && world <= PEER_MAX_RANKS && rank >= 0 && rank < world,
+                 "qkv_ln_rope_scatter: bad rank/world (%d/%d)", rank, world);
+  FINO_CHECK_ARG(head_dim == 64 && heads > 0 && heads % world == 0,
+                 "qkv_ln_rope_scatter: head_dim 64 and heads divisible by the world size (%d heads x %d over %d)", heads,
+                 head_dim, world);
+  const int dim = heads * 64;
+  FINO_CHECK_ARG(dim == 3072 || dim == 256 || dim == 512, "qkv_ln_rope_scatter: heads*64 = %d (built for 256 / 512 / 3072)", dim);
+  FINO_CHECK_ARG(row_stride % 8 == 0 && row_stride >= 3 * dim, "qkv_ln_rope_scatter: row stride");
+  const int inner = dim / world;
+  FINO_CHECK_ARG(dst_row_stride % 8 == 0 && dst_row_stride >= 3 * inner, "qkv_ln_rope_scatter: dst row stride");
+  FINO_CHECK_ARG(rows <= rows_per_rank, "qkv_ln_rope_scatter: more local rows than rows_per_rank");
+  FINO_CHECK_ARG((cos == nullptr) == (sin == nullptr) && rope_skip >= 0, "qkv_ln_rope_scatter: cos / sin / rope_skip");
+  LnScatterParams p;
+  p.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  p.rows = rows;
+  p.row_stride = row_stride;
+  p.wq = reinterpret_cast<const __nv_bfloat16*>(wq);
+  p.bq = reinterpret_cast<const __nv_bfloat16*>(bq);
+  p.wk = reinterpret_cast<const __nv_bfloat16*>(wk);
+  p.bk = reinterpret_cast<const __nv_bfloat16*>(bk);
+  p.heads = heads;
+  p.eps = eps;
+  p.cos = cos;
+  p.sin = sin;
+  p.rope_skip = rope_skip;
+  for (int r = 0; r < PEER_MAX_RANKS; ++r) {
+    FINO_CHECK_ARG(r >= world || (dst_ptrs[r] != nullptr && (reinterpret_cast<uintptr_t>(dst_ptrs[r]) & 15) == 0),
+                   "qkv_ln_rope_scatter: dst %d null or unaligned", r);
+    p.dst[r] = reinterpret_cast<__nv_bfloat16*>(dst_ptrs[r < world ? r : 0]);
+  }
+  p.world = world;
+  p.rank = rank;
+  p.rows_per_rank = rows_per_rank;
+  p.dst_row_stride = dst_row_stride;
+  p.inner = inner;
+  dim3 grid((unsigned)(3 * ((rows + 7) / 8)));
+  if (dim == 3072) qkv_ln64_rope_scatter_kernel<12, 4><<<grid, 256, 0, stream>>>(p);
+  else if (dim == 512) qkv_ln64_rope_scatter_kernel<2, 2><<<grid, 256, 0, stream>>>(p);
+  else qkv_ln64_rope_scatter_kernel<1, 1><<<grid, 256, 0, stream>>>(p);
+  FINO_CHECK_CUDA(cudaGetLastError());
+  return FINO_OK;
+}
+
 template <int GPL, int HPR>
 static void launch_scatter2(const ScatterParams& p, cudaStream_t stream) {
   dim3 grid((unsigned)(3 * ((p.rows + 7) / 8)));

@@ -694,6 +694,28 @@ def qkv_norm_rope_scatter(qkv: torch.Tensor, wq: Optional[torch.Tensor], wk: Opt
     _lib.check(status, "fino_qkv_norm_rope_scatter")
 
 
+def qkv_ln_rope_scatter(qkv: torch.Tensor, wq, bq, wk, bk, heads: int, eps: float, cos: Optional[torch.Tensor],
+                        sin: Optional[torch.Tensor], rope_skip: int, dst_ptrs, world: int, rank: int, rows_per_rank: int,
+                        dst_row_stride: int) -> None:
+    """CogVideoX: per-head LayerNorm(64) (+ RoPE on local rows >= rope_skip) of the local [rows, 3*D] projections,
+    stored into every rank's exchange buffer (``fino_qkv_ln_rope_scatter``). cos/sin: fp32 [rows - rope_skip, 64]."""
+    assert qkv.dtype == torch.bfloat16
+    lib, stream = _prep(qkv, wq, bq, wk, bk, cos, sin)
+    rows, cols, stride = _rows2d(qkv)
+    dim = cols // 3
+    assert dim * 3 == cols and dim == heads * 64
+    for t in (wq, bq, wk, bk):
+        if t is not None:
+            assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.numel() == 64
+    if cos is not None:
+        assert cos.dtype == sin.dtype == torch.float32 and cos.is_contiguous() and sin.is_contiguous()
+        assert cos.shape == sin.shape == (rows - rope_skip, 64), (tuple(cos.shape), rows, rope_skip)
+    status = lib.fino_qkv_ln_rope_scatter(qkv.data_ptr(), rows, stride, _ptr(wq), _ptr(bq), _ptr(wk), _ptr(bk), heads, 64,
+                                          float(eps), _ptr(cos), _ptr(sin), rope_skip, dst_ptrs, world, rank,
+                                          rows_per_rank, dst_row_stride, stream)
+    _lib.check(status, "fino_qkv_ln_rope_scatter")
+
+
 def attention_scatter(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, o_ptrs, num_owners: int,
                       rows_per_owner: int, o_row_stride: int, scale: Optional[float] = None) -> None:
     """``attention`` whose output rows are stored into their owners' buffers (``fino_attention_fwd_scatter``):

@@ -219,21 +219,27 @@ class FinoCogVideoXAttnProcessor:
             if cos.shape[0] != s - text_len:
                 raise ValueError(f"rotary table has {cos.shape[0]} rows for {s - text_len} video tokens")
             mode = ops.ROPE_COGVIDEOX
-        if norm_q is not None:
-            ops.qk_norm_rope(q, norm_q.weight, k, norm_k.weight, heads, b0=norm_q.bias, b1=norm_k.bias,
-                             rope1=not getattr(attn, "is_cross_attention", False),
-                             norm_mode=ops.QK_LAYERNORM_PER_HEAD, eps=getattr(norm_q, "eps", 1e-6), rope_mode=mode,
-                             cos=cos, sin=sin, seq_len=s, rope_skip=text_len)
-        elif mode != ops.ROPE_NONE:
-            raise NotImplementedError("RoPE without qk-norm is not used by the reference CogVideoX path")
         scale = getattr(attn, "scale", head_dim ** -0.5)
         sp = attn.__dict__.get("_fino_sp")
-        if sp is not None:  # Ulysses: joint rows are sharded over the ranks, one exchange pair per batch element
-            if fino_joint_text_len is None:
-                raise NotImplementedError("sequence parallelism needs the native joint-sequence block")
-            o = torch.cat([sp.attention(qkv[i:i + 1], heads, scale) for i in range(b)], dim=0)
+        if sp is not None and fino_joint_text_len is None:
+            raise NotImplementedError("sequence parallelism needs the native joint-sequence block")
+        if (sp is not None and sp.mode == "peer" and norm_q is not None and head_dim == 64
+                and not getattr(attn, "is_cross_attention", False)):
+            # Ulysses over peer memory: per-head LayerNorm + RoPE + 1st exchange in one kernel per sample, attention +
+            # 2nd exchange in another (the joint rows are sharded over the ranks; text rows sit on rank 0)
+            o = sp.fused_attention_ln(qkv, norm_q, norm_k, heads, getattr(norm_q, "eps", 1e-6), cos, sin, text_len, scale)
         else:
-            o = ops.attention(q, k, v, heads, scale=scale)
+            if norm_q is not None:
+                ops.qk_norm_rope(q, norm_q.weight, k, norm_k.weight, heads, b0=norm_q.bias, b1=norm_k.bias,
+                                 rope1=not getattr(attn, "is_cross_attention", False),
+                                 norm_mode=ops.QK_LAYERNORM_PER_HEAD, eps=getattr(norm_q, "eps", 1e-6), rope_mode=mode,
+                                 cos=cos, sin=sin, seq_len=s, rope_skip=text_len)
+            elif mode != ops.ROPE_NONE:
+                raise NotImplementedError("RoPE without qk-norm is not used by the reference CogVideoX path")
+            if sp is not None:  # NCCL exchange: one all-to-all pair per batch element
+                o = torch.cat([sp.attention(qkv[i:i + 1], heads, scale) for i in range(b)], dim=0)
+            else:
+                o = ops.attention(q, k, v, heads, scale=scale)
         if fino_residual is not None:  # x + gate * out (cogvideox_transformer_3d.py:146-147), joint layout only
             x, gate, row_index = fino_residual
             return ops.linear(o, attn.to_out[0].weight, attn.to_out[0].bias, epilogue=ops.EPI_GATE_RESIDUAL,

@@ -28,9 +28,10 @@ import torch.distributed as dist
 from . import ops
 
 
-def exchange_layout(world: int, rank: int, n_loc: int, d_model: int, elem_bytes: int = 2) -> dict:
+def exchange_layout(world: int, rank: int, n_loc: int, d_model: int, elem_bytes: int = 2, batch: int = 1) -> dict:
     """Byte layout of one rank's peer buffer and the offsets the fused kernels are given (pure arithmetic; unit-tested
-    on CPU). Buffer = [flags 256 B | qkv [world*n_loc, 3*inner] | o [n_loc, d_model]], each part 256-byte aligned.
+    on CPU). Buffer = [flags 256 B | batch x qkv [world*n_loc, 3*inner] | batch x o [n_loc, d_model]], each part
+    256-byte aligned (``batch`` > 1: CogVideoX runs its batched-CFG pair through one exchange, one slot per sample).
     ``o_col_offset`` is where THIS rank's heads start inside every owner's O row."""
     assert d_model % world == 0
     inner = d_model // world
@@ -39,24 +40,26 @@ def exchange_layout(world: int, rank: int, n_loc: int, d_model: int, elem_bytes:
         return (x + 255) // 256 * 256
 
     qkv_off = 256
-    qkv_bytes = world * n_loc * 3 * inner * elem_bytes
-    o_off = up(qkv_off + qkv_bytes)
-    o_bytes = n_loc * d_model * elem_bytes
+    qkv_bytes = up(world * n_loc * 3 * inner * elem_bytes)
+    o_off = up(qkv_off + batch * qkv_bytes)
+    o_bytes = up(n_loc * d_model * elem_bytes)
     return {"inner": inner, "n_pad": world * n_loc, "flags_off": 0, "qkv_off": qkv_off, "qkv_row_stride": 3 * inner,
             "o_off": o_off, "o_row_stride": d_model, "o_col_offset": rank * inner * elem_bytes,
-            "total_bytes": up(o_off + o_bytes)}
+            "qkv_batch_bytes": qkv_bytes, "o_batch_bytes": o_bytes, "batch": batch,
+            "total_bytes": up(o_off + batch * o_bytes)}
 
 
 class PeerExchange:
-    """The peer-mapped exchange buffers of one (n_loc, d_model) problem: own allocation + the mapped buffers of every
-    other rank (CUDA IPC handles swapped once over ``torch.distributed``)."""
+    """The peer-mapped exchange buffers of one (n_loc, d_model, batch) problem: own allocation + the mapped buffers of
+    every other rank (CUDA IPC handles swapped once over ``torch.distributed``)."""
 
-    def __init__(self, group, world: int, rank: int, n_loc: int, d_model: int, prims=ops):
+    def __init__(self, group, world: int, rank: int, n_loc: int, d_model: int, prims=ops, batch: int = 1):
         # `prims`: the device primitives (peer_alloc/export/import/release/free, pointer_table, tensor_from_ptr,
         # peer_barrier); the world-size-2 gloo test on CPU passes shared-memory stand-ins to exercise this host logic
         self.group, self.world, self.rank, self.n_loc, self.d_model = group, world, rank, n_loc, d_model
+        self.batch = batch
         self.prims = ops = prims
-        self.layout = lay = exchange_layout(world, rank, n_loc, d_model)
+        self.layout = lay = exchange_layout(world, rank, n_loc, d_model, batch=batch)
         self.base = ops.peer_alloc(lay["total_bytes"])
         handles = [None] * world
         dist.all_gather_object(handles, ops.peer_export(self.base), group=group)
@@ -69,10 +72,17 @@ class PeerExchange:
                 self.imported[r] = ops.peer_import(handles[r])
                 bases.append(self.imported[r])
         self.flag_ptrs = ops.pointer_table([b + lay["flags_off"] for b in bases])
-        self.qkv_ptrs = ops.pointer_table([b + lay["qkv_off"] for b in bases])
-        self.o_ptrs = ops.pointer_table([b + lay["o_off"] + lay["o_col_offset"] for b in bases])
-        self.qkv_local = ops.tensor_from_ptr(self.base + lay["qkv_off"], (1, lay["n_pad"], 3 * lay["inner"]))
-        self.o_local = ops.tensor_from_ptr(self.base + lay["o_off"], (1, n_loc, d_model))
+        qb, ob = lay["qkv_batch_bytes"], lay["o_batch_bytes"]
+        self.qkv_ptrs_b = [ops.pointer_table([b + lay["qkv_off"] + i * qb for b in bases]) for i in range(batch)]
+        self.o_ptrs_b = [ops.pointer_table([b + lay["o_off"] + i * ob + lay["o_col_offset"] for b in bases])
+                         for i in range(batch)]
+        self.qkv_local_b = [ops.tensor_from_ptr(self.base + lay["qkv_off"] + i * qb, (1, lay["n_pad"], 3 * lay["inner"]))
+                            for i in range(batch)]
+        self.o_local_b = [ops.tensor_from_ptr(self.base + lay["o_off"] + i * ob, (1, n_loc, d_model))
+                          for i in range(batch)]
+        # batch slot 0 under the names the single-sample (Wan) path uses
+        self.qkv_ptrs, self.o_ptrs = self.qkv_ptrs_b[0], self.o_ptrs_b[0]
+        self.qkv_local, self.o_local = self.qkv_local_b[0], self.o_local_b[0]
         self.epoch = 0
         dist.barrier(group=group)  # every rank has mapped every buffer before anyone stores into one
 
@@ -100,6 +110,7 @@ class PeerExchange:
             self.check()
         dist.barrier(group=self.group)  # nobody is still storing into a buffer that is about to go away
         self.qkv_local = self.o_local = None
+        self.qkv_local_b = self.o_local_b = []
         for p in self.imported.values():
             ops.peer_release(p)
         self.imported = {}
@@ -121,6 +132,7 @@ class SequenceParallel:
         self._exchanges = {}
         self._prims = ops
         self._qkv_scatter = ops.qkv_norm_rope_scatter
+        self._qkv_ln_scatter = ops.qkv_ln_rope_scatter
         self._attention_scatter = ops.attention_scatter
         self.n_total = 0
         self.n_pad = 0
@@ -189,14 +201,15 @@ class SequenceParallel:
         return out.view(1, n_loc, d_model)
 
     # ---- the same exchange fused into the neighbouring kernels over peer memory -------------------------------
-    def exchange(self, n_loc: int, d_model: int) -> PeerExchange:
-        key = (n_loc, d_model)
+    def exchange(self, n_loc: int, d_model: int, batch: int = 1) -> PeerExchange:
+        key = (n_loc, d_model, batch)
         ex = self._exchanges.get(key)
         if ex is None:
             for old in self._exchanges.values():  # one live problem shape at a time (the sampler's canvas is fixed)
                 old.close()
             self._exchanges = {}
-            ex = self._exchanges[key] = PeerExchange(self.group, self.world, self.rank, n_loc, d_model, self._prims)
+            ex = self._exchanges[key] = PeerExchange(self.group, self.world, self.rank, n_loc, d_model, self._prims,
+                                                     batch=batch)
         return ex
 
     def fused_attention(self, qkv: torch.Tensor, norm_q_weight, norm_k_weight, heads: int, eps: float, cos, sin,
@@ -223,6 +236,35 @@ class SequenceParallel:
         ex.barrier()
         return ex.o_local
 
+    def fused_attention_ln(self, qkv: torch.Tensor, norm_q, norm_k, heads: int, eps: float, cos, sin, rope_skip: int,
+                           scale: float) -> torch.Tensor:
+        """CogVideoX form of ``fused_attention``: qkv = local RAW fused projections [B, n_loc, 3*D] of the JOINT
+        [text | video] rows (B = the pipeline's batched CFG pair); per-head LayerNorm(64) + RoPE (local rows >=
+        ``rope_skip``, the text rows, are not rotated) + first exchange in one kernel per sample, one barrier, attention
+        + second exchange per sample, one barrier. Returns [B, n_loc, D] (a view of this rank's peer buffer)."""
+        assert qkv.dim() == 3
+        p = self.world
+        b, n_loc, d3 = qkv.shape
+        d_model = d3 // 3
+        assert heads % p == 0, f"{heads} heads cannot be split over {p} ranks"
+        assert n_loc == self.n_loc, "plan() must run before the forward"
+        ex = self.exchange(n_loc, d_model, batch=b)
+        lay = ex.layout
+        inner = lay["inner"]
+        for i in range(b):
+            self._qkv_ln_scatter(qkv[i], norm_q.weight, norm_q.bias, norm_k.weight, norm_k.bias, heads, eps, cos, sin,
+                                 rope_skip, ex.qkv_ptrs_b[i], p, self.rank, n_loc, lay["qkv_row_stride"])
+        ex.barrier()
+        for i in range(b):
+            full = ex.qkv_local_b[i][:, : self.n_total]
+            self._attention_scatter(full[..., :inner], full[..., inner:2 * inner], full[..., 2 * inner:], heads // p,
+                                    ex.o_ptrs_b[i], p, n_loc, lay["o_row_stride"], scale)
+        ex.barrier()
+        if b == 1:
+            return ex.o_local_b[0]
+        # the batch slots are 256-byte aligned, hence not one strided tensor in general: stack them (2 x n_loc x D bf16)
+        return torch.cat(ex.o_local_b[:b], dim=0)
+
     def close(self) -> None:
         for ex in self._exchanges.values():
             ex.close()
@@ -244,12 +286,9 @@ def _self_attention_modules(model):
 
 
 def enable_sequence_parallel(model, group: Optional[dist.ProcessGroup] = None, mode: str = "peer") -> SequenceParallel:
-    """Switches a ``frameino_b200`` transformer to Ulysses sequence parallelism over ``group``. Wan: ``mode="peer"``
-    (exchange fused into the neighbouring kernels over NVLink peer memory) or ``"nccl"``. CogVideoX (joint text + video
-    sequence, per-head LayerNorm): ``"nccl"`` only — the fused prologue kernel is the Wan RMSNorm / RoPE one."""
-    is_wan = hasattr(model, "blocks")
-    if not is_wan and mode != "nccl":
-        raise NotImplementedError("CogVideoX sequence parallelism uses mode='nccl' (the peer-memory prologue is Wan's)")
+    """Switches a ``frameino_b200`` transformer to Ulysses sequence parallelism over ``group``: ``mode="peer"`` (the
+    exchange fused into the neighbouring kernels over NVLink peer memory: RMSNorm + Wan RoPE prologue for Wan, per-head
+    LayerNorm + CogVideoX RoPE prologue over the joint text + video rows for CogVideoX) or ``"nccl"``."""
     sp = SequenceParallel(group, mode)
     model.sequence_parallel = sp
     for attn in _self_attention_modules(model):

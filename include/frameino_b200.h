@@ -212,6 +212,15 @@ int fino_qkv_norm_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride
                                void* const* dst_ptrs, int world, int rank, int64_t rows_per_rank,
                                int64_t dst_row_stride, void* stream);
 
+/* The CogVideoX form of the fused first all-to-all: per-head LayerNorm(64) with affine (attention_processor.py:2848-2851)
+ * and the CogVideoX RoPE on local rows >= rope_skip (the text rows are not rotated, :2858-2860; cos/sin are the float
+ * [rows - rope_skip, 64] table rows of the LOCAL video tokens) of qkv[rows, row_stride] (q | k | v), stored into the
+ * owning ranks' buffers exactly as fino_qkv_norm_rope_scatter lays them out. head_dim must be 64. */
+int fino_qkv_ln_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride, const void* wq, const void* bq,
+                             const void* wk, const void* bk, int heads, int head_dim, float eps, const float* cos,
+                             const float* sin, int64_t rope_skip, void* const* dst_ptrs, int world, int rank,
+                             int64_t rows_per_rank, int64_t dst_row_stride, void* stream);
+
 /* fino_attention_fwd whose epilogue is the second all-to-all: query row g is stored into
  * o_owners[g / rows_per_owner] at local row g % rows_per_owner (row stride o_row_stride; pass the column offset of
  * this rank's heads in each pointer). o_owners: HOST array of num_owners (<= 8) device pointers. */

@@ -118,6 +118,76 @@ def _run_fused_exchange(ops, world, n_total, heads, hd, tma):
             ops.peer_free(b)
 
 
+@pytest.mark.parametrize("world,n_total,heads,text_len,batch", [(2, 530, 4, 10, 2), (4, 777, 8, 190, 1), (8, 1001, 48, 100, 2),
+                                                                (1, 300, 4, 0, 1)])
+def test_fused_exchange_cogvideox_matches_unsharded(ops, world, n_total, heads, text_len, batch):
+    """The CogVideoX prologue (per-head LayerNorm(64) + RoPE on the video rows of the JOINT sequence) fused with the
+    first exchange, batch slots of the exchange buffer, then the attention + second exchange; against the un-sharded
+    kernels on the same data."""
+    from frameino_b200.ulysses import SequenceParallel, exchange_layout
+
+    hd = 64
+    d = heads * hd
+    g = torch.Generator().manual_seed(3)
+    qkv = (torch.randn(batch, n_total, 3 * d, generator=g) * 1.5).bfloat16().cuda()
+    wq, bq, wk, bk = ((1 + 0.1 * torch.randn(hd, generator=g)).bfloat16().cuda() for _ in range(4))
+    ang = torch.rand(n_total - text_len, hd // 2, generator=g) * 6.28
+    cos = ang.cos().repeat_interleave(2, 1).contiguous().cuda()
+    sin = ang.sin().repeat_interleave(2, 1).contiguous().cuda()
+    ops.attention_set_split(0)
+    try:
+        ref_qkv = qkv.clone()
+        ops.qk_norm_rope(ref_qkv[..., :d], wq, ref_qkv[..., d:2 * d], wk, heads, b0=bq, b1=bk,
+                         norm_mode=ops.QK_LAYERNORM_PER_HEAD, eps=1e-6, rope_mode=ops.ROPE_COGVIDEOX, cos=cos, sin=sin,
+                         seq_len=n_total, rope_skip=text_len)
+        ref = ops.attention(ref_qkv[..., :d], ref_qkv[..., d:2 * d], ref_qkv[..., 2 * d:], heads)
+        n_loc, n_pad = SequenceParallel.partition(n_total, world)
+        assert text_len <= n_loc
+        lays = [exchange_layout(world, r, n_loc, d, batch=batch) for r in range(world)]
+        bases = [ops.peer_alloc(lays[0]["total_bytes"]) for _ in range(world)]
+        try:
+            inner = lays[0]["inner"]
+            qb, ob = lays[0]["qkv_batch_bytes"], lays[0]["o_batch_bytes"]
+            for bi in range(batch):
+                qkv_ptrs = ops.pointer_table([b + lays[0]["qkv_off"] + bi * qb for b in bases])
+                for r in range(world):
+                    lo, hi = r * n_loc, min((r + 1) * n_loc, n_total)
+                    skip = text_len if r == 0 else 0
+                    local = torch.zeros(n_loc, 3 * d, dtype=torch.bfloat16, device="cuda")
+                    lcos = torch.zeros(n_loc - skip, hd, device="cuda")
+                    lsin = torch.zeros(n_loc - skip, hd, device="cuda")
+                    if hi > lo:
+                        local[: hi - lo] = qkv[bi, lo:hi]
+                        v0 = lo + skip - text_len  # first video row of this rank
+                        lcos[: hi - lo - skip] = cos[v0:v0 + hi - lo - skip]
+                        lsin[: hi - lo - skip] = sin[v0:v0 + hi - lo - skip]
+                    ops.qkv_ln_rope_scatter(local, wq, bq, wk, bk, heads, 1e-6, lcos, lsin, skip, qkv_ptrs, world, r, n_loc,
+                                            lays[r]["qkv_row_stride"])
+                for r in range(world):
+                    got = ops.tensor_from_ptr(bases[r] + lays[r]["qkv_off"] + bi * qb, (1, n_pad, 3 * inner))[:, :n_total]
+                    for part in range(3):
+                        want = ref_qkv[bi:bi + 1, :, part * d + r * inner: part * d + (r + 1) * inner]
+                        assert _same(got[..., part * inner:(part + 1) * inner], want, part == 2), (bi, r, part)
+                for r in range(world):
+                    full = ops.tensor_from_ptr(bases[r] + lays[r]["qkv_off"] + bi * qb, (1, n_pad, 3 * inner))[:, :n_total]
+                    o_ptrs = ops.pointer_table([b + lays[r]["o_off"] + bi * ob + lays[r]["o_col_offset"] for b in bases])
+                    ops.attention_scatter(full[..., :inner], full[..., inner:2 * inner], full[..., 2 * inner:],
+                                          heads // world, o_ptrs, world, n_loc, lays[r]["o_row_stride"])
+            torch.cuda.synchronize()
+            for bi in range(batch):
+                for r in range(world):
+                    lo, hi = r * n_loc, min((r + 1) * n_loc, n_total)
+                    o_loc = ops.tensor_from_ptr(bases[r] + lays[r]["o_off"] + bi * ob, (1, n_loc, d))
+                    if hi > lo:
+                        assert _same(o_loc[:, : hi - lo], ref[bi:bi + 1, lo:hi], False), (bi, r)
+        finally:
+            torch.cuda.synchronize()
+            for b in bases:
+                ops.peer_free(b)
+    finally:
+        ops.attention_set_split(-1)
+
+
 def test_ipc_export_import_roundtrip_same_process(ops):
     """cudaIpcGetMemHandle works on a peer_alloc buffer (opening it needs a second process: covered by
     tools/sp_check.py on a multi-GPU box)."""

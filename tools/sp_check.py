@@ -26,7 +26,7 @@ def main():
 
 
 def run_cog_cases():
-    """CogVideoX (joint text + video sequence, batch 2 = the pipeline's batched CFG) under mode='nccl'."""
+    """CogVideoX (joint text + video sequence, batch 2 = the pipeline's batched CFG), NCCL and fused peer exchange."""
     from frameino_b200.cogvideox import CogVideoXTransformer3DModel
 
     rank, world = dist.get_rank(), dist.get_world_size()
@@ -44,17 +44,18 @@ def run_cog_cases():
         args = dict(hidden_states=hidden.cuda(), encoder_hidden_states=text.cuda(), timestep=ts.cuda(),
                     image_rotary_emb=(cos, sin), return_dict=False)
         ref = model(**args)[0]
-        enable_sequence_parallel(model, mode="nccl")
-        out = model(**args)[0]
-        out2 = model(**args)[0]
-        assert torch.equal(out, out2), "sequence-parallel forward is not repeatable"
-        disable_sequence_parallel(model)
-        torch.cuda.synchronize()
-        err = float((out.float() - ref.float()).abs().max() / ref.float().abs().max())
-        errs = [None] * world
-        dist.all_gather_object(errs, err)
-        results[f"cog/{name}"] = {"tokens": text.shape[1] + (f + 1) * (h // 2) * (w // 2), "batch": batch,
-                                  "rel_err_per_rank": errs}
+        for mode in ("nccl", "peer"):
+            enable_sequence_parallel(model, mode=mode)
+            out = model(**args)[0]
+            out2 = model(**args)[0]
+            assert torch.equal(out, out2), "sequence-parallel forward is not repeatable"
+            disable_sequence_parallel(model)
+            torch.cuda.synchronize()
+            err = float((out.float() - ref.float()).abs().max() / ref.float().abs().max())
+            errs = [None] * world
+            dist.all_gather_object(errs, err)
+            results[f"cog/{mode}/{name}"] = {"tokens": text.shape[1] + (f + 1) * (h // 2) * (w // 2), "batch": batch,
+                                             "rel_err_per_rank": errs}
     if rank == 0:
         print("SP_CHECK " + json.dumps(results))
         ok = all(e <= 2e-2 for r in results.values() for e in r["rel_err_per_rank"])
