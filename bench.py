@@ -375,8 +375,8 @@ def run_secondary(args, world, rank, dev, wan_model, barrier):
             "config": {"workload": f"Wan2.2-TI2V-5B FrameINO one denoise-step forward, 832x1536x121 + 1 ID frame, {tokens} "
                                    f"tokens, B=1, ulysses x{world} ({args.sp_mode})"}}
         del d5, y
-    # config 3 (sequence-parallel CogVideoX only when asked for: --cog-sp)
-    if world > 1 and not args.cog_sp:
+    # config 3 (sequence-parallel when N > 1; --no-cog-sp skips it there)
+    if world > 1 and args.no_cog_sp:
         return out
     try:
         cfg = synth.COG_5B_I2V
@@ -490,10 +490,14 @@ def run_native(args, lat_f, h, w, tokens):
                 model.sequence_parallel._attention_scatter = timed_attention_scatter
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = ops.launch_count()
+        if instrument:
+            torch.cuda.nvtx.range_push("fino_timed")  # ncu --nvtx --nvtx-include "fino_timed/": the launch list of the steps
         s.record()
         for _ in range(steps):
             fn()
         e.record()
+        if instrument:
+            torch.cuda.nvtx.range_pop()
         barrier()
         ops.attention = real_attention
         if model.sequence_parallel is not None:
@@ -609,8 +613,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (cpu_baseline + parity)")
     ap.add_argument("--no-secondary", action="store_true",
                     help="skip the secondary workloads (config 3 CogVideoX B=2; at N=8 config 5, 39936 tokens)")
-    ap.add_argument("--cog-sp", action="store_true", help="N > 1: also run the CogVideoX secondary sequence-parallel")
-    ap.add_argument("--cog-sp-mode", default="nccl", choices=["peer", "nccl"], help="N > 1: exchange of the CogVideoX secondary")
+    ap.add_argument("--cog-sp", action="store_true", help="(default now; kept for old command lines)")
+    ap.add_argument("--no-cog-sp", action="store_true", help="N > 1: skip the sequence-parallel CogVideoX secondary")
+    ap.add_argument("--cog-sp-mode", default="peer", choices=["peer", "nccl"], help="N > 1: exchange of the CogVideoX secondary")
     ap.add_argument("--sp-mode", default="peer", choices=["peer", "nccl"],
                     help="N > 1: Ulysses exchange fused over NVLink peer memory (default) or NCCL all_to_all_single")
     args = ap.parse_args()
