@@ -630,28 +630,10 @@ __global__ void __launch_bounds__(256) attn_combine_kernel(const __grid_constant
   }
 }
 
-// Per-device workspace for the KV-split partials (grown on demand; <= 148 CTAs x 256 rows x (HD*4 + 8) B = 19.7 MB in
-// the automatic mode). Calls on one device are assumed stream-ordered with each other (the reference convention: one
-// stream per process), since consecutive launches reuse the same workspace.
-static void* g_attn_ws[16] = {};
-static size_t g_attn_ws_bytes[16] = {};
-static int attn_workspace(size_t bytes, void** out) {
-  int dev = 0;
-  FINO_CHECK_CUDA(cudaGetDevice(&dev));
-  FINO_CHECK_ARG(dev >= 0 && dev < 16, "attention: device index %d out of range", dev);
-  if (g_attn_ws_bytes[dev] < bytes) {
-    if (g_attn_ws[dev]) {
-      FINO_CHECK_CUDA(cudaDeviceSynchronize());
-      FINO_CHECK_CUDA(cudaFree(g_attn_ws[dev]));
-      g_attn_ws[dev] = nullptr;
-      g_attn_ws_bytes[dev] = 0;
-    }
-    size_t want = bytes < ((size_t)20 << 20) ? ((size_t)20 << 20) : bytes;
-    FINO_CHECK_CUDA(cudaMalloc(&g_attn_ws[dev], want));
-    g_attn_ws_bytes[dev] = want;
-  }
-  *out = g_attn_ws[dev];
-  return FINO_OK;
+// Workspace for the KV-split partials (grown on demand; <= 148 CTAs x 256 rows x (HD*4 + 8) B = 19.7 MB in the
+// automatic mode), one per (device, stream): consecutive launches on a stream reuse it in stream order.
+static int attn_workspace(size_t bytes, cudaStream_t stream, void** out) {
+  return stream_workspace(/*tag=*/2, stream, bytes, out);
 }
 
 template <int HD, int EMU, bool SPLIT, bool PSEP = false, int EMU_B = EMU, bool PING = false>
@@ -1217,7 +1199,7 @@ int attention_fwd_owners(const void* q, const void* k, const void* v, void* cons
   if (p.splits > 1) {
     const size_t prow = (size_t)(n_tiles - p.n_full) * p.splits * tile_rows;
     void* ws = nullptr;
-    if ((r = attn_workspace(prow * ((size_t)head_dim * 4 + 8), &ws))) return r;
+    if ((r = attn_workspace(prow * ((size_t)head_dim * 4 + 8), stream, &ws))) return r;
     p.ws_o = reinterpret_cast<float*>(ws);
     p.ws_ml = reinterpret_cast<float2*>(p.ws_o + prow * head_dim);
   }

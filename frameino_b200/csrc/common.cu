@@ -1,5 +1,6 @@
 #include "common.cuh"
 #include <stdarg.h>
+#include <mutex>
 
 namespace fino {
 
@@ -67,6 +68,43 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
                    rank > 1 ? box[1] : 0);
     return FINO_ERR_CUDA;
   }
+  return FINO_OK;
+}
+
+struct WsEntry {
+  int dev, tag;
+  cudaStream_t stream;
+  void* ptr;
+  size_t bytes;
+};
+static WsEntry g_ws[64];
+static int g_ws_n = 0;
+static std::mutex g_ws_mu;
+
+int stream_workspace(int tag, cudaStream_t stream, size_t bytes, void** out) {
+  std::lock_guard<std::mutex> lock(g_ws_mu);
+  int dev = 0;
+  FINO_CHECK_CUDA(cudaGetDevice(&dev));
+  WsEntry* e = nullptr;
+  for (int i = 0; i < g_ws_n; ++i)
+    if (g_ws[i].dev == dev && g_ws[i].tag == tag && g_ws[i].stream == stream) e = &g_ws[i];
+  if (e == nullptr) {
+    FINO_CHECK_ARG(g_ws_n < 64, "stream_workspace: more than 64 (device, stream, kind) combinations in use");
+    e = &g_ws[g_ws_n++];
+    *e = WsEntry{dev, tag, stream, nullptr, 0};
+  }
+  if (e->bytes < bytes) {
+    if (e->ptr) {
+      FINO_CHECK_CUDA(cudaStreamSynchronize(stream));  // earlier launches on this stream may still read the old block
+      FINO_CHECK_CUDA(cudaFree(e->ptr));
+      e->ptr = nullptr;
+      e->bytes = 0;
+    }
+    const size_t want = bytes < ((size_t)20 << 20) ? ((size_t)20 << 20) : bytes;
+    FINO_CHECK_CUDA(cudaMalloc(&e->ptr, want));
+    e->bytes = want;
+  }
+  *out = e->ptr;
   return FINO_OK;
 }
 

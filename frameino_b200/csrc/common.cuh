@@ -43,6 +43,11 @@ const char* get_last_error();
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                      const uint32_t* box, const uint32_t* elem_strides = nullptr);
 
+// Library-owned scratch memory keyed by (current device, stream, tag): grown on demand, never shared between streams, so
+// launches that use it on different streams (e.g. the side stream of prepare_text) cannot race on it. Launches on ONE
+// stream reuse the same block (stream order protects it).
+int stream_workspace(int tag, cudaStream_t stream, size_t bytes, void** out);
+
 int num_sms();         // SM count of the CURRENT device (cached per device)
 int current_device();  // cudaGetDevice
 

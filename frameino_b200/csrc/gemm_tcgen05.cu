@@ -486,27 +486,12 @@ __global__ void __launch_bounds__(256) gemm_fixup_kernel(const GemmParams p) {
   epilogue_group8<EPI>(p, row, col, v, p.bias ? p.bias + col : nullptr, gate_row != nullptr, g0, g1, x);
 }
 
-// Per-device workspace for the K-slices (<= 74 clusters x 256 x 256 fp32 = 19.4 MB; grown on demand). Calls on one
-// device are assumed stream-ordered with each other, like the attention workspace.
-static void* g_gemm_ws[16] = {};
-static size_t g_gemm_ws_bytes[16] = {};
-static int gemm_workspace(size_t bytes, float** out) {
-  int dev = 0;
-  FINO_CHECK_CUDA(cudaGetDevice(&dev));
-  FINO_CHECK_ARG(dev >= 0 && dev < 16, "gemm: device index %d out of range", dev);
-  if (g_gemm_ws_bytes[dev] < bytes) {
-    if (g_gemm_ws[dev]) {
-      FINO_CHECK_CUDA(cudaDeviceSynchronize());
-      FINO_CHECK_CUDA(cudaFree(g_gemm_ws[dev]));
-      g_gemm_ws[dev] = nullptr;
-      g_gemm_ws_bytes[dev] = 0;
-    }
-    const size_t want = bytes < ((size_t)20 << 20) ? ((size_t)20 << 20) : bytes;
-    FINO_CHECK_CUDA(cudaMalloc(&g_gemm_ws[dev], want));
-    g_gemm_ws_bytes[dev] = want;
-  }
-  *out = reinterpret_cast<float*>(g_gemm_ws[dev]);
-  return FINO_OK;
+// Workspace for the K-slices (<= 74 clusters x 256 x 256 fp32 = 19.4 MB; grown on demand), one per (device, stream).
+static int gemm_workspace(size_t bytes, cudaStream_t stream, float** out) {
+  void* p = nullptr;
+  int r = stream_workspace(/*tag=*/1, stream, bytes, &p);
+  *out = reinterpret_cast<float*>(p);
+  return r;
 }
 
 // Split-K plan of the pair kernel (see GemmParams): tiles of 256 x 256 on `clusters` CTA pairs, num_kb K-blocks.
@@ -647,7 +632,7 @@ int gemm_bf16(const void* a, int64_t lda, const void* w, int64_t ldw, const void
     gemm_plan(tiles, (k + GEMM_BK - 1) / GEMM_BK, num_sms() / 2, g_gemm_split, &p.num_full, &p.splits);
     if (p.splits > 1) {
       const size_t bytes = (size_t)(tiles - p.num_full) * p.splits * 256 * 256 * sizeof(float);
-      int r = gemm_workspace(bytes, &p.ws);
+      int r = gemm_workspace(bytes, stream, &p.ws);
       if (r) return r;
     }
   }

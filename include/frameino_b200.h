@@ -55,8 +55,8 @@ int fino_gemm_set_mode(int mode);
  * leaves a partly filled last round (8-way Ulysses: M = 3520, N = 3072 -> 168 tiles on 74 pairs = 2.27 rounds), the
  * tiles of that round are split along K into `splits` slices each (raw fp32 partials in a library-owned per-device
  * workspace; a small second kernel adds the slices and applies the fused epilogue). mode: -1 = automatic (default),
- * 0 = never, 2..16 = split the whole last round that many ways (test hook). Calls on one device must be
- * stream-ordered with each other. */
+ * 0 = never, 2..16 = split the whole last round that many ways (test hook). The workspace is per (device, stream):
+ * calls on different streams do not share it. */
 int fino_gemm_set_split(int mode);
 /* The decomposition fino_gemm_bf16 would use for an m x n x k problem on a device with `sms` SMs (host arithmetic). */
 int fino_gemm_plan(int64_t m, int n, int k, int sms, int mode, int* num_full, int* splits);
@@ -69,14 +69,15 @@ int fino_attention_fwd(const void* q, const void* k, const void* v, void* o, int
                        int64_t o_row_stride, int64_t q_batch_stride, int64_t k_batch_stride, int64_t v_batch_stride,
                        int64_t o_batch_stride, float scale, void* stream);
 
-/* Tuning / test hook: scheduling variant of the attention kernel (0 = default; 1..9 see attention_tcgen05.cu; 6..9 apply to head_dim 64 only). */
+/* Tuning / test hook: scheduling variant of the attention kernel (0 = default; 1..15 see attention_tcgen05.cu; 6..15
+ * apply to head_dim 64 only). */
 int fino_attention_set_variant(int variant);
 
 /* Work decomposition of fino_attention_fwd. The kernel runs one CTA per 256-query-row tile of one (batch, head); when
  * the tile count leaves a partly filled last wave on the device's SMs (8-way Ulysses: 3 heads x 110 tiles = 330 CTAs on
  * 148 SMs), the tiles of that wave are split along the key axis into `splits` partial CTAs each (fp32 partials in a
  * library-owned per-device workspace, merged by a small second kernel). mode: -1 = automatic (default), 0 = never,
- * 2..64 = split EVERY tile that many ways (test hook). Calls on one device must be stream-ordered with each other. */
+ * 2..64 = split EVERY tile that many ways (test hook). The workspace is per (device, stream). */
 int fino_attention_set_split(int mode);
 /* The decomposition fino_attention_fwd would use on a device with `sms` SMs (pure host arithmetic; no GPU needed):
  * CTAs [0, n_full) run whole tiles, the remaining tiles run as `splits` partial CTAs each. */
