@@ -187,3 +187,105 @@ def test_exchange_layout_arithmetic():
             # everything but the column offset is identical on every rank (peers index each other's buffers with it)
             assert {k: v for k, v in lay.items() if k != "o_col_offset"} == \
                    {k: v for k, v in lays[0].items() if k != "o_col_offset"}
+
+
+# ---- CogVideoX form: per-head LayerNorm prologue, batched-CFG pair through one exchange (one slot per sample) --------
+def _ln64(x, w, b, heads, eps=1e-6):
+    n, d = x.shape
+    y = torch.nn.functional.layer_norm(x.float().view(n, heads, 64), (64,), w.float(), b.float(), eps)
+    return y.view(n, d).bfloat16()
+
+
+def _cog_worker(rank, world, port, n_total, heads, batch, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from frameino_b200.ulysses import SequenceParallel
+
+        prims = ShmPrims()
+        sp = SequenceParallel(mode="peer")
+        sp._prims = prims
+        d_model = heads * 64
+
+        def ln_scatter(qkv, wq, bq, wk, bk, heads_, eps, cos, sin, rope_skip, dst_ptrs, world_, rank_, rows_per_rank,
+                       dst_row_stride):
+            # what fino_qkv_ln_rope_scatter does (no RoPE in this host-logic test); qkv: [n_loc, 3*D]
+            n_loc = qkv.shape[0]
+            inner = d_model // world_
+            q = _ln64(qkv[:, :d_model], wq, bq, heads_, eps)
+            k = _ln64(qkv[:, d_model:2 * d_model], wk, bk, heads_, eps)
+            v = qkv[:, 2 * d_model:]
+            for g in range(world_):
+                dst = prims.tensor_from_ptr(dst_ptrs[g], (world_ * rows_per_rank, dst_row_stride))
+                rows = slice(rank_ * rows_per_rank, rank_ * rows_per_rank + n_loc)
+                for part, src in enumerate((q, k, v)):
+                    dst[rows, part * inner:(part + 1) * inner] = src[:, g * inner:(g + 1) * inner]
+
+        def attention_scatter(q, k, v, heads_, o_ptrs, num_owners, rows_per_owner, o_row_stride, scale):
+            o = _torch_attention(q, k, v, heads_, scale)[0]
+            inner = o.shape[1]
+            for g in range(num_owners):
+                lo, hi = g * rows_per_owner, min((g + 1) * rows_per_owner, o.shape[0])
+                if hi <= lo:
+                    continue
+                flat = prims.tensor_from_ptr(o_ptrs[g], ((rows_per_owner - 1) * o_row_stride + inner,))
+                flat.as_strided((hi - lo, inner), (o_row_stride, 1)).copy_(o[lo:hi])
+
+        sp._qkv_ln_scatter = ln_scatter
+        sp._attention_scatter = attention_scatter
+        sp.plan(n_total)
+        g = torch.Generator().manual_seed(1)
+        qkv_full = torch.randn(batch, n_total, 3 * d_model, generator=g).bfloat16()
+
+        class Norm:
+            pass
+
+        nq, nk = Norm(), Norm()
+        nq.weight, nq.bias = (1 + 0.1 * torch.randn(64, generator=g)).bfloat16(), (0.1 * torch.randn(64, generator=g)).bfloat16()
+        nk.weight, nk.bias = (1 + 0.1 * torch.randn(64, generator=g)).bfloat16(), (0.1 * torch.randn(64, generator=g)).bfloat16()
+        refs = []
+        for b in range(batch):
+            qn = _ln64(qkv_full[b, :, :d_model], nq.weight, nq.bias, heads)
+            kn = _ln64(qkv_full[b, :, d_model:2 * d_model], nk.weight, nk.bias, heads)
+            refs.append(_torch_attention(qn[None], kn[None], qkv_full[b:b + 1, :, 2 * d_model:], heads, 0.125))
+        ref = torch.cat(refs, dim=0)
+        local = sp.shard_rows(qkv_full)
+        errs = []
+        for _ in range(2):
+            out = sp.fused_attention_ln(local, nq, nk, heads, 1e-6, None, None, 0, 0.125)
+            assert out.shape == (batch, sp.n_loc, d_model)
+            sl = sp.local_slice()
+            n_real = max(sl.stop - sl.start, 0)
+            errs.append(float((out[:, :n_real].float() - ref[:, sl].float()).abs().max()) if n_real else 0.0)
+        ex = sp.exchange(sp.n_loc, d_model, batch=batch)
+        ret[rank] = (max(errs), ex.epoch, ex.layout["batch"], len(ex.qkv_ptrs_b))
+        sp.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_total,heads,batch", [(2, 41, 2, 2), (4, 30, 4, 1)])
+def test_fused_exchange_cogvideox_host_logic(world, n_total, heads, batch):
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_cog_worker, args=(world, port, n_total, heads, batch, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for rank in range(world):
+        err, epoch, lay_batch, slots = ret[rank]
+        assert err == 0.0, (rank, err)
+        assert epoch == 4  # two barriers per call, whatever the batch
+        assert lay_batch == batch and slots == batch
+
+
+def test_exchange_layout_batch_slots():
+    from frameino_b200.ulysses import exchange_layout
+
+    one = exchange_layout(8, 3, 2391, 3072)
+    two = exchange_layout(8, 3, 2391, 3072, batch=2)
+    assert two["qkv_off"] == one["qkv_off"] and two["qkv_batch_bytes"] == one["qkv_batch_bytes"]
+    assert two["qkv_batch_bytes"] % 256 == 0 and two["o_batch_bytes"] % 256 == 0
+    assert two["o_off"] == 256 + 2 * two["qkv_batch_bytes"]
+    assert two["total_bytes"] == two["o_off"] + 2 * two["o_batch_bytes"]
+    assert two["qkv_batch_bytes"] >= 8 * 2391 * 3 * 384 * 2 and two["o_batch_bytes"] >= 2391 * 3072 * 2
