@@ -85,7 +85,9 @@ int wan_pack_model_input(const float* latents, const float* condition, const flo
   return FINO_OK;
 }
 
-// latents[b,c,f,h,w] += dsigma * (u + guidance * (v - u)), v/u = proj_out rows of the cond / uncond forwards with the
+// latents[b,c,f,h,w] += dsigma * cfg, cfg = u + guidance * (v - u) evaluated IN BF16 like the reference (the pipeline
+// combines the two bf16 forward outputs with tensor ops, pipeline_wan_i2v_motion_FrameINO.py:882: three roundings —
+// the difference, its product with the scalar, the sum); v/u = proj_out rows of the cond / uncond forwards with the
 // (pt, ph, pw, c) column order of transformer_wan.py:539-543; rows of the ID frames (f >= F) are never read.
 __global__ void __launch_bounds__(256)
 wan_cfg_euler_step_kernel(const __nv_bfloat16* __restrict__ y_cond, const __nv_bfloat16* __restrict__ y_uncond,
@@ -110,7 +112,9 @@ wan_cfg_euler_step_kernel(const __nv_bfloat16* __restrict__ y_cond, const __nv_b
     float v = __bfloat162float(y_cond[tok * ld + k]);
     if (y_uncond != nullptr) {
       const float u = __bfloat162float(y_uncond[tok * ld + k]);
-      v = __fadd_rn(u, __fmul_rn(guidance, __fsub_rn(v, u)));
+      const float d = __bfloat162float(__float2bfloat16_rn(__fsub_rn(v, u)));
+      const float m = __bfloat162float(__float2bfloat16_rn(__fmul_rn(guidance, d)));
+      v = __bfloat162float(__float2bfloat16_rn(__fadd_rn(u, m)));
     }
     latents[idx] = __fadd_rn(latents[idx], __fmul_rn(dsigma, v));
   }

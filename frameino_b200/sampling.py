@@ -15,7 +15,11 @@ This is the CALLER of the hot path (SURVEY.md §8f "next" #1), in two forms:
   there is no host synchronisation inside the loop. Same arithmetic, bit for bit, as the plain form.
 
 The scheduler is flow-match Euler with shift 5.0 (config/train_wan_motion_FrameINO.yaml:43-50) — the stepper is not
-the thing under test.
+the thing under test, and it is NOT claimed bit-comparable with a diffusers scheduler object: the scheduler classes are
+upstream-only (the checkpoint ships UniPC; the pipeline type-hints FlowMatchEulerDiscreteScheduler), and upstream's
+Euler step — recalled — multiplies in the model-output dtype and casts the new sample back to it every step, whereas
+this loop keeps the latents and the step in fp32 and applies the static shift once. Everything the reference pipeline
+FILE does around the scheduler call is reproduced with its cast points, including the guidance combine in bf16 (:882).
 """
 from __future__ import annotations
 
@@ -67,13 +71,13 @@ def wan_frameino_denoise(
             mine = prompt_embeds if cfg_parallel.branch == 0 else negative_prompt_embeds
             v, vu = cfg_parallel.exchange(
                 transformer(hidden_states=x_in, timestep=ts, encoder_hidden_states=mine, return_dict=False)[0])
-            v = vu.float() + guidance_scale * (v.float() - vu.float())  # :882
+            v = vu + guidance_scale * (v - vu)  # :882, in the transformer dtype like the reference
         else:
             v = transformer(hidden_states=x_in, timestep=ts, encoder_hidden_states=prompt_embeds, return_dict=False)[0]
         if do_cfg and cfg_parallel is None:
             vu = transformer(hidden_states=x_in, timestep=ts, encoder_hidden_states=negative_prompt_embeds,
                              return_dict=False)[0]
-            v = vu.float() + guidance_scale * (v.float() - vu.float())  # :882
+            v = vu + guidance_scale * (v - vu)  # :882, in the transformer dtype (bf16 tensor ops) like the reference
         v = v[:, :, :n_gen].float()  # :886 drop the ID frames
         latents = latents + (sigmas[i + 1] - sigmas[i]) * v  # :891 Euler
     return latents

@@ -171,7 +171,8 @@ int fino_wan_pack_model_input(const float* latents, const float* condition, cons
                               const float* id_latents, const float* traj_latents, void* rows, int b, int c, int f,
                               int n_id, int h, int w, int pt, int ph, int pw, int64_t ld, void* stream);
 
-/* latents += dsigma * (y_uncond + guidance * (y_cond - y_uncond)) over the f generated frames, reading the bf16
+/* latents += dsigma * (y_uncond + guidance * (y_cond - y_uncond)) — the guidance combine evaluated in bf16 with the
+ * reference's three roundings (it combines the bf16 forward outputs with tensor ops), the step in fp32 — over the f generated frames, reading the bf16
  * proj_out rows [(b, (f+n_id)/pt, h/ph, w/pw), (pt, ph, pw, c)] of the two forwards (row stride ld): classifier-free
  * guidance :882, ID-frame drop :886, flow-match Euler scheduler step :891, fused with the un-patchify of
  * transformer_wan.py:539-543. y_uncond may be NULL (no guidance). fp32, no FMA contraction. */

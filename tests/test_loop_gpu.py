@@ -76,7 +76,7 @@ def test_cfg_euler_step_is_the_reference_chain_bit_for_bit(b, c, f, h, w, n_id, 
     y_c = torch.randn(b * tokens, 4 * c, generator=g).bfloat16()
     y_u = torch.randn(b * tokens, 4 * c, generator=g).bfloat16()
     lat = torch.randn(b, c, f, h, w, generator=g)
-    guidance, dsigma = 5.0, -0.0371
+    guidance, dsigma = 4.3, -0.0371
 
     def unpatch(y):  # :539-543
         t = y.view(b, ft, h // 2, w // 2, 1, 2, 2, c).permute(0, 7, 1, 4, 2, 5, 3, 6)
@@ -85,7 +85,7 @@ def test_cfg_euler_step_is_the_reference_chain_bit_for_bit(b, c, f, h, w, n_id, 
     v = unpatch(y_c)
     if cfg_on:
         vu = unpatch(y_u)
-        v = vu.float() + guidance * (v.float() - vu.float())
+        v = (vu + guidance * (v - vu)).float()  # :882 on the bf16 outputs
     v = v[:, :, :f].float()
     want = lat + torch.tensor(dsigma, dtype=torch.float32) * v
     got = ops.wan_cfg_euler_step(lat.cuda().clone(), y_c.cuda(), y_u.cuda() if cfg_on else None, n_id, (1, 2, 2),
