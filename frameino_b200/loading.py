@@ -140,7 +140,8 @@ def from_pretrained(model_cls, path: str, subfolder: Optional[str] = None,
 
     from .modules import compute_dtype
 
-    torch_dtype = compute_dtype(torch_dtype)  # float16 (reference app.py:156) -> bf16 with a warning; fp32 refused
+    if not getattr(model_cls, "_stores_any_dtype", False):  # the VAE keeps its checkpoint dtype (fp32, app.py:157)
+        torch_dtype = compute_dtype(torch_dtype)  # float16 (reference app.py:156) -> bf16 with a warning; fp32 refused
 
     accepted = set(inspect.signature(model_cls.__init__).parameters) - {"self"}
     dropped = sorted(k for k in cfg if k not in accepted)

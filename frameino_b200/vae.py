@@ -243,6 +243,8 @@ class AutoencoderKLWan(ModelBase):
     """Drop-in for reference ``architecture.autoencoder_kl_wan.AutoencoderKLWan`` (see the module docstring)."""
 
     _supports_gradient_checkpointing = False
+    _stores_any_dtype = True  # parameters keep the requested dtype (the reference loads the VAE in fp32, app.py:157);
+                              # the kernels read bf16 copies packed by prepare()
 
     def __init__(self, base_dim: int = 96, decoder_base_dim: Optional[int] = None, z_dim: int = 16,
                  dim_mult=(1, 2, 4, 4), num_res_blocks: int = 2, attn_scales=(), temperal_downsample=(False, True, True),

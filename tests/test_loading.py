@@ -128,3 +128,41 @@ def test_from_pretrained_on_gpu_matches_explicit_load(tmp_path):
     hidden, ts, text = synth.make_wan_inputs(cfg, 3, 16, 16, n_id=1, text_len=16, text_true_len=11, dtype=torch.bfloat16)
     args = dict(hidden_states=hidden.cuda(), timestep=ts.cuda(), encoder_hidden_states=text.cuda(), return_dict=False)
     assert torch.equal(model(**args)[0], ref(**args)[0])
+
+
+def test_vae_from_pretrained_keeps_fp32_and_packs_bf16(tmp_path):
+    """The reference loads its VAE with torch_dtype=float32 (app.py:157): parameters stay fp32 under the diffusers key
+    names, the packed bf16 conv weights the kernels read are derived (tap-major, channels padded to 64 per tap)."""
+    from safetensors.torch import save_file
+
+    from frameino_b200.vae import AutoencoderKLWan, ConvParams
+
+    cfg = dict(synth.VAE_TINY)
+    sd = synth.make_vae_state_dict(cfg, seed=0)
+    d = tmp_path / "vae"
+    d.mkdir()
+    meta = {"_class_name": "AutoencoderKLWan", "latents_mean": [0.0] * 16, "latents_std": [1.0] * 16}
+    meta.update(cfg)
+    (d / "config.json").write_text(json.dumps(meta))
+    save_file({k: v.contiguous() for k, v in sd.items()}, str(d / loading.WEIGHTS_NAME))
+    vae = AutoencoderKLWan.from_pretrained(str(tmp_path), subfolder="vae", torch_dtype=torch.float32, device="cpu")
+    assert vae.dtype == torch.float32 and vae.config.z_dim == 16 and vae.config.latents_std == [1.0] * 16
+    got = vae.state_dict()
+    assert set(got) == set(sd)
+    for k, v in sd.items():
+        assert got[k].dtype == torch.float32 and torch.equal(got[k], v), k
+    conv = vae.decoder.up_blocks[2].resnets[0].conv1  # 256 -> 128 at the tiny widths
+    wp, bp = conv.packed()
+    assert isinstance(conv, ConvParams) and wp.dtype == torch.bfloat16 and wp.shape == (128, 27 * 256)
+    w = conv.weight.detach()
+    assert torch.equal(wp.view(128, 27, 256)[:, 13, :], w[:, :, 1, 1, 1].to(torch.bfloat16))  # centre tap
+    c_in = vae.decoder.conv_in  # z 16 -> 256: channels padded 16 -> 64 per tap with zeros
+    wp, _ = c_in.packed()
+    assert wp.shape == (256, 27 * 64) and float(wp.view(256, 27, 64)[:, :, 16:].abs().max()) == 0.0
+    c_out = vae.decoder.conv_out  # 64 -> 12: output rows padded 12 -> 16
+    wp, bp = c_out.packed()
+    assert wp.shape[0] == 16 and float(wp[12:].abs().max()) == 0.0 and float(bp[12:].abs().max()) == 0.0
+    with pytest.raises(NotImplementedError):
+        AutoencoderKLWan(**{**cfg, "is_residual": False})
+    with pytest.raises(RuntimeError):
+        vae.decode(torch.zeros(1, 16, 1, 4, 6))  # no CPU path
