@@ -183,33 +183,49 @@ class Decoder3d(nn.Module):  # :783-909
 
 # ---- run-time state: the causal history of every convolution (the reference's feat_cache) ---------------------------
 class _ConvCaches:
-    """Per-convolution input buffers ``[hist + t, H, W, C]``: frames [0, hist) are the cached history (zeros before the
-    first chunk), frames [hist, hist + t) are written by the producer of the convolution's input."""
+    """Per-convolution input buffers: a strip of frames ``[capacity, H, W, C]`` in which every chunk's input is written
+    right behind the previous chunk's, so the last ``hist`` frames of the previous chunk ARE the causal history of the
+    next one (the reference's ``feat_cache``, :360-367) without moving them; only when the strip is full are the last
+    ``hist`` frames copied back to its start (every ``ROOM`` chunks). Frames before the first chunk are zeros."""
+
+    ROOM = 4  # chunks of the current length a strip holds before it wraps
 
     def __init__(self, device):
         self.device = device
         self.bufs: Dict[int, torch.Tensor] = {}
+        self.pos: Dict[int, int] = {}  # first frame of the current chunk's input inside the strip
 
     def input(self, conv: ConvParams, t: int, h: int, w: int, hist: int = 2) -> torch.Tensor:
         c = _up8(conv.c_in)
-        buf = self.bufs.get(id(conv))
-        if buf is None or buf.shape[0] < hist + t:
-            new = torch.zeros(hist + t, h, w, c, dtype=torch.bfloat16, device=self.device)
-            if buf is not None:
-                new[:hist].copy_(buf[:hist])
-            buf = self.bufs[id(conv)] = new
+        key = id(conv)
+        buf = self.bufs.get(key)
+        if buf is None:
+            buf = self.bufs[key] = torch.zeros(hist + self.ROOM * t, h, w, c, dtype=torch.bfloat16, device=self.device)
+            self.pos[key] = hist
         assert tuple(buf.shape[1:]) == (h, w, c), "canvas changed inside one encode / decode"
-        return buf[hist:hist + t]
+        pos = self.pos[key]
+        if hist + self.ROOM * t > buf.shape[0]:  # the chunks got longer (first chunk: 1 frame, later 2 or 4): grow
+            new = torch.zeros(hist + self.ROOM * t, h, w, c, dtype=torch.bfloat16, device=self.device)
+            new[:hist].copy_(buf[pos - hist:pos])
+            buf = self.bufs[key] = new
+            pos = self.pos[key] = hist
+        elif pos + t > buf.shape[0]:  # strip full: the history goes back to the start
+            for i in range(hist):  # ascending: frame pos - hist + i >= i, never overwritten before it is read
+                buf[i].copy_(buf[pos - hist + i])
+            pos = self.pos[key] = hist
+        return buf[pos:pos + t]
 
     def window(self, conv: ConvParams, t: int, hist: int = 2) -> torch.Tensor:
-        return self.bufs[id(conv)][: hist + t]
+        pos = self.pos[id(conv)]
+        return self.bufs[id(conv)][pos - hist:pos + t]
 
     def advance(self, conv: ConvParams, t: int, hist: int = 2) -> None:
-        """The last ``hist`` input frames become the history of the next chunk (:360-367: cache_x = x[:, :, -CACHE_T:],
-        topped up from the previous cache when the chunk is shorter)."""
-        buf = self.bufs[id(conv)]
-        for i in range(hist):  # ascending order: source frame t + i is never overwritten before it is read
-            buf[i].copy_(buf[t + i])
+        """The chunk's frames become history: the next chunk is written right behind them."""
+        self.pos[id(conv)] += t
+
+    def set_history(self, conv: ConvParams, frame: torch.Tensor, hist: int = 1) -> None:
+        """Overwrites the most recent history frame (downsample3d's first chunk, :303-305)."""
+        self.bufs[id(conv)][self.pos[id(conv)] - 1].copy_(frame)
 
 
 @dataclass
@@ -389,7 +405,7 @@ class AutoencoderKLWan(ModelBase):
             h2, w2 = h // 2, w // 2
             if first_chunk:  # :303-305: the first frame passes through and becomes the cache
                 caches.input(tc, t, h2, w2, hist=1)
-                caches.bufs[id(tc)][0].copy_(x[t - 1])
+                caches.set_history(tc, x[t - 1])
             else:
                 caches.input(tc, t, h2, w2, hist=1).copy_(x)
                 wt, bt = tc.packed()
