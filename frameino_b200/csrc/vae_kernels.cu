@@ -261,37 +261,48 @@ int dupup_add_cl(void* y, const void* src, int To, int Ho, int Wo, int Co, int T
 __global__ void __launch_bounds__(256)
 avgdown_add_cl_kernel(__nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ src, int To, int Ho, int Wo, int Co,
                       int Ti, int Hi, int Wi, int Ci, int ft, int fs, int group, int t_pad) {
-  const int64_t total = (int64_t)To * Ho * Wo * Co;
+  // one thread = 8 consecutive output channels of one output pixel (one 16-byte vector of y): the pixel coordinates are
+  // decoded once, the folded-channel index k = co*group + g only needs small divisions by ft / fs
+  const int groups8 = Co >> 3;
+  const int64_t total = (int64_t)To * Ho * Wo * groups8;
   const float inv = 1.0f / (float)group;
+  const int fss = fs * fs;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int co = (int)(idx % Co);
-    int64_t r = idx / Co;
+    const int c0 = (int)(idx % groups8) * 8;
+    int64_t r = idx / groups8;
     const int wo = (int)(r % Wo);
     r /= Wo;
     const int ho = (int)(r % Ho);
     const int to = (int)(r / Ho);
-    float acc = 0.f;
-    for (int gidx = 0; gidx < group; ++gidx) {
-      const int k = co * group + gidx;
-      const int d = k % fs;
-      const int b = (k / fs) % fs;
-      const int a = (k / (fs * fs)) % ft;
-      const int c = k / (fs * fs * ft);
-      const int ti = to * ft + a - t_pad;
-      if (ti >= 0) acc += __bfloat162float(src[(((int64_t)ti * Hi + ho * fs + b) * Wi + wo * fs + d) * Ci + c]);
+    uint4* yp = reinterpret_cast<uint4*>(y + (((int64_t)to * Ho + ho) * Wo + wo) * Co + c0);
+    float v[8];
+    unpack8f(*yp, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float acc = 0.f;
+      for (int gidx = 0; gidx < group; ++gidx) {
+        const int k = (c0 + e) * group + gidx;
+        const int sp = k % fss;  // position inside the fs x fs block
+        const int ca = k / fss;  // c * ft + a
+        const int a = ca % ft, c = ca / ft;
+        const int ti = to * ft + a - t_pad;
+        if (ti >= 0)
+          acc += __bfloat162float(src[(((int64_t)ti * Hi + ho * fs + sp / fs) * Wi + wo * fs + sp % fs) * Ci + c]);
+      }
+      v[e] += acc * inv;
     }
-    y[idx] = __float2bfloat16_rn(__bfloat162float(y[idx]) + acc * inv);
+    *yp = pack8f(v);
   }
 }
 
 int avgdown_add_cl(void* y, const void* src, int To, int Ho, int Wo, int Co, int Ti, int Hi, int Wi, int Ci, int ft, int fs,
                    cudaStream_t stream) {
-  FINO_CHECK_ARG(y && src && To > 0 && Ho > 0 && Wo > 0 && Co > 0 && Ci > 0, "avgdown_add_cl: bad arguments");
+  FINO_CHECK_ARG(y && src && To > 0 && Ho > 0 && Wo > 0 && Co > 0 && Co % 8 == 0 && Ci > 0, "avgdown_add_cl: bad arguments");
   FINO_CHECK_ARG(ft >= 1 && fs >= 1 && (Ci * ft * fs * fs) % Co == 0, "avgdown_add_cl: in_channels*factor %% out_channels");
   const int t_pad = (ft - Ti % ft) % ft;
   FINO_CHECK_ARG(Hi == Ho * fs && Wi == Wo * fs && (Ti + t_pad) == To * ft, "avgdown_add_cl: shape mismatch");
   const int group = Ci * ft * fs * fs / Co;
-  const int64_t total = (int64_t)To * Ho * Wo * Co;
+  const int64_t total = (int64_t)To * Ho * Wo * (Co / 8);
   int64_t blocks = (total + 255) / 256;
   const int64_t cap = (int64_t)num_sms() * 32;
   if (blocks > cap) blocks = cap;
