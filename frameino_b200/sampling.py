@@ -51,6 +51,7 @@ def wan_frameino_denoise(
     model_dtype: torch.dtype = torch.bfloat16,
     patch_hw: int = 2,
     cfg_parallel=None,              # frameino_b200.ulysses.CfgParallel: this rank runs one of the two CFG forwards
+    callback: Optional[Callable] = None,  # callback(i, t, latents) -> None | replacement latents (pipeline :893-901)
 ) -> torch.Tensor:
     dev = latents.device
     sigmas = flow_match_sigmas(num_steps, shift, dev)
@@ -80,6 +81,9 @@ def wan_frameino_denoise(
             v = vu + guidance_scale * (v - vu)  # :882, in the transformer dtype (bf16 tensor ops) like the reference
         v = v[:, :, :n_gen].float()  # :886 drop the ID frames
         latents = latents + (sigmas[i + 1] - sigmas[i]) * v  # :891 Euler
+        if callback is not None:
+            new = callback(i, t, latents)
+            latents = latents if new is None else new.to(latents)
     return latents
 
 
@@ -97,6 +101,7 @@ def wan_frameino_denoise_fused(
     guidance_scale: float = 5.0,
     shift: float = 5.0,
     cfg_parallel=None,              # frameino_b200.ulysses.CfgParallel: this rank runs one of the two CFG forwards
+    callback: Optional[Callable] = None,  # callback(i, t, latents) -> None | replacement latents (pipeline :893-901)
 ) -> torch.Tensor:
     """Same contract and result as ``wan_frameino_denoise`` (see the module docstring for what is fused)."""
     from . import ops
@@ -159,6 +164,10 @@ def wan_frameino_denoise_fused(
             y_c, y_u = cfg_parallel.exchange(y_c if run_c else y_u)
         dsigma = float(sig_host[i + 1] - sig_host[i])  # fp32 difference, as the tensor form computes it
         ops.wan_cfg_euler_step(lat, y_c, y_u, n_id, patch, guidance_scale, dsigma)
+        if callback is not None:
+            new = callback(i, t, lat)
+            if new is not None and new is not lat:
+                lat.copy_(new)
     return lat
 
 

@@ -242,6 +242,24 @@ def build_wan_on_device(cfg: dict, seed: int = 0, device="cuda", dtype: torch.dt
     return model.eval()
 
 
+def build_vae_on_device(cfg: dict, seed: int = 0, device="cuda"):
+    """Random-init ``frameino_b200.vae.AutoencoderKLWan`` (fp32 parameters, as the reference loads its VAE: app.py:157)
+    materialised directly on ``device`` with its bf16 weight packs prepared."""
+    from .vae import AutoencoderKLWan
+
+    with torch.device("meta"):
+        m = AutoencoderKLWan(**cfg)
+    m.to_empty(device=device)
+    shapes = vae_param_shapes(cfg)
+    params = dict(m.named_parameters())
+    assert set(params) == set(shapes), "state-dict layout drifted from synth.vae_param_shapes"
+    gen = torch.Generator(device=device).manual_seed(seed)
+    with torch.no_grad():
+        for name in sorted(shapes):
+            params[name].data = _fill(name, shapes[name], gen, device)
+    return m.eval().prepare()
+
+
 def build_cog_on_device(cfg: dict, seed: int = 0, device="cuda", dtype: torch.dtype = torch.bfloat16):
     """Random-init ``frameino_b200.CogVideoXTransformer3DModel`` materialised directly on ``device``."""
     from .cogvideox import CogVideoXTransformer3DModel
@@ -385,3 +403,34 @@ def make_vae_inputs(cfg: dict, latent_frames: int = 3, h: int = 4, w: int = 6, s
     z = torch.randn(1, cfg["z_dim"], latent_frames, h, w, generator=g, device=device)
     x = torch.randn(1, 3, 1 + 4 * (latent_frames - 1), h * s_, w * s_, generator=g, device=device).clamp(-1, 1)
     return z, x
+
+
+def with_latent_stats(cfg: dict, seed: int = 11) -> dict:
+    """A copy of a VAE config with seeded ``latents_mean`` / ``latents_std`` lists (the released values are in the
+    HF config, not under /root/reference; the pipeline only needs them to be per-channel numbers)."""
+    g = torch.Generator().manual_seed(seed)
+    z = cfg["z_dim"]
+    out = dict(cfg)
+    out["latents_mean"] = (0.3 * torch.randn(z, generator=g)).tolist()
+    out["latents_std"] = (0.5 + torch.rand(z, generator=g)).tolist()
+    return out
+
+
+def make_pipeline_inputs(vae_cfg: dict, text_dim: int, num_frames: int, height: int, width: int, n_id: int = 1,
+                         text_len: int = 16, seed: int = 9, batch: int = 1):
+    """Pixel-space inputs of the Wan FrameINO pipeline call (app.py:705-714): first-frame canvas [1, 3, H, W] in
+    [-1, 1], trajectory video [F, 3, H, W], ID image(s) [1, 3, n_id, H, W], prompt / negative prompt embeddings."""
+    g = torch.Generator().manual_seed(seed)
+    image = torch.rand(1, 3, height, width, generator=g) * 2 - 1
+    image[:, :, : height // 4] = -1.0  # an outpainting border, as the FrameINO canvas has
+    traj = (torch.rand(num_frames, 3, height, width, generator=g) < 0.05).float() * 2 - 1
+    ident = torch.rand(1, 3, n_id, height, width, generator=g) * 2 - 1 if n_id else None
+    pos = torch.randn(batch, text_len, text_dim, generator=g)
+    pos[:, text_len * 3 // 4:] = 0  # zero rows after the true length (pipeline :235-238)
+    neg = torch.zeros(batch, text_len, text_dim)
+    neg[:, :2] = torch.randn(batch, 2, text_dim, generator=g)
+    lat_shape = (batch, vae_cfg["z_dim"], (num_frames - 1) // vae_cfg["scale_factor_temporal"] + 1,
+                 height // vae_cfg["scale_factor_spatial"], width // vae_cfg["scale_factor_spatial"])
+    latents = torch.randn(lat_shape, generator=g)
+    return dict(image=image, traj_tensor=traj, ID_tensor=ident, prompt_embeds=pos, negative_prompt_embeds=neg,
+                latents=latents)

@@ -291,9 +291,15 @@ class AutoencoderKLWan(ModelBase):
         self.use_slicing = False
         self.use_tiling = False
 
-    # memory work-arounds of the reference (:1084-1133): not needed on a 180 GB part
+    # memory work-arounds of the reference (:1084-1133). Tiling cannot be mirrored for this VAE because the reference's
+    # own tiled path does not run for it: tiled_encode (:1301-1312) feeds the raw 3-channel tile to an encoder whose
+    # conv_in expects the 12 patchified channels (patchify happens after the tiling branch, :1148-1153), and
+    # tiled_decode (:1373-1397) returns the 12-channel tiles without unpatchify / clamp. No Wan caller enables it
+    # (only the CogVideoX scripts call vae.enable_tiling()).
     def enable_tiling(self, *a, **k):
-        raise NotImplementedError("tiled VAE encode / decode is a memory work-around that frameino_b200 does not need")
+        raise NotImplementedError("tiled encode / decode: the reference's tiled path fails for the Wan2.2 (patch_size 2) "
+                                  "VAE (un-patchified tiles into a 12-channel conv_in, autoencoder_kl_wan.py:1148-1153, "
+                                  ":1301-1312); the whole-frame path peaks at 32 GB at 704x1280x121, which fits")
 
     def disable_tiling(self):
         self.use_tiling = False

@@ -13,21 +13,10 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from frameino_b200 import ops, synth  # noqa: E402
-from frameino_b200.vae import AutoencoderKLWan  # noqa: E402
 
 
 def build(cfg, dev):
-    with torch.device("meta"):
-        m = AutoencoderKLWan(**cfg)
-    m.to_empty(device=dev)
-    shapes = synth.vae_param_shapes(cfg)
-    params = dict(m.named_parameters())
-    assert set(params) == set(shapes)
-    gen = torch.Generator(device=dev).manual_seed(0)
-    with torch.no_grad():
-        for name in sorted(shapes):
-            params[name].data = synth._fill(name, shapes[name], gen, dev)
-    return m.eval().prepare()
+    return synth.build_vae_on_device(cfg, seed=0, device=dev)
 
 
 def main():
