@@ -410,7 +410,73 @@ def run_secondary(args, world, rank, dev, wan_model, barrier):
     except Exception as ex:  # the secondary line must never take the headline down
         out["config3_cogvideox_b2"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
     torch.cuda.empty_cache()
+    if world == 1:
+        try:
+            out["wan_vae_704x1280x121"] = run_vae_secondary(dev)
+        except Exception as ex:
+            out["wan_vae_704x1280x121"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+        torch.cuda.empty_cache()
     return out
+
+
+def run_vae_secondary(dev):
+    """SURVEY §8f row 3 beside the loop: the Wan2.2 VAE (random-init TI2V-5B VAE architecture) at config 2's canvas —
+    one decode of the [1, 48, 31, 44, 80] latent and one encode of a 704x1280x121 clip, device-resident, CUDA events;
+    plus a parity check of the same code path against the CPU oracle at the tiny config (checker only)."""
+    import torch
+
+    from frameino_b200 import synth
+
+    vae = synth.build_vae_on_device(synth.WAN22_VAE, seed=0, device=dev)
+    g = torch.Generator(device=dev).manual_seed(3)
+    z = torch.randn(1, 48, 31, 44, 80, generator=g, device=dev)
+    x = torch.randn(1, 3, 121, 704, 1280, generator=g, device=dev).clamp_(-1, 1)
+    res = {"config": {"workload": "Wan2.2-TI2V-5B VAE (704.7 M parameters, random init), 704x1280x121 <-> latent "
+                                  "31x44x80x48, B=1, bf16 activations / fp32 accumulation, inputs resident in HBM"},
+           "unit": "ms"}
+    for name, fn in (("decode", lambda: vae.decode(z, return_dict=False)[0]),
+                     ("encode", lambda: vae.encode(x).latent_dist.mode())):
+        fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        y = fn()
+        e.record()
+        torch.cuda.synchronize()
+        res[name + "_ms"] = s.elapsed_time(e)
+        res[name + "_finite"] = bool(torch.isfinite(y.float()).all())
+        del y
+    del vae, z, x
+    torch.cuda.empty_cache()
+    # parity of the same kernels / chunking against the oracle, at a size the CPU finishes in a second
+    from frameino_b200.vae import AutoencoderKLWan
+    from oracle import vae_oracle
+
+    cfg = synth.VAE_TINY
+    sd = synth.make_vae_state_dict(cfg, seed=1)
+    tiny = AutoencoderKLWan(**cfg)
+    tiny.load_state_dict(sd, strict=True)
+    tiny = tiny.to(dev).eval().prepare()
+    zt, xt = synth.make_vae_inputs(cfg, latent_frames=3, h=4, w=6)
+    taps = {}
+    vae_oracle.decode(sd, cfg, zt, taps)
+    want_enc = vae_oracle.encode(sd, cfg, xt)[:, : cfg["z_dim"]]
+    tiny.__dict__["_fino_taps"] = {}
+    tiny.decode(zt.to(dev), return_dict=False)
+    got_head = tiny.__dict__.pop("_fino_taps")["head"]
+    got_enc = tiny.encode(xt.to(dev)).latent_dist.mode()
+
+    def rel(a, b):
+        return float((a.float().cpu() - b).abs().max() / b.abs().max())
+
+    head = taps["head"]
+    got_head = torch.cat(got_head, dim=0).permute(3, 0, 1, 2)[None]  # per-chunk channels-last frames -> NCTHW
+    res["parity"] = {"what": "tiny VAE config (3 latent frames, 64x96): decoder head before the clamp and posterior mean "
+                             "vs the CPU oracle, max |a-b| / max |b|", "decode_head_rel_err": rel(got_head, head),
+                     "encode_mean_rel_err": rel(got_enc, want_enc), "tolerance": 2e-2}
+    res["parity"]["pass"] = bool(res["parity"]["decode_head_rel_err"] <= 2e-2
+                                 and res["parity"]["encode_mean_rel_err"] <= 2e-2)
+    return res
 
 
 # ---------------------------------------------------------------------------------------------------------------
