@@ -441,11 +441,14 @@ def rms_act_cl(x: torch.Tensor, gamma: torch.Tensor, bias: Optional[torch.Tensor
     return out
 
 
-def upsample2x_cl(x: torch.Tensor) -> torch.Tensor:
+def upsample2x_cl(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     assert x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous()
-    lib, stream = _prep(x)
+    lib, stream = _prep(x, out)
     t, h, w, c = x.shape
-    out = torch.empty(t, 2 * h, 2 * w, c, dtype=x.dtype, device=x.device)
+    if out is None:
+        out = torch.empty(t, 2 * h, 2 * w, c, dtype=x.dtype, device=x.device)
+    assert out.dtype == x.dtype and tuple(out.shape) == (t, 2 * h, 2 * w, c) and (t == 1 or out.is_contiguous())
+    assert out[0].is_contiguous()
     _lib.check(lib.fino_upsample2x_cl(x.data_ptr(), out.data_ptr(), t, h, w, c, stream), "fino_upsample2x_cl")
     return out
 

@@ -181,31 +181,114 @@ class Decoder3d(nn.Module):  # :783-909
         self.conv_out = ConvParams(dims[-1], out_channels, (3, 3, 3))
 
 
+# ---- multi-GPU: the frame rows of a decode split across the ranks of a process group -------------------------------
+class RowParallel:
+    """Every rank decodes a horizontal band of the frames (latent rows ``rows(h)``, the same band scaled by 2 after each
+    up-sampling stage). Everything in the decoder is pixel-local except (i) the 3x3 spatial taps of the convolutions —
+    each convolution's input buffer carries one halo row above and below the band, refreshed from the neighbouring
+    ranks right after the producer has written the band (``exchange``: one small all-gather of the two edge rows per
+    convolution, NCCL over NVLink) — and (ii) the mid-block attention, whose keys / values are the whole frame
+    (``gather_rows`` of the 1024-channel latent-resolution activations, 7 MB per frame at 44 x 80). Bands at the image
+    border keep their outer halo row zero: that IS the convolution's zero padding. The arithmetic per output pixel is
+    the un-sharded one, in the same order — the result is bit-identical."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+
+        if not dist.is_initialized():
+            raise RuntimeError("RowParallel needs an initialised torch.distributed process group")
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    @staticmethod
+    def split(h: int, world: int) -> List[Tuple[int, int]]:
+        """Row ranges [a, b) per rank: the first ``h % world`` ranks hold one row more."""
+        if h < world:
+            raise ValueError(f"cannot split {h} latent rows over {world} ranks")
+        base, extra = divmod(h, world)
+        out, a = [], 0
+        for r in range(world):
+            b = a + base + (1 if r < extra else 0)
+            out.append((a, b))
+            a = b
+        return out
+
+    def rows(self, h: int) -> Tuple[int, int]:
+        return self.split(h, self.world)[self.rank]
+
+    def exchange(self, frames: torch.Tensor) -> None:
+        """frames: [t, h_loc + 2, W, C] (rows 1..h_loc written): fills row 0 from the rank above, row h_loc + 1 from the
+        rank below."""
+        import torch.distributed as dist
+
+        if self.world == 1:
+            return
+        t, hp, w, c = frames.shape
+        hl = hp - 2
+        edge = torch.stack((frames[:, 1], frames[:, hl]))  # [2, t, W, C]: my first and last rows
+        flat = torch.empty((self.world * 2,) + tuple(edge.shape[1:]), dtype=edge.dtype, device=edge.device)
+        dist.all_gather_into_tensor(flat, edge, group=self.group)
+        allb = flat.view((self.world,) + tuple(edge.shape))
+        if self.rank > 0:
+            frames[:, 0].copy_(allb[self.rank - 1, 1])
+        if self.rank < self.world - 1:
+            frames[:, hl + 1].copy_(allb[self.rank + 1, 0])
+
+    def gather_rows(self, x: torch.Tensor, h_total: int, dim: int = 1) -> torch.Tensor:
+        """The bands of all ranks concatenated along ``dim`` (the row axis): every rank gets the whole frames."""
+        import torch.distributed as dist
+
+        if self.world == 1:
+            return x
+        sizes = [b - a for a, b in self.split(h_total, self.world)]
+        scale = x.shape[dim] // sizes[self.rank]  # bands grow by 2 per up-sampling stage (and by the patch size)
+        assert x.shape[dim] == sizes[self.rank] * scale, "band height does not match the row split"
+        hmax = max(sizes) * scale
+        if x.shape[dim] != hmax:
+            pad_shape = list(x.shape)
+            pad_shape[dim] = hmax - x.shape[dim]
+            x = torch.cat([x, x.new_zeros(pad_shape)], dim=dim)
+        x = x.contiguous()
+        flat = torch.empty((self.world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(flat, x, group=self.group)
+        allb = flat.view((self.world,) + tuple(x.shape))
+        return torch.cat([allb[r].narrow(dim, 0, sizes[r] * scale) for r in range(self.world)], dim=dim)
+
+
 # ---- run-time state: the causal history of every convolution (the reference's feat_cache) ---------------------------
 class _ConvCaches:
     """Per-convolution input buffers: a strip of frames ``[capacity, H, W, C]`` in which every chunk's input is written
     right behind the previous chunk's, so the last ``hist`` frames of the previous chunk ARE the causal history of the
     next one (the reference's ``feat_cache``, :360-367) without moving them; only when the strip is full are the last
-    ``hist`` frames copied back to its start (every ``ROOM`` chunks). Frames before the first chunk are zeros."""
+    ``hist`` frames copied back to its start (every ``ROOM`` chunks). Frames before the first chunk are zeros.
+    With ``halo = 1`` (row-parallel decode) the strips of the spatial convolutions hold one extra row above and below
+    every frame (``input`` returns the band, ``frames`` / ``window`` the band with its halo rows)."""
 
     ROOM = 4  # chunks of the current length a strip holds before it wraps
 
-    def __init__(self, device):
+    def __init__(self, device, halo: int = 0):
         self.device = device
+        self.halo = halo
         self.bufs: Dict[int, torch.Tensor] = {}
         self.pos: Dict[int, int] = {}  # first frame of the current chunk's input inside the strip
+        self.pad: Dict[int, int] = {}
+        self.scratch: Dict[tuple, torch.Tensor] = {}
 
-    def input(self, conv: ConvParams, t: int, h: int, w: int, hist: int = 2) -> torch.Tensor:
+    def input(self, conv: ConvParams, t: int, h: int, w: int, hist: int = 2, spatial: bool = True) -> torch.Tensor:
         c = _up8(conv.c_in)
         key = id(conv)
+        pad = self.halo if spatial else 0
+        hp = h + 2 * pad
         buf = self.bufs.get(key)
         if buf is None:
-            buf = self.bufs[key] = torch.zeros(hist + self.ROOM * t, h, w, c, dtype=torch.bfloat16, device=self.device)
+            buf = self.bufs[key] = torch.zeros(hist + self.ROOM * t, hp, w, c, dtype=torch.bfloat16, device=self.device)
             self.pos[key] = hist
-        assert tuple(buf.shape[1:]) == (h, w, c), "canvas changed inside one encode / decode"
+            self.pad[key] = pad
+        assert tuple(buf.shape[1:]) == (hp, w, c) and self.pad[key] == pad, "canvas changed inside one encode / decode"
         pos = self.pos[key]
         if hist + self.ROOM * t > buf.shape[0]:  # the chunks got longer (first chunk: 1 frame, later 2 or 4): grow
-            new = torch.zeros(hist + self.ROOM * t, h, w, c, dtype=torch.bfloat16, device=self.device)
+            new = torch.zeros(hist + self.ROOM * t, hp, w, c, dtype=torch.bfloat16, device=self.device)
             new[:hist].copy_(buf[pos - hist:pos])
             buf = self.bufs[key] = new
             pos = self.pos[key] = hist
@@ -213,7 +296,12 @@ class _ConvCaches:
             for i in range(hist):  # ascending: frame pos - hist + i >= i, never overwritten before it is read
                 buf[i].copy_(buf[pos - hist + i])
             pos = self.pos[key] = hist
-        return buf[pos:pos + t]
+        return buf[pos:pos + t, pad:pad + h] if pad else buf[pos:pos + t]
+
+    def frames(self, conv: ConvParams, t: int) -> torch.Tensor:
+        """The current chunk's frames with their halo rows."""
+        pos = self.pos[id(conv)]
+        return self.bufs[id(conv)][pos:pos + t]
 
     def window(self, conv: ConvParams, t: int, hist: int = 2) -> torch.Tensor:
         pos = self.pos[id(conv)]
@@ -226,6 +314,14 @@ class _ConvCaches:
     def set_history(self, conv: ConvParams, frame: torch.Tensor, hist: int = 1) -> None:
         """Overwrites the most recent history frame (downsample3d's first chunk, :303-305)."""
         self.bufs[id(conv)][self.pos[id(conv)] - 1].copy_(frame)
+
+    def padded(self, conv: ConvParams, t: int, h: int, w: int, c: int) -> torch.Tensor:
+        """A zero-initialised [t, h + 2 halo, w, c] buffer kept per (convolution, t): the input of a 2-D convolution."""
+        key = (id(conv), t, h, w, c)
+        buf = self.scratch.get(key)
+        if buf is None:
+            buf = self.scratch[key] = torch.zeros(t, h + 2 * self.halo, w, c, dtype=torch.bfloat16, device=self.device)
+        return buf
 
 
 @dataclass
@@ -290,6 +386,7 @@ class AutoencoderKLWan(ModelBase):
         self.spatial_compression_ratio = 2 ** len(self.temperal_downsample)
         self.use_slicing = False
         self.use_tiling = False
+        self.row_parallel: Optional[RowParallel] = None
 
     # memory work-arounds of the reference (:1084-1133). Tiling cannot be mirrored for this VAE because the reference's
     # own tiled path does not run for it: tiled_encode (:1301-1312) feeds the raw 3-channel tile to an encoder whose
@@ -303,6 +400,15 @@ class AutoencoderKLWan(ModelBase):
 
     def disable_tiling(self):
         self.use_tiling = False
+
+    def enable_row_parallel(self, group=None) -> "RowParallel":
+        """``decode`` splits the frame rows over the ranks of ``group`` (every rank calls it with the same latents and
+        gets the whole video); ``encode`` stays replicated."""
+        self.row_parallel = RowParallel(group)
+        return self.row_parallel
+
+    def disable_row_parallel(self) -> None:
+        self.row_parallel = None
 
     def enable_slicing(self):
         self.use_slicing = True  # batch elements are processed one at a time anyway
@@ -335,20 +441,37 @@ class AutoencoderKLWan(ModelBase):
         return y.view(t, h, wd, w.shape[0])
 
     def _causal(self, caches: _ConvCaches, conv: ConvParams, t: int, h: int, w: int,
-                residual: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Runs a 3x3x3 causal convolution on the frames its producer has written into ``caches.input(conv, ...)``."""
+                residual: Optional[torch.Tensor] = None, exchange: bool = True) -> torch.Tensor:
+        """Runs a 3x3x3 causal convolution on the frames its producer has written into ``caches.input(conv, ...)``.
+        Row-parallel: the band's halo rows come from the neighbouring ranks first, and the convolution is "valid"
+        along H over the band + halo."""
         wp, bp = conv.packed()
-        y = ops.conv3d_cl(caches.window(conv, t), wp, bp, conv.kernel3, pad_hw=(1, 1), residual=residual)
+        if caches.halo:
+            if exchange:
+                self.row_parallel.exchange(caches.frames(conv, t))
+            y = ops.conv3d_cl(caches.window(conv, t), wp, bp, conv.kernel3, pad_hw=(0, 1), residual=residual)
+        else:
+            y = ops.conv3d_cl(caches.window(conv, t), wp, bp, conv.kernel3, pad_hw=(1, 1), residual=residual)
         caches.advance(conv, t)
         return y
+
+    @staticmethod
+    def _rms_into(x: torch.Tensor, gamma: torch.Tensor, dst: torch.Tensor) -> None:
+        """WanRMS_norm + SiLU of x [t, h, w, c] into a convolution's input frames (frame-strided when they carry halo
+        rows: one launch per frame then)."""
+        if dst.is_contiguous():
+            ops.rms_act_cl(x, gamma, silu=True, out=dst)
+        else:
+            for f in range(x.shape[0]):
+                ops.rms_act_cl(x[f], gamma, silu=True, out=dst[f])
 
     def _res_block(self, caches: _ConvCaches, blk: ResidualBlock, x: torch.Tensor) -> torch.Tensor:
         """WanResidualBlock.forward (:342-382)."""
         t, h, w, _ = x.shape
         skip = x if blk.conv_shortcut is None else self._conv1x1(blk.conv_shortcut, x)
-        ops.rms_act_cl(x, blk.norm1.gamma32(), silu=True, out=caches.input(blk.conv1, t, h, w))
+        self._rms_into(x, blk.norm1.gamma32(), caches.input(blk.conv1, t, h, w))
         y = self._causal(caches, blk.conv1, t, h, w)
-        ops.rms_act_cl(y, blk.norm2.gamma32(), silu=True, out=caches.input(blk.conv2, t, h, w))
+        self._rms_into(y, blk.norm2.gamma32(), caches.input(blk.conv2, t, h, w))
         return self._causal(caches, blk.conv2, t, h, w, residual=skip)
 
     def _attention(self, blk: AttentionBlock, x: torch.Tensor) -> torch.Tensor:
@@ -356,25 +479,36 @@ class AutoencoderKLWan(ModelBase):
         softmax and P V are two tcgen05 GEMMs around a softmax kernel (head_dim = C is far beyond a flash tile); V is
         produced already transposed (V^T = W_v X^T) and its bias is added after P V (softmax rows sum to one)."""
         t, h, w, c = x.shape
-        n = h * w
-        if n % 8 != 0:
-            raise NotImplementedError(f"VAE attention: {h} x {w} latent pixels per frame must be a multiple of 8")
-        npad = _up8(n)
+        rp = self.row_parallel
+        nq = h * w  # this rank's query pixels (the whole frame unless row-parallel)
         wqkv, bqkv = blk.to_qkv.dense()
         wp, bp = blk.proj.dense()
         out = torch.empty_like(x)
         xn = ops.rms_act_cl(x, blk.norm.gamma32(), silu=False)
-        scores = torch.empty(n, n, dtype=torch.float32, device=x.device)
-        probs = torch.empty(n, npad, dtype=torch.bfloat16, device=x.device)
+        # keys / values are the whole frame: gathered from all bands when the rows are split
+        xkv = xn if rp is None else rp.gather_rows(xn, self._latent_rows)
+        n = xkv.shape[1] * w
+        if n % 8 != 0:
+            raise NotImplementedError(f"VAE attention: {xkv.shape[1]} x {w} latent pixels per frame must be a multiple "
+                                      f"of 8")
+        npad = _up8(n)
+        scores = torch.empty(nq, n, dtype=torch.float32, device=x.device)
+        probs = torch.empty(nq, npad, dtype=torch.bfloat16, device=x.device)
         v_t = torch.zeros(c, npad, dtype=torch.bfloat16, device=x.device)
         for f in range(t):
-            xf = xn[f].reshape(n, c)
-            qk = ops.linear(xf, wqkv[: 2 * c], bqkv[: 2 * c])  # [n, 2C]
+            xf = xkv[f].reshape(n, c)
+            if rp is None:
+                qk = ops.linear(xf, wqkv[: 2 * c], bqkv[: 2 * c])  # [n, 2C]
+                q, k = qk[:, :c], qk[:, c:]
+            else:
+                q = ops.linear(xn[f].reshape(nq, c), wqkv[:c], bqkv[:c].contiguous())
+                k = ops.linear(xf, wqkv[c: 2 * c], bqkv[c: 2 * c].contiguous())
             ops.linear(wqkv[2 * c: 3 * c], xf, None, out=v_t[:, :n])  # V^T without bias: [C, n]
-            ops.linear(qk[:, :c], qk[:, c:], None, out=scores)  # Q K^T, fp32
+            ops.linear(q, k, None, out=scores)  # Q K^T, fp32
             ops.softmax_rows(scores, float(c) ** -0.5, probs)
-            o = ops.linear(probs, v_t, bqkv[2 * c: 3 * c].contiguous())  # P V + b_v: [n, C]
-            ops.linear(o, wp, bp, epilogue=ops.EPI_GATE_RESIDUAL, residual=x[f].reshape(n, c), out=out[f].reshape(n, c))
+            o = ops.linear(probs, v_t, bqkv[2 * c: 3 * c].contiguous())  # P V + b_v: [nq, C]
+            ops.linear(o, wp, bp, epilogue=ops.EPI_GATE_RESIDUAL, residual=x[f].reshape(nq, c),
+                       out=out[f].reshape(nq, c))
         return out
 
     def _mid(self, caches: _ConvCaches, mid: MidBlock, x: torch.Tensor) -> torch.Tensor:
@@ -387,7 +521,7 @@ class AutoencoderKLWan(ModelBase):
         t, h, w, c = x.shape
         if up.mode == "upsample3d" and not first_chunk:  # the first chunk only marks the cache ("Rep", :269-271)
             tc = up.time_conv
-            caches.input(tc, t, h, w).copy_(x)
+            caches.input(tc, t, h, w, spatial=False).copy_(x)
             wp, bp = tc.packed()
             y = torch.empty(2 * t, h, w, c, dtype=x.dtype, device=x.device)
             win = caches.window(tc, t)
@@ -397,6 +531,13 @@ class AutoencoderKLWan(ModelBase):
             x = y
         conv = up.resample[1]
         wp, bp = conv.packed()
+        if caches.halo:  # the up-sampled band goes between the halo rows of a kept buffer, frame by frame
+            t2, h2, w2 = x.shape[0], 2 * x.shape[1], 2 * x.shape[2]
+            buf = caches.padded(conv, t2, h2, w2, c)
+            for f in range(t2):
+                ops.upsample2x_cl(x[f:f + 1], out=buf[f:f + 1, 1:1 + h2])
+            self.row_parallel.exchange(buf)
+            return ops.conv3d_cl(buf, wp, bp, (1, 3, 3), pad_hw=(0, 1))
         return ops.conv3d_cl(ops.upsample2x_cl(x), wp, bp, (1, 3, 3), pad_hw=(1, 1))
 
     def _downsample(self, caches: _ConvCaches, ds: Resample, x: torch.Tensor, first_chunk: bool) -> torch.Tensor:
@@ -424,9 +565,18 @@ class AutoencoderKLWan(ModelBase):
     def _decode_chunk(self, caches: _ConvCaches, x: torch.Tensor, first_chunk: bool, taps: Optional[dict]) -> torch.Tensor:
         """WanDecoder3d.forward (:874-909) on one latent frame; returns channels-last [t_out, H, W, up8(out_channels)]."""
         dec = self.decoder
-        t, h, w, _ = x.shape
-        caches.input(dec.conv_in, t, h, w).copy_(x)
-        x = self._causal(caches, dec.conv_in, t, h, w)
+        if caches.halo:  # x is the whole latent frame: the band AND its halo rows are at hand, nothing to exchange
+            t, hfull, w, _ = x.shape
+            a, b = self.row_parallel.rows(hfull)
+            h = b - a
+            caches.input(dec.conv_in, t, h, w)
+            lo, hi = max(a - 1, 0), min(b + 1, hfull)
+            caches.frames(dec.conv_in, t)[:, lo - (a - 1):lo - (a - 1) + (hi - lo)].copy_(x[:, lo:hi])
+            x = self._causal(caches, dec.conv_in, t, h, w, exchange=False)
+        else:
+            t, h, w, _ = x.shape
+            caches.input(dec.conv_in, t, h, w).copy_(x)
+            x = self._causal(caches, dec.conv_in, t, h, w)
         x = self._mid(caches, dec.mid_block, x)
         if taps is not None:
             taps.setdefault("mid", []).append(x.clone())
@@ -440,7 +590,7 @@ class AutoencoderKLWan(ModelBase):
             if taps is not None:
                 taps.setdefault(f"up{i}", []).append(x.clone())
         t, h, w, _ = x.shape
-        ops.rms_act_cl(x, dec.norm_out.gamma32(), silu=True, out=caches.input(dec.conv_out, t, h, w))
+        self._rms_into(x, dec.norm_out.gamma32(), caches.input(dec.conv_out, t, h, w))
         y = self._causal(caches, dec.conv_out, t, h, w)
         if taps is not None:
             taps.setdefault("head", []).append(y[..., : dec.conv_out.c_out].clone())
@@ -468,11 +618,18 @@ class AutoencoderKLWan(ModelBase):
         ho, wo = h * (2 ** n_up) * ps, w * (2 ** n_up) * ps
         t_total = 1 + (tl - 1) * (2 ** n_tup)
         dt = output_dtype or (z.dtype if z.dtype in (torch.float32, torch.bfloat16) else torch.float32)
-        out = torch.empty(b, c_img, t_total, ho, wo, dtype=dt, device=z.device)
+        rp = self.row_parallel if (self.row_parallel is not None and self.row_parallel.world > 1) else None
         taps = self.__dict__.get("_fino_taps")
+        if rp is not None:  # this rank's band of every frame; gathered at the end
+            if taps is not None:
+                raise NotImplementedError("stage taps are an un-sharded debugging aid")
+            a, b_ = rp.rows(h)
+            self._latent_rows = h
+            ho_full, ho = ho, (b_ - a) * (2 ** n_up) * ps
+        out = torch.empty(b, c_img, t_total, ho, wo, dtype=dt, device=z.device)
         zin = z if z.dtype in (torch.float32, torch.bfloat16) else z.float()
         for bi in range(b):
-            caches = _ConvCaches(z.device)
+            caches = _ConvCaches(z.device, halo=0 if rp is None else 1)
             x_all = self._conv1x1(self.post_quant_conv, ops.vae_to_cl(zin[bi], 1, _up8(zc)))  # :1207
             f0 = 0
             for i in range(tl):  # :1208-1216
@@ -480,6 +637,9 @@ class AutoencoderKLWan(ModelBase):
                 ops.vae_from_cl(y, out[bi, :, f0:f0 + y.shape[0]], c_img, ps, clamp=True)  # :1218-1224
                 f0 += y.shape[0]
             assert f0 == t_total
+        if rp is not None:
+            out = rp.gather_rows(out, h, dim=3)
+            assert out.shape[3] == ho_full
         if not return_dict:
             return (out,)
         return DecoderOutput(sample=out)
