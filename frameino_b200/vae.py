@@ -474,13 +474,12 @@ class AutoencoderKLWan(ModelBase):
         self._rms_into(y, blk.norm2.gamma32(), caches.input(blk.conv2, t, h, w))
         return self._causal(caches, blk.conv2, t, h, w, residual=skip)
 
-    def _attention(self, blk: AttentionBlock, x: torch.Tensor) -> torch.Tensor:
+    def _attention(self, blk: AttentionBlock, x: torch.Tensor, rp: Optional[RowParallel] = None) -> torch.Tensor:
         """WanAttentionBlock.forward (:402-427): per frame, one head of width C over the H*W pixels. Q K^T, the row
         softmax and P V are two tcgen05 GEMMs around a softmax kernel (head_dim = C is far beyond a flash tile); V is
         produced already transposed (V^T = W_v X^T) and its bias is added after P V (softmax rows sum to one)."""
         t, h, w, c = x.shape
-        rp = self.row_parallel
-        nq = h * w  # this rank's query pixels (the whole frame unless row-parallel)
+        nq = h * w  # this rank's query pixels (the whole frame unless row-parallel: rp is set by a sharded decode only)
         wqkv, bqkv = blk.to_qkv.dense()
         wp, bp = blk.proj.dense()
         out = torch.empty_like(x)
@@ -513,7 +512,7 @@ class AutoencoderKLWan(ModelBase):
 
     def _mid(self, caches: _ConvCaches, mid: MidBlock, x: torch.Tensor) -> torch.Tensor:
         x = self._res_block(caches, mid.resnets[0], x)
-        x = self._attention(mid.attentions[0], x)
+        x = self._attention(mid.attentions[0], x, self.row_parallel if caches.halo else None)
         return self._res_block(caches, mid.resnets[1], x)
 
     def _upsample(self, caches: _ConvCaches, up: Resample, x: torch.Tensor, first_chunk: bool) -> torch.Tensor:

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--height", type=int, default=704)
     ap.add_argument("--width", type=int, default=1280)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--no-vae-parallel", action="store_true", help="keep the VAE decode replicated under torchrun")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -44,6 +45,8 @@ def main():
         from frameino_b200.ulysses import enable_sequence_parallel
 
         enable_sequence_parallel(tf)
+        if not args.no_vae_parallel:
+            vae.enable_row_parallel()  # decode split by frame rows; the three encodes stay replicated
     pipe = WanFrameINOPipeline(vae=vae, transformer=tf)
     inp = synth.make_pipeline_inputs(vcfg, synth.WAN22_5B["text_dim"], args.frames, args.height, args.width, n_id=1,
                                      text_len=512)
@@ -67,10 +70,11 @@ def main():
     vae.decode = timed("vae_decode", real_decode)
 
     def call(steps):
-        return pipe(image=host["image"], traj_tensor=host["traj_tensor"], ID_tensor=host["ID_tensor"],
-                    prompt_embeds=host["prompt_embeds"], negative_prompt_embeds=host["negative_prompt_embeds"],
-                    latents=host["latents"], height=args.height, width=args.width, num_frames=args.frames,
-                    num_inference_steps=steps, guidance_scale=5.0, output_type="pt").frames.cpu()
+        v = pipe(image=host["image"], traj_tensor=host["traj_tensor"], ID_tensor=host["ID_tensor"],
+                 prompt_embeds=host["prompt_embeds"], negative_prompt_embeds=host["negative_prompt_embeds"],
+                 latents=host["latents"], height=args.height, width=args.width, num_frames=args.frames,
+                 num_inference_steps=steps, guidance_scale=5.0, output_type="pt").frames
+        return v.cpu() if rank == 0 else v  # every rank holds the video; rank 0 hands it to the host
 
     call(1)  # warm-up: weight packs, workspaces, peer buffers
     torch.cuda.synchronize()
@@ -87,7 +91,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     res = {"workload": f"Wan FrameINO pipeline call, {args.height}x{args.width}x{args.frames}, {args.steps} steps x 2 "
                        f"CFG forwards, guidance 5.0, random-init Wan2.2-5B + Wan2.2 VAE, synthetic inputs",
-           "n_gpus": world, "total_ms": float(t.item()),
+           "n_gpus": world, "parallelism": "single GPU" if world == 1 else
+           f"DiT: ulysses x{world}; VAE decode: " + ("replicated" if args.no_vae_parallel else f"row bands x{world}")
+           + "; VAE encodes replicated", "total_ms": float(t.item()),
            "stage_ms": {k: a.elapsed_time(b) for k, (a, b) in stages.items()},
            "video_shape": list(video.shape), "finite": bool(torch.isfinite(video).all()),
            "h2d_bytes": int(sum(v.numel() * v.element_size() for v in host.values() if isinstance(v, torch.Tensor))),

@@ -53,7 +53,12 @@ def main():
         ref = vae.decode(z, return_dict=False)[0]
         vae.enable_row_parallel()
         got = vae.decode(z, return_dict=False)[0]
+        # encode stays replicated while row-parallel decode is enabled (the pipeline encodes first, then decodes)
+        clip = ref[:, :, : 1 + 4 * ((ref.shape[2] - 1) // 4)].contiguous()
+        enc_rp = vae.encode(clip).latent_dist.mode()
         vae.disable_row_parallel()
+        enc = vae.encode(clip).latent_dist.mode()
+        assert torch.equal(enc, enc_rp), "encode changed under enable_row_parallel"
         diff = float((got - ref).abs().max())
         t = torch.tensor([diff], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
