@@ -402,8 +402,8 @@ class AutoencoderKLWan(ModelBase):
         self.use_tiling = False
 
     def enable_row_parallel(self, group=None) -> "RowParallel":
-        """``decode`` splits the frame rows over the ranks of ``group`` (every rank calls it with the same latents and
-        gets the whole video); ``encode`` stays replicated."""
+        """``decode`` and ``encode`` split the frame rows over the ranks of ``group``: every rank calls them with the
+        same input and gets the whole result, bit-identical to the un-sharded one."""
         self.row_parallel = RowParallel(group)
         return self.row_parallel
 
@@ -545,33 +545,46 @@ class AutoencoderKLWan(ModelBase):
         conv = ds.resample[1]
         wp, bp = conv.packed()
         # ZeroPad2d((0, 1, 0, 1)) + Conv2d(stride 2): the pad row / column is the TMA out-of-bounds fill
-        x = ops.conv3d_cl(x, wp, bp, (1, 3, 3), pad_hw=(0, 0), stride_hw=2, out_hw=(h // 2, w // 2))
+        if caches.halo:  # row-parallel: output row r reads rows 2r .. 2r+2, i.e. one row of the band below
+            buf = caches.padded(conv, t, h, w, c)
+            buf[:, 1:1 + h].copy_(x)
+            self.row_parallel.exchange(buf)
+            x = ops.conv3d_cl(buf[:, 1:], wp, bp, (1, 3, 3), pad_hw=(0, 0), stride_hw=2, out_hw=(h // 2, w // 2))
+        else:
+            x = ops.conv3d_cl(x, wp, bp, (1, 3, 3), pad_hw=(0, 0), stride_hw=2, out_hw=(h // 2, w // 2))
         if ds.mode == "downsample3d":
             tc = ds.time_conv
             h2, w2 = h // 2, w // 2
             if first_chunk:  # :303-305: the first frame passes through and becomes the cache
-                caches.input(tc, t, h2, w2, hist=1)
+                caches.input(tc, t, h2, w2, hist=1, spatial=False)
                 caches.set_history(tc, x[t - 1])
             else:
-                caches.input(tc, t, h2, w2, hist=1).copy_(x)
+                caches.input(tc, t, h2, w2, hist=1, spatial=False).copy_(x)
                 wt, bt = tc.packed()
                 y = ops.conv3d_cl(caches.window(tc, t, hist=1), wt, bt, (3, 1, 1), stride_t=2)
                 caches.advance(tc, t, hist=1)
                 x = y
         return x
 
+    def _conv_in_band(self, caches: _ConvCaches, conv: ConvParams, x: torch.Tensor) -> torch.Tensor:
+        """Row-parallel first convolution: x [t, H, W, C] holds WHOLE frames (the input is on every rank), so this rank's
+        band — the latent split scaled to x's resolution — and its two halo rows are copied from it directly."""
+        t, hfull, w, _ = x.shape
+        sc = hfull // self._latent_rows
+        a, b = self.row_parallel.rows(self._latent_rows)
+        a, b = a * sc, b * sc
+        h = b - a
+        caches.input(conv, t, h, w)
+        lo, hi = max(a - 1, 0), min(b + 1, hfull)
+        caches.frames(conv, t)[:, lo - (a - 1):lo - (a - 1) + (hi - lo)].copy_(x[:, lo:hi])
+        return self._causal(caches, conv, t, h, w, exchange=False)
+
     # ---- decode ------------------------------------------------------------------------------------------------------
     def _decode_chunk(self, caches: _ConvCaches, x: torch.Tensor, first_chunk: bool, taps: Optional[dict]) -> torch.Tensor:
         """WanDecoder3d.forward (:874-909) on one latent frame; returns channels-last [t_out, H, W, up8(out_channels)]."""
         dec = self.decoder
         if caches.halo:  # x is the whole latent frame: the band AND its halo rows are at hand, nothing to exchange
-            t, hfull, w, _ = x.shape
-            a, b = self.row_parallel.rows(hfull)
-            h = b - a
-            caches.input(dec.conv_in, t, h, w)
-            lo, hi = max(a - 1, 0), min(b + 1, hfull)
-            caches.frames(dec.conv_in, t)[:, lo - (a - 1):lo - (a - 1) + (hi - lo)].copy_(x[:, lo:hi])
-            x = self._causal(caches, dec.conv_in, t, h, w, exchange=False)
+            x = self._conv_in_band(caches, dec.conv_in, x)
         else:
             t, h, w, _ = x.shape
             caches.input(dec.conv_in, t, h, w).copy_(x)
@@ -647,9 +660,12 @@ class AutoencoderKLWan(ModelBase):
     def _encode_chunk(self, caches: _ConvCaches, x: torch.Tensor, first_chunk: bool, taps: Optional[dict]) -> torch.Tensor:
         """WanEncoder3d.forward (:586-623) on one chunk (1 frame, then 4 at a time); returns [t', h, w, 2 z_dim]."""
         enc = self.encoder
-        t, h, w, _ = x.shape
-        caches.input(enc.conv_in, t, h, w).copy_(x)
-        x = self._causal(caches, enc.conv_in, t, h, w)
+        if caches.halo:  # x holds whole frames (the clip is on every rank): band + halo rows without an exchange
+            x = self._conv_in_band(caches, enc.conv_in, x)
+        else:
+            t, h, w, _ = x.shape
+            caches.input(enc.conv_in, t, h, w).copy_(x)
+            x = self._causal(caches, enc.conv_in, t, h, w)
         for i, blk in enumerate(enc.down_blocks):
             x_copy = x
             for res in blk.resnets:
@@ -661,7 +677,7 @@ class AutoencoderKLWan(ModelBase):
                 taps.setdefault(f"down{i}", []).append(x.clone())
         x = self._mid(caches, enc.mid_block, x)
         t, h, w, _ = x.shape
-        ops.rms_act_cl(x, enc.norm_out.gamma32(), silu=True, out=caches.input(enc.conv_out, t, h, w))
+        self._rms_into(x, enc.norm_out.gamma32(), caches.input(enc.conv_out, t, h, w))
         return self._causal(caches, enc.conv_out, t, h, w)
 
     @torch.no_grad()
@@ -681,10 +697,18 @@ class AutoencoderKLWan(ModelBase):
         tl = 1 + (tf - 1) // 4
         xin = x if x.dtype in (torch.float32, torch.bfloat16) else x.float()
         dt = xin.dtype
-        params = torch.empty(b, 2 * cfg.z_dim, tl, hl, wl, dtype=dt, device=x.device)
+        rp = self.row_parallel if (self.row_parallel is not None and self.row_parallel.world > 1) else None
         taps = self.__dict__.get("_fino_taps")
+        hl_loc = hl
+        if rp is not None:  # this rank's band of the latent rows; gathered at the end
+            if taps is not None:
+                raise NotImplementedError("stage taps are an un-sharded debugging aid")
+            a, b_ = rp.rows(hl)
+            self._latent_rows = hl
+            hl_loc = b_ - a
+        params = torch.empty(b, 2 * cfg.z_dim, tl, hl_loc, wl, dtype=dt, device=x.device)
         for bi in range(b):
-            caches = _ConvCaches(x.device)
+            caches = _ConvCaches(x.device, halo=0 if rp is None else 1)
             x_all = ops.vae_to_cl(xin[bi], ps, _up8(cfg.in_channels))  # patchify (:1152-1153) + channels-last
             f0 = 0
             for i in range(tl):  # :1155-1166
@@ -694,6 +718,8 @@ class AutoencoderKLWan(ModelBase):
                 ops.vae_from_cl(y.contiguous(), params[bi, :, f0:f0 + y.shape[0]], 2 * cfg.z_dim, 1, clamp=False)
                 f0 += y.shape[0]
             assert f0 == tl
+        if rp is not None:
+            params = rp.gather_rows(params, hl, dim=3)
         dist = DiagonalGaussianDistribution(params)
         if not return_dict:
             return (dist,)

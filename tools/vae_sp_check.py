@@ -53,18 +53,20 @@ def main():
         ref = vae.decode(z, return_dict=False)[0]
         vae.enable_row_parallel()
         got = vae.decode(z, return_dict=False)[0]
-        # encode stays replicated while row-parallel decode is enabled (the pipeline encodes first, then decodes)
         clip = ref[:, :, : 1 + 4 * ((ref.shape[2] - 1) // 4)].contiguous()
-        enc_rp = vae.encode(clip).latent_dist.mode()
+        enc_rp = vae.encode(clip).latent_dist.parameters
         vae.disable_row_parallel()
-        enc = vae.encode(clip).latent_dist.mode()
-        assert torch.equal(enc, enc_rp), "encode changed under enable_row_parallel"
+        enc = vae.encode(clip).latent_dist.parameters
+        ediff = (enc_rp - enc).abs().max().reshape(1)
+        dist.all_reduce(ediff, op=dist.ReduceOp.MAX)
         diff = float((got - ref).abs().max())
         t = torch.tensor([diff], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         case = {"vae": name, "latent": [tl, h, w], "max_abs_diff_vs_unsharded": float(t.item()),
-                "equal": bool(t.item() == 0.0), "shape": list(got.shape)}
-        ok = ok and got.shape == ref.shape and case["max_abs_diff_vs_unsharded"] <= 1e-2
+                "equal": bool(t.item() == 0.0), "shape": list(got.shape),
+                "encode_max_abs_diff_vs_unsharded": float(ediff.item()), "encode_shape": list(enc_rp.shape)}
+        ok = ok and got.shape == ref.shape and enc_rp.shape == enc.shape and case["max_abs_diff_vs_unsharded"] <= 1e-2 \
+            and case["encode_max_abs_diff_vs_unsharded"] <= 1e-2
         res["cases"].append(case)
         del vae
         torch.cuda.empty_cache()
@@ -83,6 +85,18 @@ def main():
         res["full_704x1280x121"] = {"unsharded_ms": ms_1, "row_parallel_ms": ms_n, "speedup": ms_1 / ms_n,
                                     "max_abs_diff_vs_unsharded": float(diff.item()), "finite": bool(torch.isfinite(got).all())}
         ok = ok and float(diff.item()) <= 1e-2
+        del got, ref
+        x = torch.randn(1, 3, 121, 704, 1280, generator=g, device=dev).clamp_(-1, 1)
+        vae.encode(x[:, :, :5])
+        enc_n, ems_n = timed(lambda: vae.encode(x).latent_dist.parameters)
+        vae.disable_row_parallel()
+        vae.encode(x[:, :, :5])
+        enc_1, ems_1 = timed(lambda: vae.encode(x).latent_dist.parameters)
+        ediff = (enc_n - enc_1).abs().max().reshape(1)
+        dist.all_reduce(ediff, op=dist.ReduceOp.MAX)
+        res["full_704x1280x121_encode"] = {"unsharded_ms": ems_1, "row_parallel_ms": ems_n, "speedup": ems_1 / ems_n,
+                                           "max_abs_diff_vs_unsharded": float(ediff.item())}
+        ok = ok and float(ediff.item()) <= 1e-2
     res["ok"] = bool(ok)
     if rank == 0:
         print("VAE_SP " + json.dumps(res))
