@@ -46,7 +46,7 @@ def main():
 
         enable_sequence_parallel(tf)
         if not args.no_vae_parallel:
-            vae.enable_row_parallel()  # decode split by frame rows; the three encodes stay replicated
+            vae.enable_row_parallel()  # encodes and decode split by frame rows
     pipe = WanFrameINOPipeline(vae=vae, transformer=tf)
     inp = synth.make_pipeline_inputs(vcfg, synth.WAN22_5B["text_dim"], args.frames, args.height, args.width, n_id=1,
                                      text_len=512)
@@ -92,8 +92,7 @@ def main():
     res = {"workload": f"Wan FrameINO pipeline call, {args.height}x{args.width}x{args.frames}, {args.steps} steps x 2 "
                        f"CFG forwards, guidance 5.0, random-init Wan2.2-5B + Wan2.2 VAE, synthetic inputs",
            "n_gpus": world, "parallelism": "single GPU" if world == 1 else
-           f"DiT: ulysses x{world}; VAE decode: " + ("replicated" if args.no_vae_parallel else f"row bands x{world}")
-           + "; VAE encodes replicated", "total_ms": float(t.item()),
+           f"DiT: ulysses x{world}; VAE encode / decode: " + ("replicated" if args.no_vae_parallel else f"row bands x{world}"), "total_ms": float(t.item()),
            "stage_ms": {k: a.elapsed_time(b) for k, (a, b) in stages.items()},
            "video_shape": list(video.shape), "finite": bool(torch.isfinite(video).all()),
            "h2d_bytes": int(sum(v.numel() * v.element_size() for v in host.values() if isinstance(v, torch.Tensor))),

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Multi-GPU check of the row-parallel VAE decode (frameino_b200/vae.py RowParallel) against the un-sharded decode of the
-same model on the same latents — expected bit-identical — and its timing at config 2's canvas.
+"""Multi-GPU check of the row-parallel VAE decode and encode (frameino_b200/vae.py RowParallel) against the un-sharded
+ones of the same model on the same inputs — expected bit-identical — and their timing at config 2's canvas.
 
   python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/vae_sp_check.py [--full] [--out f.json]
 
