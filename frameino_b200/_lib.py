@@ -65,6 +65,7 @@ SIGNATURES = {
     "fino_peer_release": (_I, [_P]),
     "fino_peer_barrier": (_I, [_P, _I, _I, c_uint32, _P]),
     "fino_peer_status": (_I, [_P, _P, _P]),
+    "fino_halo_exchange": (_I, [_P, _I, _I, _L, _L, _P, _P, _P, c_uint32, _L, _I, _P]),
     "fino_qkv_norm_rope_scatter": (_I, [_P, _L, _L, _P, _P, _I, _I, _F, _P, _P, _P, _I, _I, _L, _L, _P]),
     "fino_qkv_ln_rope_scatter": (_I, [_P, _L, _L, _P, _P, _P, _P, _I, _I, _F, _P, _P, _L, _P, _I, _I, _L, _L, _P]),
     "fino_attention_fwd_scatter": (_I, [_P, _P, _P, _P, _I, _L, _I, _I, _L, _L, _I, _L, _L, _L, _L, _L, _L, _L, _L, _F,

@@ -46,6 +46,8 @@ int peer_import(const void* handle64, void** ptr);
 int peer_release(void* ptr);
 int peer_barrier(void* const* flag_ptrs, int rank, int world, uint32_t epoch, cudaStream_t stream);
 int peer_status(const void* own_flags, uint32_t* status8, cudaStream_t stream);
+int halo_exchange(void* frames, int t, int hl, int64_t row_bytes, int64_t frame_stride_bytes, void* up, void* down,
+                  void* own, uint32_t seq, int64_t slot_bytes, int rank, cudaStream_t stream);
 int qkv_norm_rope_scatter(const void* qkv, int64_t rows, int64_t row_stride, const void* wq, const void* wk,
                           int heads, int head_dim, float eps, const float* cos, const float* sin,
                           void* const* dst_ptrs, int world, int rank, int64_t rows_per_rank, int64_t dst_row_stride,
@@ -372,6 +374,12 @@ int fino_peer_barrier(void* const* flag_ptrs, int rank, int world, uint32_t epoc
 int fino_peer_status(const void* own_flags, uint32_t* status8, void* stream) {
   int d = ensure_device();
   return d ? d : fino::peer_status(own_flags, status8, (cudaStream_t)stream);
+}
+
+int fino_halo_exchange(void* frames, int t, int hl, int64_t row_bytes, int64_t frame_stride_bytes, void* up, void* down,
+                       void* own, uint32_t seq, int64_t slot_bytes, int rank, void* stream) {
+  FINO_ENTRY(fino::halo_exchange(frames, t, hl, row_bytes, frame_stride_bytes, up, down, own, seq, slot_bytes, rank,
+                                 (cudaStream_t)stream));
 }
 
 int fino_wan_pack_model_input(const float* latents, const float* condition, const float* mask,

@@ -157,6 +157,141 @@ int peer_status(const void* own_flags, uint32_t* status8, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// halo rows of a row-parallel convolution (VAE, frameino_b200/vae.py RowParallel), pushed through peer memory
+// ------------------------------------------------------------------------------------------------
+// Every rank owns a band of the frame rows; a 3x3 convolution's input frames [t, hl + 2, W, C] carry one halo row above
+// and below the band. One launch per convolution and rank: (1) PUSH the band's first row of every frame into the rank
+// above's mailbox ("from below" slot) and its last row into the rank below's ("from above" slot), (2) the last CTA to
+// finish raises the neighbours' flags to `seq`, (3) wait until both own flags reached `seq`, (4) PULL the two mailbox
+// slots into the halo rows. Mailbox (peer-mapped, zeroed): words 0 / 1 = flag from above / from below, word 2 = CTA
+// arrival counter, words 4 / 5 = time-out records; data at byte 256: slot (seq & 1, direction) of `slot_bytes` each.
+// Two slot parities suffice: a neighbour can run at most one exchange ahead (its exchange seq + 1 needs this rank's
+// push seq + 1, which is stream-ordered behind this rank's pull seq). All CTAs must be co-resident (they spin in (3)
+// while the last one signals in (2)): the grid is at most HALO_MAX_CTAS.
+constexpr int HALO_DATA_OFF = 256;
+constexpr int HALO_MAX_CTAS = 32;
+struct HaloParams {
+  char* frames;          // first frame of the chunk, halo row 0
+  int t, hl;             // frames, band rows
+  long long row_bytes, frame_stride;
+  char *up, *down, *own; // mailboxes of the rank above / below (null at the image border) and this rank's
+  uint32_t seq;
+  long long slot_bytes;
+  unsigned long long timeout_ns;
+  int rank;
+};
+
+__device__ __forceinline__ void halo_wait(const uint32_t* flag, uint32_t seq, const HaloParams& p, int which) {
+  uint32_t v;
+  unsigned long long t0 = 0;
+  unsigned spins = 0;
+  do {
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if ((int32_t)(v - seq) >= 0) break;
+    __nanosleep(32);
+    if ((++spins & 0xfffu) == 0 && p.timeout_ns != 0) {
+      const unsigned long long now = global_ns();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > p.timeout_ns) {
+        if (blockIdx.x == 0) {
+          printf("fino halo_exchange timeout: rank %d gave up waiting for the rank %s at exchange %u (saw %u)\n", p.rank,
+                 which ? "below" : "above", seq, v);
+          reinterpret_cast<uint32_t*>(p.own)[4 + which] = seq ? seq : 1u;
+        }
+        break;
+      }
+    }
+  } while (true);
+}
+
+__global__ void __launch_bounds__(256) halo_exchange_kernel(const __grid_constant__ HaloParams p) {
+  const long long cpr = p.row_bytes / 16, total = (long long)p.t * cpr;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  const int par = (int)(p.seq & 1u);
+  uint32_t* own_words = reinterpret_cast<uint32_t*>(p.own);
+  // (1) push
+  if (p.up != nullptr) {
+    int4* dst = reinterpret_cast<int4*>(p.up + HALO_DATA_OFF + (par * 2 + 1) * p.slot_bytes);
+    for (long long i = tid; i < total; i += nth) {
+      const long long f = i / cpr, c = i - f * cpr;
+      dst[i] = *reinterpret_cast<const int4*>(p.frames + f * p.frame_stride + p.row_bytes + c * 16);
+    }
+  }
+  if (p.down != nullptr) {
+    int4* dst = reinterpret_cast<int4*>(p.down + HALO_DATA_OFF + (par * 2 + 0) * p.slot_bytes);
+    for (long long i = tid; i < total; i += nth) {
+      const long long f = i / cpr, c = i - f * cpr;
+      dst[i] = *reinterpret_cast<const int4*>(p.frames + f * p.frame_stride + (long long)p.hl * p.row_bytes + c * 16);
+    }
+  }
+  // (2) last CTA signals
+  __threadfence_system();
+  __syncthreads();
+  __shared__ int is_last;
+  if (threadIdx.x == 0) is_last = (atomicAdd(own_words + 2, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last && threadIdx.x == 0) {
+    own_words[2] = 0u;
+    __threadfence_system();
+    if (p.up != nullptr)
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(reinterpret_cast<uint32_t*>(p.up) + 1), "r"(p.seq) : "memory");
+    if (p.down != nullptr)
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(reinterpret_cast<uint32_t*>(p.down) + 0), "r"(p.seq) : "memory");
+  }
+  // (3) wait for the neighbours' rows
+  if (threadIdx.x == 0) {
+    if (p.up != nullptr) halo_wait(own_words + 0, p.seq, p, 0);
+    if (p.down != nullptr) halo_wait(own_words + 1, p.seq, p, 1);
+    __threadfence_system();
+  }
+  __syncthreads();
+  // (4) pull (L2 is the coherence point of the peer's stores: bypass L1)
+  if (p.up != nullptr) {
+    const int4* src = reinterpret_cast<const int4*>(p.own + HALO_DATA_OFF + (par * 2 + 0) * p.slot_bytes);
+    for (long long i = tid; i < total; i += nth) {
+      const long long f = i / cpr, c = i - f * cpr;
+      *reinterpret_cast<int4*>(p.frames + f * p.frame_stride + c * 16) = __ldcg(src + i);
+    }
+  }
+  if (p.down != nullptr) {
+    const int4* src = reinterpret_cast<const int4*>(p.own + HALO_DATA_OFF + (par * 2 + 1) * p.slot_bytes);
+    for (long long i = tid; i < total; i += nth) {
+      const long long f = i / cpr, c = i - f * cpr;
+      *reinterpret_cast<int4*>(p.frames + f * p.frame_stride + (long long)(p.hl + 1) * p.row_bytes + c * 16) = __ldcg(src + i);
+    }
+  }
+}
+
+int halo_exchange(void* frames, int t, int hl, int64_t row_bytes, int64_t frame_stride_bytes, void* up, void* down,
+                  void* own, uint32_t seq, int64_t slot_bytes, int rank, cudaStream_t stream) {
+  FINO_CHECK_ARG(frames != nullptr && own != nullptr && t > 0 && hl > 0, "halo_exchange: bad arguments");
+  FINO_CHECK_ARG(row_bytes > 0 && row_bytes % 16 == 0 && frame_stride_bytes % 16 == 0 &&
+                 frame_stride_bytes >= (int64_t)(hl + 2) * row_bytes, "halo_exchange: rows must be multiples of 16 bytes "
+                 "and frames hold hl + 2 rows");
+  FINO_CHECK_ARG(((reinterpret_cast<uintptr_t>(frames) | reinterpret_cast<uintptr_t>(own) | reinterpret_cast<uintptr_t>(up) |
+                   reinterpret_cast<uintptr_t>(down)) & 15) == 0, "halo_exchange: pointers must be 16-byte aligned");
+  FINO_CHECK_ARG(slot_bytes % 16 == 0 && (int64_t)t * row_bytes <= slot_bytes,
+                 "halo_exchange: %lld bytes of rows do not fit a %lld-byte mailbox slot", (long long)t * row_bytes,
+                 (long long)slot_bytes);
+  if (up == nullptr && down == nullptr) return FINO_OK;
+  HaloParams p;
+  p.frames = reinterpret_cast<char*>(frames);
+  p.t = t, p.hl = hl;
+  p.row_bytes = row_bytes, p.frame_stride = frame_stride_bytes;
+  p.up = reinterpret_cast<char*>(up), p.down = reinterpret_cast<char*>(down), p.own = reinterpret_cast<char*>(own);
+  p.seq = seq;
+  p.slot_bytes = slot_bytes;
+  p.timeout_ns = peer_timeout_ns();
+  p.rank = rank;
+  const long long chunks = (long long)t * (row_bytes / 16);
+  int grid = (int)((chunks + 256 * 4 - 1) / (256 * 4));
+  grid = grid < 1 ? 1 : (grid > HALO_MAX_CTAS ? HALO_MAX_CTAS : grid);
+  halo_exchange_kernel<<<grid, 256, 0, stream>>>(p);
+  FINO_CHECK_CUDA(cudaGetLastError());
+  return FINO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // q/k RMSNorm-across-heads + RoPE, with the stores scattered to the ranks that own each head group
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum_f(float v) {

@@ -674,6 +674,21 @@ def peer_status(own_flags_ptr: int):
     return list(out)
 
 
+HALO_DATA_OFF = 256  # mailbox header bytes (fino_halo_exchange)
+
+
+def halo_exchange(frames: torch.Tensor, own: int, up: Optional[int], down: Optional[int], seq: int, slot_bytes: int,
+                  rank: int) -> None:
+    """Row-parallel convolution halo rows through peer memory. frames: bf16 [t, hl + 2, W, C] with contiguous frames
+    interior (rows 1..hl written); own / up / down: mailbox device pointers (up / down None at the image border)."""
+    assert frames.dtype == torch.bfloat16 and frames.dim() == 4 and frames[0].is_contiguous()
+    lib, stream = _prep(frames)
+    t, hp, w, c = frames.shape
+    fs = frames.stride(0) if t > 1 else hp * w * c
+    _lib.check(lib.fino_halo_exchange(frames.data_ptr(), t, hp - 2, w * c * 2, fs * 2, up, down, own,
+                                      seq & 0xFFFFFFFF, slot_bytes, rank, stream), "fino_halo_exchange")
+
+
 def qkv_norm_rope_scatter(qkv: torch.Tensor, wq: Optional[torch.Tensor], wk: Optional[torch.Tensor], heads: int,
                           eps: float, cos: Optional[torch.Tensor], sin: Optional[torch.Tensor], dst_ptrs, world: int,
                           rank: int, rows_per_rank: int, dst_row_stride: int) -> None:

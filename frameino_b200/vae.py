@@ -186,13 +186,17 @@ class RowParallel:
     """Every rank decodes a horizontal band of the frames (latent rows ``rows(h)``, the same band scaled by 2 after each
     up-sampling stage). Everything in the decoder is pixel-local except (i) the 3x3 spatial taps of the convolutions —
     each convolution's input buffer carries one halo row above and below the band, refreshed from the neighbouring
-    ranks right after the producer has written the band (``exchange``: one small all-gather of the two edge rows per
-    convolution, NCCL over NVLink) — and (ii) the mid-block attention, whose keys / values are the whole frame
+    ranks right after the producer has written the band (``exchange``: ONE launch per convolution that pushes the two
+    edge rows into the neighbours' peer-mapped mailboxes over NVLink, raises their flags and pulls its own two halo
+    rows, ``fino_halo_exchange``; an all-gather of the edge rows where peer memory is not available) — and (ii) the
+    mid-block attention, whose keys / values are the whole frame
     (``gather_rows`` of the 1024-channel latent-resolution activations, 7 MB per frame at 44 x 80). Bands at the image
     border keep their outer halo row zero: that IS the convolution's zero padding. The arithmetic per output pixel is
     the un-sharded one, in the same order — the result is bit-identical."""
 
-    def __init__(self, group=None):
+    SLOT_BYTES = 4 << 20  # one mailbox slot: t x W x C bf16 of one row (1.3 MB at 704x1280x121's widest stage)
+
+    def __init__(self, group=None, peer: bool = True, prims=ops):
         import torch.distributed as dist
 
         if not dist.is_initialized():
@@ -200,6 +204,50 @@ class RowParallel:
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        self.prims = prims
+        self.seq = 0
+        self.own = self.up = self.down = None
+        # halo rows travel through peer memory (one fused launch per convolution, fino_halo_exchange) when every rank
+        # is a CUDA device of this node; otherwise — the gloo host-logic tests — through an all-gather of the edge rows
+        self.peer = bool(peer and self.world > 1 and torch.cuda.is_available() and dist.get_backend(group) == "nccl")
+        if self.peer:
+            self._open_mailboxes()
+
+    def _open_mailboxes(self) -> None:
+        import torch.distributed as dist
+
+        ops_ = self.prims
+        self.own = ops_.peer_alloc(ops_.HALO_DATA_OFF + 4 * self.SLOT_BYTES)
+        handles = [None] * self.world
+        dist.all_gather_object(handles, ops_.peer_export(self.own), group=self.group)
+        self._imported = []
+        if self.rank > 0:
+            self.up = ops_.peer_import(handles[self.rank - 1])
+            self._imported.append(self.up)
+        if self.rank < self.world - 1:
+            self.down = ops_.peer_import(handles[self.rank + 1])
+            self._imported.append(self.down)
+        dist.barrier(group=self.group)  # every mailbox is mapped before anyone pushes into one
+
+    def close(self) -> None:
+        """Unmaps the neighbours' mailboxes and frees this rank's (collective: every rank calls it)."""
+        import torch.distributed as dist
+
+        if self.own is None:
+            return
+        torch.cuda.synchronize()
+        words = self.prims.tensor_from_ptr(self.own, (8,), torch.int32).cpu().tolist()
+        dist.barrier(group=self.group)
+        for p in self._imported:
+            self.prims.peer_release(p)
+        self._imported = []
+        dist.barrier(group=self.group)
+        self.prims.peer_free(self.own)
+        self.own = self.up = self.down = None
+        self.peer = False
+        if words[4] or words[5]:
+            raise RuntimeError(f"rank {self.rank}: a halo exchange timed out (exchange {words[4] or words[5]}); results "
+                               f"after that are invalid")
 
     @staticmethod
     def split(h: int, world: int) -> List[Tuple[int, int]]:
@@ -226,6 +274,10 @@ class RowParallel:
             return
         t, hp, w, c = frames.shape
         hl = hp - 2
+        if self.peer and frames.is_cuda and t * w * c * 2 <= self.SLOT_BYTES:
+            self.seq += 1
+            self.prims.halo_exchange(frames, self.own, self.up, self.down, self.seq, self.SLOT_BYTES, self.rank)
+            return
         edge = torch.stack((frames[:, 1], frames[:, hl]))  # [2, t, W, C]: my first and last rows
         flat = torch.empty((self.world * 2,) + tuple(edge.shape[1:]), dtype=edge.dtype, device=edge.device)
         dist.all_gather_into_tensor(flat, edge, group=self.group)
@@ -401,14 +453,25 @@ class AutoencoderKLWan(ModelBase):
     def disable_tiling(self):
         self.use_tiling = False
 
-    def enable_row_parallel(self, group=None) -> "RowParallel":
+    def enable_row_parallel(self, group=None, peer: bool = True) -> "RowParallel":
         """``decode`` and ``encode`` split the frame rows over the ranks of ``group``: every rank calls them with the
         same input and gets the whole result, bit-identical to the un-sharded one."""
-        self.row_parallel = RowParallel(group)
+        self.disable_row_parallel()
+        self.row_parallel = RowParallel(group, peer=peer)
         return self.row_parallel
 
     def disable_row_parallel(self) -> None:
+        if self.row_parallel is not None:
+            self.row_parallel.close()
         self.row_parallel = None
+
+    def _row_parallel_for(self, latent_rows: int) -> Optional["RowParallel"]:
+        """The row split to use for a canvas, or None: one rank, or fewer latent rows than ranks (a band needs at least
+        one row) — every rank then runs the whole frames, which is the same result."""
+        rp = self.row_parallel
+        if rp is None or rp.world == 1 or latent_rows < rp.world:
+            return None
+        return rp
 
     def enable_slicing(self):
         self.use_slicing = True  # batch elements are processed one at a time anyway
@@ -630,7 +693,7 @@ class AutoencoderKLWan(ModelBase):
         ho, wo = h * (2 ** n_up) * ps, w * (2 ** n_up) * ps
         t_total = 1 + (tl - 1) * (2 ** n_tup)
         dt = output_dtype or (z.dtype if z.dtype in (torch.float32, torch.bfloat16) else torch.float32)
-        rp = self.row_parallel if (self.row_parallel is not None and self.row_parallel.world > 1) else None
+        rp = self._row_parallel_for(h)
         taps = self.__dict__.get("_fino_taps")
         if rp is not None:  # this rank's band of every frame; gathered at the end
             if taps is not None:
@@ -697,7 +760,7 @@ class AutoencoderKLWan(ModelBase):
         tl = 1 + (tf - 1) // 4
         xin = x if x.dtype in (torch.float32, torch.bfloat16) else x.float()
         dt = xin.dtype
-        rp = self.row_parallel if (self.row_parallel is not None and self.row_parallel.world > 1) else None
+        rp = self._row_parallel_for(hl)
         taps = self.__dict__.get("_fino_taps")
         hl_loc = hl
         if rp is not None:  # this rank's band of the latent rows; gathered at the end

@@ -204,6 +204,16 @@ int fino_peer_barrier(void* const* flag_ptrs, int rank, int world, uint32_t epoc
  * own_flags = this rank's flag array. Synchronises `stream`. */
 int fino_peer_status(const void* own_flags, uint32_t* status8, void* stream);
 
+/* Halo rows of a row-parallel 3x3 convolution (Wan VAE split by frame rows across GPUs; no reference counterpart — the
+ * reference VAE, architecture/autoencoder_kl_wan.py, is single-GPU). frames: bf16 [t, hl + 2, W, C] (frame stride
+ * frame_stride_bytes, rows of row_bytes = W*C*2), rows 1..hl written. One launch: rows 1 / hl of every frame are pushed
+ * into the mailbox of the rank above / below (`up` / `down`: peer-mapped, NULL at the image border), flags raised to
+ * `seq`, then rows 0 / hl + 1 are filled from this rank's mailbox `own` once the neighbours' pushes `seq` arrived.
+ * Mailbox = fino_peer_alloc(256 + 4 * slot_bytes), zeroed; `seq` starts at 1 and increases by one per call, the same
+ * sequence on every rank. Waits give up after FINO_PEER_TIMEOUT_S like fino_peer_barrier (words 4 / 5 of `own`). */
+int fino_halo_exchange(void* frames, int t, int hl, int64_t row_bytes, int64_t frame_stride_bytes, void* up, void* down,
+                       void* own, uint32_t seq, int64_t slot_bytes, int rank, void* stream);
+
 /* First all-to-all fused into the q/k prologue: RMSNorm across heads (+ Wan RoPE when cos/sin != NULL; transformer_wan.py
  * :64-90) of the local fused projection rows qkv[rows, row_stride] (q | k | v, heads*head_dim columns each), stored
  * straight into the owning ranks' buffers: head group g = columns [g*inner, (g+1)*inner), inner = heads*head_dim/world,

@@ -138,6 +138,10 @@ def test_output_types_callbacks_and_generators(setup):
     # CFG without a negative prompt and without a text encoder: loud
     with pytest.raises(NotImplementedError, match="UMT5"):
         _call(pipe, inp, negative_prompt_embeds=None)
+    # no ID image: nothing appended to the sequence
+    e = _call(pipe, inp, ID_tensor=None, output_type="latent").frames
+    assert e.shape == (1, 16, 3, 4, 6) and torch.isfinite(e).all()
+    assert torch.equal(e, _call(pipe, inp, ID_tensor=None, output_type="latent", fused=False).frames)
     # num_frames is rounded down to 1 + 4k like the reference (:707-711)
     d = _call(pipe, inp, num_frames=F + 2, output_type="latent").frames
     assert d.shape[2] == 3

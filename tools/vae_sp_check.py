@@ -70,6 +70,15 @@ def main():
         res["cases"].append(case)
         del vae
         torch.cuda.empty_cache()
+    # fewer latent rows than ranks: falls back to whole frames on every rank (same result)
+    if world > 2:
+        vae = synth.build_vae_on_device(synth.VAE_TINY, seed=1, device=dev)
+        z = torch.randn(1, 16, 2, 2, 8, generator=torch.Generator(device=dev).manual_seed(5), device=dev)
+        ref = vae.decode(z, return_dict=False)[0]
+        vae.enable_row_parallel()
+        ok = ok and torch.equal(vae.decode(z, return_dict=False)[0], ref)
+        res["fallback_fewer_rows_than_ranks"] = bool(ok)
+        del vae
     if args.full:
         cfg = synth.WAN22_VAE
         vae = synth.build_vae_on_device(cfg, seed=0, device=dev)
