@@ -10,8 +10,11 @@ Only ``tests/`` may import this file. What is NOT restated because it is not und
   * ``VideoProcessor`` (upstream diffusers, recalled): ``preprocess`` of a tensor in [0, 1] is ``2 x - 1``,
     ``postprocess_video`` is ``(x / 2 + 0.5).clamp(0, 1)`` per frame, ``"pt"`` -> [B, F, C, H, W], ``"np"`` -> [B, F, H, W, C].
 
-Parity is "unpinned" for those three pieces (no reference output exists here); every line taken from the pipeline file
-itself is restated with its cast points and cited.
+Pinned: tests/test_oracle_golden.py compares ``prepare_latents`` and ``generate`` with outputs of the reference's OWN
+pipeline file executed on CPU around the reference transformer and VAE (tests/golden/pipeline_golden.pt, written by
+``make_golden.py pipeline`` through the diffusers shim): 1e-5 / 1e-4. The three upstream-only pieces above are the shim's
+restatements on the reference side of that comparison too, so for THEM parity stays "unpinned"; every line taken from
+the pipeline file itself is restated with its cast points, cited, and pinned.
 """
 from __future__ import annotations
 

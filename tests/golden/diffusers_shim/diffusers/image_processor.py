@@ -1,2 +1,5 @@
 class IPAdapterMaskProcessor:
     pass
+
+
+PipelineImageInput = object  # a typing alias upstream

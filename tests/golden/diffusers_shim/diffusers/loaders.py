@@ -4,3 +4,7 @@ class FromOriginalModelMixin:
 
 class PeftAdapterMixin:
     pass
+
+
+class WanLoraLoaderMixin:
+    pass

@@ -36,3 +36,14 @@ def is_torch_version(op, version):
 
     ops = {">": operator.gt, ">=": operator.ge, "<": operator.lt, "<=": operator.le, "==": operator.eq}
     return ops[op](V.parse(V.parse(torch.__version__).base_version), V.parse(version))
+
+
+def is_ftfy_available():
+    return False
+
+
+def replace_example_docstring(example_docstring):
+    def wrap(fn):
+        return fn
+
+    return wrap

@@ -222,8 +222,56 @@ def vae_golden():
     print("wrote vae_golden.pt:", {k: tuple(v.shape) for k, v in out.items()})
 
 
+def pipeline_golden():
+    """The reference pipeline file itself — ``WanImageToVideoPipeline.prepare_latents`` and ``__call__``
+    (pipelines/pipeline_wan_i2v_motion_FrameINO.py, Wan2.2 ``expand_timesteps`` branch) — executed on CPU in fp32 around
+    the reference transformer and the reference VAE (tiny configs), with pre-computed prompt embeddings and the shim's
+    flow-match Euler scheduler (shift 5). Pixel-space inputs come from synth.make_pipeline_inputs, so the fixture holds
+    only outputs: the five prepare_latents tensors, the final latents and the decoded video."""
+    os.chdir(REF)
+    from architecture.autoencoder_kl_wan import AutoencoderKLWan
+    from architecture.transformer_wan import WanTransformer3DModel
+    from diffusers.schedulers import FlowMatchEulerDiscreteScheduler
+    from pipelines.pipeline_wan_i2v_motion_FrameINO import WanImageToVideoPipeline
+
+    vcfg = synth.with_latent_stats(synth.VAE_TINY)
+    torch.manual_seed(0)
+    vae = AutoencoderKLWan(**vcfg).eval()
+    vae.load_state_dict(synth.make_vae_state_dict(synth.VAE_TINY, seed=1), strict=True)
+    tf = WanTransformer3DModel(**synth.WAN_TINY).eval()
+    tf.load_state_dict(synth.make_wan_state_dict(synth.WAN_TINY, seed=0), strict=True)
+    pipe = WanImageToVideoPipeline(tokenizer=None, text_encoder=None, vae=vae,
+                                   scheduler=FlowMatchEulerDiscreteScheduler(shift=5.0), transformer=tf,
+                                   expand_timesteps=True)
+    h, w, f = 64, 96, 9
+    inp = synth.make_pipeline_inputs(vcfg, 64, num_frames=f, height=h, width=w, n_id=1)
+    out = {}
+    with torch.no_grad():
+        image = pipe.video_processor.preprocess(inp["image"], height=h, width=w).to(torch.float32)
+        names = ["latents", "latent_condition", "traj_latents", "ID_latent_condition", "first_frame_mask"]
+        got = pipe.prepare_latents(image, inp["traj_tensor"], inp["ID_tensor"], 1, vcfg["z_dim"], h, w, f,
+                                   torch.float32, torch.device("cpu"), None, inp["latents"].clone(), None)
+        for n, t in zip(names, got):
+            out["prepare." + n] = t.clone()
+        common = dict(image=inp["image"], traj_tensor=inp["traj_tensor"], prompt_embeds=inp["prompt_embeds"],
+                      negative_prompt_embeds=inp["negative_prompt_embeds"], height=h, width=w, num_frames=f,
+                      num_inference_steps=4, guidance_scale=5.0)
+        out["call.latents"] = pipe(ID_tensor=inp["ID_tensor"].clone(), latents=inp["latents"].clone(),
+                                   output_type="latent", **common).frames.clone()
+        out["call.video"] = pipe(ID_tensor=inp["ID_tensor"].clone(), latents=inp["latents"].clone(), output_type="pt",
+                                 **common).frames.clone()
+        # no ID frame (the `ID_tensor.shape[2] == 0` branch, :489/:520) and no guidance (a single forward per step)
+        empty = inp["ID_tensor"][:, :, :0]
+        out["call_noid_nocfg.latents"] = pipe(ID_tensor=empty, latents=inp["latents"].clone(), output_type="latent",
+                                              **{**common, "guidance_scale": 1.0}).frames.clone()
+    torch.save(out, os.path.join(HERE, "pipeline_golden.pt"))
+    print("wrote pipeline_golden.pt:", {k: tuple(v.shape) for k, v in out.items()})
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["wan", "cog", "bf16", "vae"]
+    which = sys.argv[1:] or ["wan", "cog", "bf16", "vae", "pipeline"]
+    if "pipeline" in which:
+        pipeline_golden()
     if "vae" in which:
         vae_golden()
     if "bf16" in which:

@@ -178,3 +178,40 @@ def test_vae_oracle_matches_reference_chunked_execution(golden_dir):
     assert torch.allclose(dec, g["decode.sample"], rtol=0, atol=1e-5), float((dec - g["decode.sample"]).abs().max())
     assert torch.allclose(dec1, g["decode1.sample"], rtol=0, atol=1e-5)
     assert torch.allclose(enc, g["encode.parameters"], rtol=0, atol=1e-5), float((enc - g["encode.parameters"]).abs().max())
+
+
+def test_pipeline_oracle_matches_reference_pipeline_file(golden_dir):
+    """oracle/pipeline_oracle.py against outputs of the reference's OWN pipeline file executed on CPU
+    (pipelines/pipeline_wan_i2v_motion_FrameINO.py ``prepare_latents`` + ``__call__`` around the reference transformer
+    and VAE, tiny configs; make_golden.py pipeline): the five prepare_latents tensors, the final latents after 4 steps
+    with guidance 5 and one ID frame, the decoded video, and the no-ID / no-guidance branch."""
+    import os
+
+    from oracle import pipeline_oracle, wan_oracle
+
+    gold = torch.load(os.path.join(golden_dir, "pipeline_golden.pt"))
+    vcfg = synth.with_latent_stats(synth.VAE_TINY)
+    vsd = synth.make_vae_state_dict(synth.VAE_TINY, seed=1)
+    wcfg = wan_oracle.WanConfig(**synth.WAN_TINY)
+    wsd = synth.make_wan_state_dict(synth.WAN_TINY, seed=0)
+    h, w, f = 64, 96, 9
+    inp = synth.make_pipeline_inputs(vcfg, 64, num_frames=f, height=h, width=w, n_id=1)
+    got = pipeline_oracle.prepare_latents(vsd, vcfg, inp["image"], inp["traj_tensor"], inp["ID_tensor"], 1, h, w, f,
+                                          inp["latents"])
+    names = ["latents", "latent_condition", "traj_latents", "ID_latent_condition", "first_frame_mask"]
+    for n, t in zip(names, got):
+        ref = gold["prepare." + n]
+        assert t.shape == ref.shape and t.dtype == ref.dtype, n
+        assert float((t - ref).abs().max()) <= 1e-5, (n, float((t - ref).abs().max()))
+    args = (wsd, wcfg, vsd, vcfg, inp["image"], inp["traj_tensor"])
+    kw = dict(height=h, width=w, num_frames=f, num_inference_steps=4, shift=5.0, latents=inp["latents"])
+    lat = pipeline_oracle.generate(*args, inp["ID_tensor"], inp["prompt_embeds"], inp["negative_prompt_embeds"],
+                                   guidance_scale=5.0, output_type="latent", **kw)
+    assert float((lat - gold["call.latents"]).abs().max()) <= 1e-4, float((lat - gold["call.latents"]).abs().max())
+    video = pipeline_oracle.generate(*args, inp["ID_tensor"], inp["prompt_embeds"], inp["negative_prompt_embeds"],
+                                     guidance_scale=5.0, output_type="pt", **kw)
+    assert video.shape == gold["call.video"].shape
+    assert float((video - gold["call.video"]).abs().max()) <= 1e-4
+    lat1 = pipeline_oracle.generate(*args, None, inp["prompt_embeds"], None, guidance_scale=1.0, output_type="latent",
+                                    **kw)
+    assert float((lat1 - gold["call_noid_nocfg.latents"]).abs().max()) <= 1e-4
