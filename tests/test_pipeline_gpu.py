@@ -97,6 +97,26 @@ def test_pipeline_end_to_end_vs_oracle(setup):
     assert cosine(video.float() - 0.5, want - 0.5) >= 0.99
 
 
+def test_pipeline_vs_the_reference_pipeline_files_own_output(setup, golden_dir):
+    """The native call against tests/golden/pipeline_golden.pt — outputs of the reference's own pipeline file executed
+    on CPU in fp32 around the reference transformer and VAE (make_golden.py pipeline)."""
+    import os
+
+    pipe, inp, *_ = setup
+    gold = torch.load(os.path.join(golden_dir, "pipeline_golden.pt"))
+    got = pipe.prepare_latents(inp["image"], inp["traj_tensor"], inp["ID_tensor"], 1, 16, H, W, F, torch.float32,
+                               torch.device("cuda"), None, inp["latents"])
+    for n, g in zip(["latents", "latent_condition", "traj_latents", "ID_latent_condition", "first_frame_mask"], got):
+        assert rel_err(g, gold["prepare." + n]) <= TOL and cosine(g, gold["prepare." + n]) >= COS, n
+    lat = _call(pipe, inp, output_type="latent").frames
+    assert cosine(lat, gold["call.latents"]) >= COS, cosine(lat, gold["call.latents"])
+    video = _call(pipe, inp).frames
+    assert float((video.float().cpu() - gold["call.video"]).abs().mean()) <= 2e-2
+    lat1 = _call(pipe, inp, ID_tensor=inp["ID_tensor"][:, :, :0], guidance_scale=1.0, negative_prompt_embeds=None,
+                 output_type="latent").frames
+    assert cosine(lat1, gold["call_noid_nocfg.latents"]) >= COS
+
+
 def test_fused_and_plain_loop_agree_bit_for_bit(setup):
     pipe, inp, *_ = setup
     a = _call(pipe, inp, output_type="latent").frames
