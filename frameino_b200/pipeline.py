@@ -23,10 +23,15 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Any, Callable, Dict, List, Optional, Union
 
+import logging
+
 import torch
 
 from .modules import ConfigDict
 from .sampling import wan_frameino_denoise, wan_frameino_denoise_fused
+
+
+logger = logging.getLogger(__name__)
 
 
 @dataclass
@@ -318,6 +323,8 @@ class WanFrameINOPipeline:
         num_frames = max(num_frames, 1)
         self._guidance_scale = guidance_scale
         self._attention_kwargs = attention_kwargs
+        if attention_kwargs is not None and attention_kwargs.get("scale", None) is not None:  # transformer_wan.py:463-476
+            logger.warning("Passing `scale` via `attention_kwargs` when not using the PEFT backend is ineffective.")
         self._current_timestep = None
         self._interrupt = False
         device = self._execution_device
