@@ -416,7 +416,64 @@ def run_secondary(args, world, rank, dev, wan_model, barrier):
         except Exception as ex:
             out["wan_vae_704x1280x121"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
         torch.cuda.empty_cache()
+    else:
+        try:
+            out["wan_vae_704x1280x121_row_parallel"] = run_vae_rows_secondary(dev, world, barrier)
+        except Exception as ex:
+            out["wan_vae_704x1280x121_row_parallel"] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+        torch.cuda.empty_cache()
     return out
+
+
+def run_vae_rows_secondary(dev, world, barrier):
+    """N > 1: the Wan2.2 VAE split by frame rows over the ranks (frameino_b200/vae.py RowParallel; halo rows through peer
+    mailboxes) at config 2's canvas: decode and encode, sharded vs the un-sharded run of the same model on the same
+    inputs (expected bit-identical), device times as the max over ranks. Same sequence as tools/vae_sp_check.py --full."""
+    import torch
+    import torch.distributed as dist
+
+    from frameino_b200 import synth
+
+    vae = synth.build_vae_on_device(synth.WAN22_VAE, seed=0, device=dev)
+    g = torch.Generator(device=dev).manual_seed(3)
+    z = torch.randn(1, 48, 31, 44, 80, generator=g, device=dev)
+
+    def timed(fn):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        y = fn()
+        e.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([s.elapsed_time(e)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return y, float(t.item())
+
+    def max_diff(a, b):
+        d = (a - b).abs().max().reshape(1).float()
+        dist.all_reduce(d, op=dist.ReduceOp.MAX)
+        return float(d.item())
+
+    vae.decode(z[:, :, :2], return_dict=False)
+    ref, dec_1 = timed(lambda: vae.decode(z, return_dict=False)[0])
+    vae.enable_row_parallel()
+    vae.decode(z[:, :, :2], return_dict=False)
+    got, dec_n = timed(lambda: vae.decode(z, return_dict=False)[0])
+    dec_diff = max_diff(got, ref)
+    del got, ref
+    x = torch.randn(1, 3, 121, 704, 1280, generator=g, device=dev).clamp_(-1, 1)
+    vae.encode(x[:, :, :5])
+    enc_rp, enc_n = timed(lambda: vae.encode(x).latent_dist.parameters)
+    vae.disable_row_parallel()
+    vae.encode(x[:, :, :5])
+    enc, enc_1 = timed(lambda: vae.encode(x).latent_dist.parameters)
+    enc_diff = max_diff(enc_rp, enc)
+    return {"config": {"workload": f"Wan2.2-TI2V-5B VAE (random init), 704x1280x121 <-> latent 31x44x80x48, B=1, frame rows "
+                                   f"split over {world} ranks (halo rows through peer memory), inputs resident in HBM"},
+            "unit": "ms", "n_gpus": world, "decode_ms": dec_n, "decode_unsharded_ms": dec_1, "encode_ms": enc_n,
+            "encode_unsharded_ms": enc_1,
+            "parity_sharded_vs_unsharded": {"decode_max_abs_diff": dec_diff, "encode_max_abs_diff": enc_diff,
+                                            "pass": bool(dec_diff == 0.0 and enc_diff == 0.0)}}
 
 
 def run_vae_secondary(dev):
@@ -678,7 +735,7 @@ def main():
     ap.add_argument("--width", type=int, default=1280, help="canvas width in pixels (multiple of 32)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle leg (cpu_baseline + parity)")
     ap.add_argument("--no-secondary", action="store_true",
-                    help="skip the secondary workloads (config 3 CogVideoX B=2; at N=8 config 5, 39936 tokens)")
+                    help="skip the secondary workloads (config 3 CogVideoX B=2; the Wan VAE; at N=8 config 5, 39936 tokens)")
     ap.add_argument("--cog-sp", action="store_true", help="(default now; kept for old command lines)")
     ap.add_argument("--no-cog-sp", action="store_true", help="N > 1: skip the sequence-parallel CogVideoX secondary")
     ap.add_argument("--cog-sp-mode", default="peer", choices=["peer", "nccl"], help="N > 1: exchange of the CogVideoX secondary")
