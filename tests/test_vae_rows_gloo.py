@@ -92,3 +92,19 @@ def test_row_split():
     assert RowParallel.split(4, 4) == [(0, 1), (1, 2), (2, 3), (3, 4)]
     with pytest.raises(ValueError):
         RowParallel.split(3, 4)
+
+
+def test_row_parallel_falls_back_when_the_canvas_has_fewer_rows_than_ranks():
+    from types import SimpleNamespace
+
+    from frameino_b200 import synth
+    from frameino_b200.vae import AutoencoderKLWan
+
+    vae = AutoencoderKLWan(**synth.VAE_TINY)
+    assert vae._row_parallel_for(44) is None  # not enabled
+    vae.row_parallel = SimpleNamespace(world=8)
+    assert vae._row_parallel_for(44) is vae.row_parallel
+    assert vae._row_parallel_for(8) is vae.row_parallel
+    assert vae._row_parallel_for(7) is None  # a band needs at least one latent row: whole frames on every rank
+    vae.row_parallel = SimpleNamespace(world=1)
+    assert vae._row_parallel_for(44) is None
