@@ -191,3 +191,22 @@ def test_pipeline_text_encoder_hook_and_scheduler_shift():
     assert calls == [(("a", "b"), 77), (("", ""), 77)]  # the empty negative prompt of app.py:707
     with pytest.raises(NotImplementedError, match="shift"):
         WanFrameINOPipeline(vae=base.vae, transformer=base.transformer, scheduler=object())
+
+
+def test_prepare_latents_argument_errors_come_before_any_device_work():
+    """pipeline :419-424 (generator list length) and the shape the call needs; Wan2.1 inputs raise."""
+    pipe = _cpu_pipe()
+    img = torch.zeros(1, 3, 64, 64)
+    traj = torch.zeros(5, 3, 64, 64)
+    gens = [torch.Generator().manual_seed(i) for i in range(3)]
+    with pytest.raises(ValueError, match="list of generators of length 3"):
+        pipe.prepare_latents(img, traj, None, 2, 16, 64, 64, 5, torch.float32, torch.device("cpu"), gens, None)
+    with pytest.raises(ValueError, match="latents have shape"):
+        pipe.prepare_latents(img, traj, None, 1, 16, 64, 64, 5, torch.float32, torch.device("cpu"), None,
+                             torch.zeros(1, 16, 3, 4, 4))
+    with pytest.raises(NotImplementedError, match="last_image"):
+        pipe.prepare_latents(img, traj, None, 1, 16, 64, 64, 5, torch.float32, torch.device("cpu"), None, None, img)
+    # the VAE itself refuses CPU tensors (no CPU path), after the argument checks passed
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        pipe.prepare_latents(img, traj, None, 1, 16, 64, 64, 5, torch.float32, torch.device("cpu"), None,
+                             torch.zeros(1, 16, 2, 4, 4))
